@@ -1,0 +1,179 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map construction (cached), tile-shape selection, launch.
+#include "gemm.h"
+
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_tc.cuh"
+
+namespace echo {
+
+// ------------------------------------------------------------------ driver entry point for tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  uint64_t ptr, d0, d1, d2, s1, s2;
+  uint32_t b0, b1, rank, swz;
+  bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+// bf16 tensor, dim0 contiguous. rank 2: (d0, d1) ; rank 3: (d0, d1, d2). Strides in BYTES for dims >= 1.
+static bool get_tensor_map(CUtensorMap* out, const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2,
+                           uint64_t s1, uint64_t s2, uint32_t box0, uint32_t box1, int row_bytes) {
+  MapKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.ptr = (uint64_t)ptr; key.d0 = d0; key.d1 = d1; key.d2 = d2; key.s1 = s1; key.s2 = s2;
+  key.b0 = box0; key.b1 = box1; key.rank = rank; key.swz = row_bytes;
+  {
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return true; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                             : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  {
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    if (g_maps.size() > 65536) g_maps.clear();
+    g_maps[key] = m;
+  }
+  *out = m;
+  return true;
+}
+
+static int g_num_sms = 0;
+int gemm_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int BK, int ATOMS, int EPI>
+static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+  static bool configured = false;
+  constexpr int SMEM = gemm_smem_bytes(BN, BK, ATOMS);
+  auto kern = gemm_tc_kernel<BN, BK, ATOMS, EPI>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.batches * ((p.N + BN - 1) / BN);
+  const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
+  kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+static int pick_bn(const GemmCall& c) {
+  const GemmParams& p = c.p;
+  if (p.epi != EPI_GENERIC) return 256;
+  if (c.bn) return c.bn;
+  if (p.N % 64 != 0) {
+    if (p.N % 96 == 0 && p.N <= 192) return p.N;  // 96 or 192
+    return 0;
+  }
+  if (p.N == 192 || p.N == 384) return 192;
+  const int sms = gemm_num_sms();
+  const long mt = (long)((p.M + GEMM_BM - 1) / GEMM_BM) * p.batches;
+  const int cand[3] = {256, 128, 64};
+  const double mma_eff[3] = {1.0, 0.85, 0.6};
+  double best = -1;
+  int best_bn = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (p.N % cand[i] != 0 && !(p.N > cand[i] && i == 2)) continue;
+    const long tiles = mt * ((p.N + cand[i] - 1) / cand[i]);
+    const long waves = (tiles + sms - 1) / sms;
+    const double eff = (double)tiles / (double)(waves * sms) * mma_eff[i];
+    if (eff > best + 1e-9) { best = eff; best_bn = cand[i]; }
+  }
+  return best_bn;
+}
+
+cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
+  GemmParams p = c.p;
+  if (p.batches < 1) p.batches = 1;
+  if (p.taps < 1) p.taps = 1;
+  if (p.a_batch_div < 1) p.a_batch_div = 1;
+  if (p.scale == 0.f) p.scale = 1.f;
+  if (p.pos_period < 1) p.pos_period = 1;
+  if (p.M <= 0 || p.N <= 0 || p.Kc <= 0 || p.taps > 8) return cudaErrorInvalidValue;
+  if (p.N % 32 != 0 || (c.lda % 8) != 0 || (c.ldb % 8) != 0) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15)) return cudaErrorInvalidValue;
+
+  const int bn = pick_bn(c);
+  if (bn == 0) return cudaErrorInvalidValue;
+  const bool small_k = (p.Kc % 64 != 0) && (p.Kc % 96 == 0) && bn == 96;  // DAC last stage: 96 channels / tap
+  const int bk = small_k ? 32 : 64;
+  const int a_batches = (p.batches + p.a_batch_div - 1) / p.a_batch_div;
+  const int64_t a_bstride = c.a_batch_stride ? c.a_batch_stride : (int64_t)p.M * c.lda;
+
+  CUtensorMap ma, mb;
+  if (!get_tensor_map(&ma, c.A, 3, (uint64_t)p.Kc, (uint64_t)p.M, (uint64_t)a_batches, (uint64_t)c.lda * 2,
+                      (uint64_t)a_bstride * 2, bk, GEMM_BM, bk * 2))
+    return cudaErrorInvalidValue;
+  const uint64_t b_rows = c.b_rows ? (uint64_t)c.b_rows : (uint64_t)p.N * (p.b_batch_rows ? p.batches : 1);
+  if (!get_tensor_map(&mb, c.B, 2, (uint64_t)p.taps * p.Kc, b_rows, 1, (uint64_t)c.ldb * 2, 0, bk, bn, bk * 2))
+    return cudaErrorInvalidValue;
+
+  switch (p.epi) {
+    case EPI_SWIGLU:
+      if (p.N % 256 != 0) return cudaErrorInvalidValue;
+      return launch_inst<256, 64, 1, EPI_SWIGLU>(ma, mb, p, s);
+    case EPI_QKV:
+      if (p.sec_width % 128 != 0 || p.N % 128 != 0) return cudaErrorInvalidValue;
+      return launch_inst<256, 64, 1, EPI_QKV>(ma, mb, p, s);
+    case EPI_GENERIC:
+      if (small_k) return launch_inst<96, 32, 3, EPI_GENERIC>(ma, mb, p, s);
+      switch (bn) {
+        case 256: return launch_inst<256, 64, 1, EPI_GENERIC>(ma, mb, p, s);
+        case 192: return launch_inst<192, 64, 1, EPI_GENERIC>(ma, mb, p, s);
+        case 128: return launch_inst<128, 64, 1, EPI_GENERIC>(ma, mb, p, s);
+        case 64: return launch_inst<64, 64, 1, EPI_GENERIC>(ma, mb, p, s);
+        default: return cudaErrorInvalidValue;
+      }
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace echo

@@ -1,0 +1,76 @@
+// Host-visible description of one tcgen05 GEMM launch (see gemm_tc.cuh for the kernel).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace echo {
+
+typedef __nv_bfloat16 bf16;
+
+enum EpiMode : int { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV = 2 };
+enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SNAKE = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SILU = 5 };
+
+struct QkvSection {
+  bf16* out;            // [rows, sec_width] bf16
+  const float* norm_w;  // [sec_width] per-(head,dim) RMSNorm weight, or null (no norm)
+  int rope_heads;       // RoPE applied to 128-column groups with index < rope_heads (0 = none)
+  int sigmoid;          // store sigmoid(v)
+};
+
+struct GemmParams {
+  int M;        // rows per batch item
+  int N;        // output columns
+  int Kc;       // reduction length per tap
+  int batches;  // batch items (A is addressed (k, row, batch))
+  int taps;     // 1 for plain GEMM
+  int tap_shift[8];  // row offset added to the A row coordinate for each tap
+  int a_batch_div;   // A batch coordinate = batch / a_batch_div (>=1): lets several weight sets share one A
+  int b_batch_rows;  // B row coordinate = batch * b_batch_rows + n0 (0: weights shared by all batch items)
+
+  int epi;  // EpiMode (must match the template instantiation)
+  // ---- EPI_GENERIC: v = (acc + bias[c]) * scale; v *= gate[g]; v += resid[r,c];
+  //      out_f32[r,c] = v; out_bf16[r,c] = act(v).   c index for bias/alpha/gate is (col % col_mod).
+  const float* bias;
+  int bias_bstride;    // bias index += batch * bias_bstride
+  float scale;
+  const float* gate;   // fp32; index = (row / rows_per_gate) * gate_ld + (col % col_mod); rows_per_gate==0 -> row term 0
+  int rows_per_gate;
+  int gate_ld;
+  const float* resid;  // fp32 [rows, ld_f32] (may alias out_f32: each element is read then written by one thread)
+  float* out_f32;
+  int ld_f32;
+  bf16* out_bf16;
+  int ld_bf16;
+  int act;             // ActMode applied to the bf16 output only
+  const float* alpha;  // snake alpha [col_mod]
+  int col_mod;
+  // ---- EPI_SWIGLU: tile columns [0,BN/2) hold w1 rows, [BN/2,BN) the matching w3 rows;
+  //      out_bf16[r, n0/2 + c] = silu(a) * b.     (uses out_bf16 / ld_bf16)
+  // ---- EPI_QKV: N = nsec * sec_width, each 128-column group is normalised / rotated independently.
+  QkvSection sec[4];
+  int sec_width;
+  const float* rope_cos;  // [pos, head_dim/2] fp32
+  const float* rope_sin;
+  int head_dim;    // 128 (DiT/encoders) or 64 (DAC post_module)
+  int pos_period;  // position = pos_offset + pos_mult * (row % pos_period)
+  int pos_offset;
+  int pos_mult;
+  float eps;
+};
+
+struct GemmCall {
+  const bf16* A;           // [a_batches][M][lda] bf16, K contiguous
+  int64_t lda;             // elements
+  int64_t a_batch_stride;  // elements; 0 -> M*lda
+  const bf16* B;           // [b_rows][ldb] bf16, K contiguous (nn.Linear weight layout)
+  int64_t ldb;
+  int64_t b_rows;  // 0 -> N (or N*batches when b_batch_rows is set)
+  GemmParams p;
+  int bn;  // tile N override (0 = auto)
+};
+
+cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s);
+int gemm_num_sms();
+
+}  // namespace echo

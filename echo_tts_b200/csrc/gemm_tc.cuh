@@ -1,0 +1,326 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = sum_taps A[rows + shift(tap), Kc] * B[N, tap*Kc + k]^T  (+ fused epilogues).
+//
+// One kernel serves every dense contraction on the Echo-TTS hot path:
+//   * DiT / encoder linears (reference model.py:217-224, 263-266, 308): taps = 1, A = activations [M,K] bf16,
+//     B = nn.Linear weight [N,K] bf16 (already K-major, no transpose needed).
+//   * DAC causal convs (reference autoencoder.py:285-289, 310-316, 884-900): activations are kept time-major
+//     (B, T, C), so a dilated causal conv is a GEMM whose K loop walks (tap, channel-block) and whose A tile for
+//     tap j is the SAME matrix loaded at row offset -(k-1-j)*dilation. TMA zero-fills negative rows, which is
+//     exactly the causal left padding; a 3-D tensor map (C, T, batch) keeps batches from bleeding.
+//
+// Structure (persistent, warp-specialised, 384 threads, 1 CTA / SM):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warp 2      : TMEM allocator
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b -> registers -> fused math -> global)
+// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "common.cuh"
+#include "gemm.h"
+
+namespace echo {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARP0 = 4;
+constexpr int GEMM_EPI_WARPS = 8;
+
+__host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
+__host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS) { return (GEMM_BM + BN) * BK * 2 * ATOMS; }
+__host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS) {
+  int s = (200 * 1024) / gemm_stage_bytes(BN, BK, ATOMS);
+  return s > 8 ? 8 : s;
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int BN, int BK, int ATOMS) {
+  return gemm_stages(BN, BK, ATOMS) * gemm_stage_bytes(BN, BK, ATOMS) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+ECHO_DEVICE float apply_act(float v, int act, float alpha) {
+  switch (act) {
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case ACT_SNAKE: {
+      float s = sinf(alpha * v);
+      return v + s * s / (alpha + 1e-9f);
+    }
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIGMOID: return sigmoid_f(v);
+    case ACT_SILU: return silu_f(v);
+    default: return v;
+  }
+}
+
+template <int BN, int BK, int ATOMS, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int STAGES = gemm_stages(BN, BK, ATOMS);
+  constexpr int A_ATOM = GEMM_BM * BK * 2;
+  constexpr int B_ATOM = BN * BK * 2;
+  constexpr int STAGE_BYTES = (A_ATOM + B_ATOM) * ATOMS;
+  constexpr int ACC_STRIDE = gemm_acc_stride(BN);
+  constexpr int ROW_BYTES = BK * 2;
+  static_assert(BK == 64 || BK == 32, "BK must match a swizzle span");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(A_ATOM % 1024 == 0 && B_ATOM % 1024 == 0, "atoms must keep 1024B alignment");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * p.batches * tiles_n;
+  const int kb_per_tap = (p.Kc + BK * ATOMS - 1) / (BK * ATOMS);
+  const int num_kb = kb_per_tap * p.taps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * ACC_STRIDE>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile % tiles_m;
+        const int rest = tile / tiles_m;
+        const int bt = rest % p.batches;
+        const int nt = rest / p.batches;
+        const int m0 = mt * GEMM_BM, n0 = nt * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kb_per_tap;
+          const int kc0 = (kb - tap * kb_per_tap) * (BK * ATOMS);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_ATOM * ATOMS;
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a) {
+            tma_load_3d(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
+            tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_ATOM * ATOMS;
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a) {
+            const uint64_t adesc = make_smem_desc<ROW_BYTES>(sa + a * A_ATOM);
+            const uint64_t bdesc = make_smem_desc<ROW_BYTES>(sb + a * B_ATOM);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
+              tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | a | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - GEMM_EPI_WARP0;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;      // which half of the column chunks
+    const int r_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile % tiles_m;
+      const int rest = tile / tiles_m;
+      const int bt = rest % p.batches;
+      const int nt = rest / p.batches;
+      const int m = mt * GEMM_BM + r_in_tile;
+      const int n0 = nt * BN;
+      const bool row_ok = m < p.M;
+      const size_t row = (size_t)bt * p.M + m;
+      const int as = it & 1;
+      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+
+      if constexpr (EPI == EPI_GENERIC) {
+        const int cmod = p.col_mod > 0 ? p.col_mod : p.N;
+        const size_t grow = (p.gate && p.rows_per_gate > 0) ? (row / p.rows_per_gate) * (size_t)p.gate_ld : 0;
+        for (int ch = half; ch < BN / 32; ch += 2) {
+          float v[32];
+          tc_ld_32x32(tbase + ch * 32, v);
+          tc_wait_ld();
+          const int c0 = n0 + ch * 32;
+          if (row_ok && c0 < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cm = (c0 + j) % cmod;
+              float x = v[j];
+              if (p.bias) x += __ldg(p.bias + bt * p.bias_bstride + cm);
+              x *= p.scale;
+              if (p.gate) x *= __ldg(p.gate + grow + cm);
+              v[j] = x;
+            }
+            if (p.resid) {
+              const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ld_f32 + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 r = rp[j];
+                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.out_bf16) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a0 = v[2 * j], a1 = v[2 * j + 1];
+                if (p.act != ACT_NONE) {
+                  const float al0 = p.alpha ? __ldg(p.alpha + (c0 + 2 * j) % cmod) : 1.f;
+                  const float al1 = p.alpha ? __ldg(p.alpha + (c0 + 2 * j + 1) % cmod) : 1.f;
+                  a0 = apply_act(a0, p.act, al0);
+                  a1 = apply_act(a1, p.act, al1);
+                }
+                pk[j] = pack_bf16(a0, a1);
+              }
+              uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_bf16 + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_SWIGLU) {
+        constexpr int HALF_CH = BN / 64;  // chunks in the w1 half
+        for (int ch = half; ch < HALF_CH; ch += 2) {
+          float a[32], b[32];
+          tc_ld_32x32(tbase + ch * 32, a);
+          tc_ld_32x32(tbase + (ch + HALF_CH) * 32, b);
+          tc_wait_ld();
+          const int c0 = n0 / 2 + ch * 32;
+          if (row_ok) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              pk[j] = pack_bf16(silu_f(a[2 * j]) * b[2 * j], silu_f(a[2 * j + 1]) * b[2 * j + 1]);
+            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_bf16 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+      } else {  // EPI_QKV: this thread owns one row x 128 contiguous columns (group `half` of the 256-wide tile)
+        static_assert(EPI != EPI_QKV || BN == 256, "QKV epilogue needs BN == 256");
+        const int g0 = n0 + half * 128;  // first global column of the group
+        if (g0 < p.N) {
+          const int si = g0 / p.sec_width;
+          const int cs = g0 - si * p.sec_width;  // column inside the section
+          const QkvSection sec = p.sec[si];
+          const int grp = cs >> 7;
+          float rstd = 1.f;
+          if (sec.norm_w) {
+            // RMSNorm over head_dim columns (reference model.py:99-104); head_dim == 128 whenever norm_w is set
+            float ss = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              float v[32];
+              tc_ld_32x32(tbase + (half * 4 + ch) * 32, v);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+            }
+            rstd = rsqrtf(ss * (1.f / 128.f) + p.eps);
+          }
+          const bool do_rope = grp < sec.rope_heads;
+          const int pos = p.pos_offset + p.pos_mult * (int)(row % (size_t)p.pos_period);
+          const int hd2 = p.head_dim >> 1;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            float v[32];
+            tc_ld_32x32(tbase + (half * 4 + ch) * 32, v);
+            tc_wait_ld();
+            if (row_ok) {
+              const int cc = cs + ch * 32;
+              if (sec.norm_w) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] * rstd * __ldg(sec.norm_w + cc + j);
+              }
+              if (do_rope) {
+                const int pi0 = ((cc % p.head_dim) >> 1);
+                const float* cp = p.rope_cos + (size_t)pos * hd2 + pi0;
+                const float* sp = p.rope_sin + (size_t)pos * hd2 + pi0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float c = __ldg(cp + j), s = __ldg(sp + j);
+                  const float a = v[2 * j], b = v[2 * j + 1];
+                  v[2 * j] = a * c - b * s;
+                  v[2 * j + 1] = a * s + b * c;
+                }
+              }
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a0 = v[2 * j], a1 = v[2 * j + 1];
+                if (sec.sigmoid) { a0 = sigmoid_f(a0); a1 = sigmoid_f(a1); }
+                pk[j] = pack_bf16(a0, a1);
+              }
+              uint4* op = reinterpret_cast<uint4*>(sec.out + row * p.sec_width + cc);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<2 * ACC_STRIDE>(tmem_base);
+}
+
+}  // namespace echo

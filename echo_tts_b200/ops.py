@@ -1,0 +1,112 @@
+"""Op-level wrappers over the C ABI (echo_op_gemm / echo_op_attention) taking torch CUDA tensors.
+
+Used by the parity tests and micro-benchmarks; the model-level calls launch the same kernels from C++.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, EPI_GENERIC, EPI_QKV, EPI_SWIGLU, AttnDesc, GemmDesc
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence[int] = (0,), bias=None,
+         scale: float = 1.0, gate=None, rows_per_gate: int = 0, resid=None, out_f32=None, out_bf16=None,
+         act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0) -> None:
+    """out = epilogue(sum_taps a[rows + shift] @ w[:, tap*Kc:(tap+1)*Kc].T).  a: (batches, M, Kc) or (M, Kc) bf16."""
+    lib = _lib.load(strict=False)
+    if a.dim() == 2:
+        a = a.unsqueeze(0)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(-1) == 1 and w.stride(-1) == 1
+    batches, M, Kc = a.shape
+    N = w.shape[0]
+    d = GemmDesc()
+    d.A, d.lda, d.a_batch_stride = a.data_ptr(), a.stride(1), a.stride(0)
+    d.B, d.ldb, d.b_rows = w.data_ptr(), w.stride(0), N
+    d.M, d.N, d.Kc, d.batches, d.taps = M, N, Kc, batches, taps
+    for i, s in enumerate(tap_shift):
+        d.tap_shift[i] = int(s)
+    d.epi = EPI_GENERIC
+    d.bias, d.scale = _ptr(bias), scale
+    d.gate, d.rows_per_gate, d.gate_ld = _ptr(gate), rows_per_gate, (gate.stride(0) if gate is not None and gate.dim() > 1 else 0)
+    d.resid, d.out_f32 = _ptr(resid), _ptr(out_f32)
+    d.ld_f32 = (out_f32 if out_f32 is not None else resid).stride(-2) if (out_f32 is not None or resid is not None) else 0
+    d.out_bf16, d.ld_bf16 = _ptr(out_bf16), (out_bf16.stride(-2) if out_bf16 is not None else 0)
+    d.act, d.alpha, d.col_mod, d.bn = act, _ptr(alpha), col_mod, bn
+    _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm")
+
+
+def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor) -> None:
+    """w13: (2*I, K) packed so that each 256-row tile is [128 rows of w1 | the matching 128 rows of w3]."""
+    lib = _lib.load(strict=False)
+    M, K = a.shape
+    d = GemmDesc()
+    d.A, d.lda, d.a_batch_stride = a.data_ptr(), a.stride(0), 0
+    d.B, d.ldb, d.b_rows = w13.data_ptr(), w13.stride(0), w13.shape[0]
+    d.M, d.N, d.Kc, d.batches, d.taps = M, w13.shape[0], K, 1, 1
+    d.epi = EPI_SWIGLU
+    d.out_bf16, d.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm(swiglu)")
+
+
+def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoids, sec_width: int, rope_cos=None,
+             rope_sin=None, head_dim: int = 128, pos_period: int = 1, pos_offset: int = 0, pos_mult: int = 1,
+             eps: float = 1e-5) -> None:
+    lib = _lib.load(strict=False)
+    M, K = a.shape
+    d = GemmDesc()
+    d.A, d.lda, d.a_batch_stride = a.data_ptr(), a.stride(0), 0
+    d.B, d.ldb, d.b_rows = w.data_ptr(), w.stride(0), w.shape[0]
+    d.M, d.N, d.Kc, d.batches, d.taps = M, w.shape[0], K, 1, 1
+    d.epi = EPI_QKV
+    for i, o in enumerate(outs):
+        d.sec_out[i] = o.data_ptr()
+        d.sec_norm_w[i] = _ptr(norm_ws[i])
+        d.sec_rope_heads[i] = rope_heads[i]
+        d.sec_sigmoid[i] = sigmoids[i]
+    d.sec_width, d.rope_cos, d.rope_sin, d.head_dim = sec_width, _ptr(rope_cos), _ptr(rope_sin), head_dim
+    d.pos_period, d.pos_offset, d.pos_mult, d.eps = pos_period, pos_offset, pos_mult, eps
+    _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm(qkv)")
+
+
+def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch.Tensor] = None,
+              scale: Optional[float] = None) -> None:
+    """q: (b, S, H, D) bf16. segments: list of dicts with keys k, v ((b, L, H, D) bf16) and optional mask (b, L) bool,
+    eff_len (b,) int32, pos_limit_mult, pos_limit, causal, window."""
+    lib = _lib.load(strict=False)
+    b, S, H, D = q.shape
+    d = AttnDesc()
+    d.Q, d.q_batch_stride, d.q_row_stride = q.data_ptr(), q.stride(0), q.stride(1)
+    d.gate, d.out = _ptr(gate), out.data_ptr()
+    d.b, d.S, d.H, d.D = b, S, H, D
+    d.scale = scale if scale is not None else D ** -0.5
+    d.nseg = len(segments)
+    keep = []
+    for i, sg in enumerate(segments):
+        k, v = sg["k"], sg["v"]
+        assert k.stride() == v.stride() and k.stride(3) == 1 and k.stride(2) == D
+        s = d.seg[i]
+        s.K, s.V = k.data_ptr(), v.data_ptr()
+        s.batch_stride, s.row_stride, s.len = (k.stride(0) if k.shape[0] > 1 else 0), k.stride(1), k.shape[1]
+        m = sg.get("mask")
+        if m is not None:
+            m8 = m.view(torch.uint8) if m.dtype == torch.bool else m
+            keep.append(m8)
+            s.mask, s.mask_ld, s.mask_stride = m8.data_ptr(), m8.stride(0), m8.stride(1)
+        e = sg.get("eff_len")
+        if e is not None:
+            s.eff_len = e.data_ptr()
+        s.pos_limit_mult, s.pos_limit = sg.get("pos_limit_mult", 0), sg.get("pos_limit", 0)
+        s.causal, s.window = int(sg.get("causal", 0)), int(sg.get("window", 0))
+    _lib.check(lib.echo_op_attention(C.byref(d), _stream()), "echo_op_attention")

@@ -1,0 +1,195 @@
+/*
+ * echo_b200.h -- C ABI of libecho_b200.so: the B200-native (sm_100a) implementation of the Echo-TTS sampling
+ * hot path (Euler sampler + independent text/speaker CFG + 24-layer latent DiT + Fish S1-DAC decoder).
+ *
+ * The reference (sruckh/echo-tts) has no FFI: its boundary is four Python objects (model, sample_fn, fish_ae,
+ * pca_state) threaded through inference.sample_pipeline (reference inference.py:309-347). Each entry point below
+ * names the reference function it replaces; the echo_tts_b200 Python package mirrors the Python call signatures on top of
+ * these symbols, INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative ECHO_ERR_* code on failure; echo_last_error() returns a
+ *     human-readable message for the calling thread. No exception crosses the ABI.
+ *   - all data pointers are CUDA DEVICE pointers owned by the caller unless a parameter says "host".
+ *   - `stream` is a cudaStream_t passed as void*; the library never synchronises the device behind the caller's
+ *     back except in the *_host entry points (documented there).
+ *   - a handle is bound to one device and is not thread-safe; use one handle per (device, thread).
+ *   - there is NO CPU fallback: without an sm_100 device echo_create fails with ECHO_ERR_DEVICE.
+ */
+#ifndef ECHO_B200_H
+#define ECHO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECHO_OK 0
+#define ECHO_ERR_ARG (-1)     /* bad argument / unsupported shape */
+#define ECHO_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+#define ECHO_ERR_DEVICE (-3)  /* no sm_100 device */
+#define ECHO_ERR_STATE (-4)   /* call order (e.g. weights missing) */
+
+#define ECHO_DTYPE_F32 0
+#define ECHO_DTYPE_BF16 1
+
+typedef struct echo_handle echo_handle;
+
+/* Architecture of EchoDiT (reference model.py:472-559; echo-tts-base values at inference.py:16-24). */
+typedef struct echo_dit_config {
+  int latent_size;       /* 80   */
+  int model_size;        /* 2048 */
+  int num_layers;        /* 24   */
+  int num_heads;         /* 16   (head_dim must be 128) */
+  int intermediate_size; /* 5888 */
+  float norm_eps;        /* 1e-5 */
+  int text_vocab_size;   /* 256  */
+  int text_model_size;   /* 1280 */
+  int text_num_layers;   /* 14   */
+  int text_num_heads;    /* 10   */
+  int text_intermediate_size; /* 3328 */
+  int speaker_patch_size;     /* 4    */
+  int speaker_model_size;     /* 1280 */
+  int speaker_num_layers;     /* 14   */
+  int speaker_num_heads;      /* 10   */
+  int speaker_intermediate_size; /* 3328 */
+  int timestep_embed_size;       /* 512  */
+  int adaln_rank;                /* 256  */
+} echo_dit_config;
+
+/* Architecture of the Fish S1-DAC decode path (reference autoencoder.py:1144-1192 build_ae). */
+typedef struct echo_dac_config {
+  int latent_dim;      /* 1024 */
+  int pca_dim;         /* 80   */
+  int post_layers;     /* 8    quantizer.post_module (window-limited causal transformer) */
+  int post_heads;      /* 16   (head_dim 64) */
+  int post_intermediate; /* 3072 */
+  int post_window;     /* 128  */
+  float post_norm_eps; /* 1e-5 */
+  int num_upsample;    /* 2    quantizer.upsample stages (ConvTranspose k2 s2 + ConvNeXt) */
+  int decoder_dim;     /* 1536 */
+  int num_rates;       /* 4    */
+  int rates[8];        /* 8, 8, 4, 2 */
+} echo_dac_config;
+
+/* Knobs of sample_euler_cfg_independent_guidances (reference inference.py:427-447). */
+typedef struct echo_sampler_args {
+  int num_steps;
+  float cfg_scale_text;
+  float cfg_scale_speaker;
+  float cfg_min_t;
+  float cfg_max_t;
+  int has_truncation; float truncation_factor;
+  int has_rescale;    float rescale_k; float rescale_sigma;
+  int has_kv_scale;   float speaker_kv_scale; int speaker_kv_max_layers; /* <=0: all layers */ float speaker_kv_min_t;
+  int sequence_length;   /* latents to generate (<= 640 in the reference) */
+  int round_t_to_bf16;   /* 1: t is rounded to bf16 before the timestep embedding, as the reference does when
+                            model.dtype is bfloat16 (inference.py:489); 0: fp32 t */
+} echo_sampler_args;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int echo_create(echo_handle** out, int device);
+int echo_destroy(echo_handle* h);
+const char* echo_last_error(void);
+int echo_num_launches(echo_handle* h, int64_t* out); /* kernels launched by this handle so far */
+
+/* ---- weights: replaces load_state_dict (reference inference.py:14-47, 56-76) ---------------------------- */
+int echo_dit_configure(echo_handle* h, const echo_dit_config* cfg);
+int echo_dac_configure(echo_handle* h, const echo_dac_config* cfg);
+/* `key` is the reference state-dict key (e.g. "blocks.3.attention.wq.weight", "dac.decoder.model.1.block.0.alpha"
+ * -- DAC keys carry a "dac." prefix). The tensor is copied/packed into library-owned bf16/fp32 buffers (QKV|gate and
+ * W1|W3 fused, weight-norm folded), so the caller may free `data` afterwards. dtype: ECHO_DTYPE_*. */
+int echo_set_weight(echo_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype,
+                    void* stream);
+int echo_dit_finalize(echo_handle* h, void* stream); /* checks that every required key arrived, builds tables */
+int echo_dac_finalize(echo_handle* h, void* stream);
+
+/* ---- EchoDiT: replaces model.py:563-636 ------------------------------------------------------------------ */
+/* K[i], V[i]: 24 (num_layers) output device pointers, each (B, L, num_heads, 128) bf16 contiguous. */
+int echo_kv_text(echo_handle* h, const int32_t* ids, const uint8_t* mask /* (B,Lt) bool or NULL */, int B, int Lt,
+                 void* const* K, void* const* V, void* stream);
+int echo_kv_speaker(echo_handle* h, const void* latent_bf16 /* (B,Ls,80) */, int B, int Ls, void* const* K,
+                    void* const* V, void* stream);
+int echo_kv_latent(echo_handle* h, const void* prefix_bf16 /* (B,Lp,80) */, int B, int Lp, void* const* K,
+                   void* const* V, void* stream);
+/* == EchoDiT.forward. x (b,S,80) fp32; t (b,) fp32; masks uint8 (bool) (b,Lt) / (b,Ls_unstrided);
+ * caches as produced above with batch b; Kl/Vl may be NULL (Pl = 0). out (b,S,80) fp32.
+ * layer_out: optional (num_layers) device pointers receiving each block's output (b,S,D) fp32 (parity tests). */
+int echo_dit_forward(echo_handle* h, const float* x, const float* t, const uint8_t* text_mask,
+                     const uint8_t* speaker_mask, void* const* Kt, void* const* Vt, int Lt, void* const* Ks,
+                     void* const* Vs, int Ls_unstrided, void* const* Kl, void* const* Vl, int Pl, int start_pos,
+                     int b, int S, float* out, void* const* layer_out, void* stream);
+
+/* ---- samplers: replace inference.py:427-517 and inference_blockwise.py:15-123 -------------------------- */
+/* noise: (B, sequence_length, 80) fp32 drawn by the caller (torch.randn with the reference's generator, so seeds
+ * stay compatible). x_out: (B, sequence_length, 80) fp32. */
+int echo_sample_euler(echo_handle* h, const echo_sampler_args* a, const void* speaker_latent_bf16,
+                      const uint8_t* speaker_mask, int Ls, const int32_t* text_ids, const uint8_t* text_mask,
+                      int Lt, int B, const float* noise, float* x_out, void* stream);
+/* noise: concatenation over blocks of (B, block, 80); continuation (B,Lc,80) fp32 or NULL;
+ * prefix_out (B, Lc + sum(blocks), 80) fp32. */
+int echo_sample_blockwise(echo_handle* h, const echo_sampler_args* a, const int* block_sizes, int nblocks,
+                          const void* speaker_latent_bf16, const uint8_t* speaker_mask, int Ls,
+                          const int32_t* text_ids, const uint8_t* text_mask, int Lt, int B,
+                          const float* continuation, int Lc, const float* noise, float* prefix_out, void* stream);
+
+/* ---- DAC decode: replaces ae_decode (inference.py:226-229) + DAC.decode_zq (autoencoder.py:1128-1132) ---- */
+/* z (B,T,80) fp32 PCA latents; pca_components (80,1024) fp32; pca_mean (1024) fp32; audio (B,1,2048*T) fp32. */
+int echo_dac_decode(echo_handle* h, const float* z, const float* pca_components, const float* pca_mean,
+                    float latent_scale, int B, int T, float* audio, void* stream);
+/* == DAC.decode_zq: zq (B,1024,T) fp32 channels-first. */
+int echo_dac_decode_zq(echo_handle* h, const float* zq, int B, int T, float* audio, void* stream);
+
+/* ---- host-buffer convenience (what a non-PyTorch host binds): copies in, runs, copies out, synchronises. -- */
+int echo_sample_euler_host(echo_handle* h, const echo_sampler_args* a, const float* speaker_latent_f32_host,
+                           const uint8_t* speaker_mask_host, int Ls, const int32_t* text_ids_host,
+                           const uint8_t* text_mask_host, int Lt, int B, const float* noise_host,
+                           float* x_out_host);
+
+/* ---- op-level entry points (used by the parity tests; same kernels the calls above launch) -------------- */
+typedef struct echo_gemm_desc {
+  const void* A; int64_t lda; int64_t a_batch_stride; /* bf16 [batches][M][lda] */
+  const void* B; int64_t ldb; int64_t b_rows;          /* bf16 [b_rows][ldb]; K extent = taps*Kc */
+  int M, N, Kc, batches, taps;
+  int tap_shift[8];
+  int epi; /* 0 generic, 1 swiglu, 2 qkv */
+  const float* bias; float scale;
+  const float* gate; int rows_per_gate; int gate_ld;
+  const float* resid; float* out_f32; int ld_f32;
+  void* out_bf16; int ld_bf16;
+  int act; const float* alpha; int col_mod;
+  /* qkv */
+  void* sec_out[4]; const float* sec_norm_w[4]; int sec_rope_heads[4]; int sec_sigmoid[4];
+  int sec_width; const float* rope_cos; const float* rope_sin; int head_dim; int pos_period; int pos_offset;
+  int pos_mult; float eps;
+  int bn; /* 0 = auto */
+} echo_gemm_desc;
+int echo_op_gemm(const echo_gemm_desc* d, void* stream);
+
+typedef struct echo_attn_segment {
+  const void* K; const void* V;   /* bf16, key j of batch b at K + (b*batch_stride + j*row_stride) elements */
+  int64_t batch_stride; int64_t row_stride;
+  int len;                        /* keys in this segment */
+  const int32_t* eff_len;         /* optional device (b): keys >= eff_len[batch] are all invalid (tile skipping) */
+  const uint8_t* mask;            /* (batch, mask_ld) bool per key, or NULL = all valid */
+  int mask_ld; int mask_stride;   /* key j reads mask[b*mask_ld + j*mask_stride] */
+  int pos_limit_mult;             /* >0: key j valid iff j*pos_limit_mult < pos_limit (latent prefix, model.py:243-244) */
+  int pos_limit;
+  int causal;                     /* 1: key j valid iff j <= query index (+ window) */
+  int window;                     /* >0 with causal: also j > q - window */
+} echo_attn_segment;
+typedef struct echo_attn_desc {
+  const void* Q; int64_t q_batch_stride; int64_t q_row_stride; /* bf16 (b, S, H, D) */
+  const void* gate;  /* optional bf16 (b,S,H*D): output multiplied by it (already sigmoid-ed) */
+  void* out;         /* bf16 (b, S, H*D) */
+  int b, S, H, D;    /* D = 128 or 64 */
+  float scale;       /* softmax scale, 1/sqrt(D) */
+  int nseg; echo_attn_segment seg[4];
+} echo_attn_desc;
+int echo_op_attention(const echo_attn_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECHO_B200_H */

@@ -1,0 +1,196 @@
+"""Op-level parity: the CUDA kernels behind the C ABI vs plain PyTorch fp32 math on the same bf16-rounded inputs.
+
+Tolerances: GEMM outputs are fp32-accumulated products of bf16 operands, so they are compared against an fp32 matmul
+of the SAME bf16-rounded operands: rel-L2 <= 2e-3 for bf16 outputs (one bf16 rounding), <= 1e-5 for fp32 outputs.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from echo_tts_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 0), (640, 2048, 2048, 0), (1920, 2048, 2048, 256),
+                                      (200, 512, 1280, 128), (77, 192, 320, 0), (300, 128, 80, 64),
+                                      (1920, 2048, 5888, 0)])
+def test_gemm_plain(ops, M, N, K, bn):
+    a, w = _rand((M, K), 1), _rand((N, K), 2, scale=K ** -0.5)
+    out32 = torch.empty(M, N, device="cuda")
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out_f32=out32, out_bf16=out16, bn=bn)
+    ref = a.float() @ w.float().T
+    assert rel_l2(out32, ref) < 1e-5
+    assert rel_l2(out16, ref) < 3e-3
+
+
+def test_gemm_epilogue_bias_gate_resid_act(ops):
+    from echo_tts_b200._lib import ACT_GELU, ACT_SNAKE
+    M, N, K, S = 384, 512, 256, 128
+    a, w = _rand((M, K), 3), _rand((N, K), 4, scale=K ** -0.5)
+    bias = _rand((N,), 5, dtype=torch.float32)
+    gate = _rand((M // S, N), 6, dtype=torch.float32)
+    resid = _rand((M, N), 7, dtype=torch.float32)
+    x = resid.clone()
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, bias=bias, scale=0.5, gate=gate, rows_per_gate=S, resid=x, out_f32=x, out_bf16=out16, act=ACT_GELU)
+    ref = (a.float() @ w.float().T + bias) * 0.5 * gate.repeat_interleave(S, 0) + resid
+    assert rel_l2(x, ref) < 1e-5
+    assert rel_l2(out16, torch.nn.functional.gelu(ref)) < 3e-3
+    alpha = (_rand((N,), 8, dtype=torch.float32).abs() + 0.5)
+    ops.gemm(a, w, bias=bias, out_bf16=out16, act=ACT_SNAKE, alpha=alpha)
+    y = a.float() @ w.float().T + bias
+    ref = y + torch.sin(alpha * y) ** 2 / (alpha + 1e-9)
+    assert rel_l2(out16, ref) < 3e-3
+
+
+@pytest.mark.parametrize("C,Cout,T,B,dil", [(64, 64, 300, 2, 1), (192, 192, 1000, 1, 3), (96, 96, 777, 2, 9),
+                                            (384, 384, 512, 1, 9)])
+def test_gemm_causal_conv(ops, C, Cout, T, B, dil):
+    """Causal dilated conv k=7 as a 7-tap GEMM over time-major activations (reference autoencoder.py:285-289)."""
+    x = _rand((B, T, C), 11)
+    wt = _rand((Cout, C, 7), 12, scale=(7 * C) ** -0.5)  # torch conv1d weight layout (Cout, Cin, k)
+    bias = _rand((Cout,), 13, dtype=torch.float32)
+    w_packed = wt.permute(0, 2, 1).reshape(Cout, 7 * C).contiguous()  # [Cout][tap][Cin]
+    out = torch.empty(B, T, Cout, device="cuda")
+    ops.gemm(x, w_packed, taps=7, tap_shift=[-(6 - j) * dil for j in range(7)], bias=bias, out_f32=out)
+    xin = torch.nn.functional.pad(x.float().transpose(1, 2), (6 * dil, 0))
+    ref = torch.nn.functional.conv1d(xin, wt.float(), bias, dilation=dil).transpose(1, 2)
+    assert rel_l2(out, ref) < 1e-5
+
+
+def test_gemm_swiglu(ops):
+    M, K, I = 640, 512, 768
+    a = _rand((M, K), 21)
+    w1, w3 = _rand((I, K), 22, scale=K ** -0.5), _rand((I, K), 23, scale=K ** -0.5)
+    w13 = torch.stack([w1.view(I // 128, 128, K), w3.view(I // 128, 128, K)], 1).reshape(2 * I, K).contiguous()
+    out = torch.empty(M, I, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_swiglu(a, w13, out)
+    ref = torch.nn.functional.silu(a.float() @ w1.float().T) * (a.float() @ w3.float().T)
+    assert rel_l2(out, ref) < 3e-3
+
+
+def _rope_tables(npos, hd):
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, hd, 2)[: hd // 2] / hd))
+    ang = torch.outer(torch.arange(npos), freqs)
+    return torch.cos(ang).cuda().contiguous(), torch.sin(ang).cuda().contiguous()
+
+
+def _rope_ref(x, cos, sin, pos):
+    # x (rows, heads, hd) fp32; interleaved pairs (reference model.py:17-24)
+    xr = x.reshape(*x.shape[:-1], -1, 2)
+    c, s = cos[pos][:, None, :], sin[pos][:, None, :]
+    o = torch.stack([xr[..., 0] * c - xr[..., 1] * s, xr[..., 0] * s + xr[..., 1] * c], -1)
+    return o.reshape(x.shape)
+
+
+def test_gemm_qkv_norm_rope(ops):
+    """Fused wq|wk|wv|gate projection + per-head RMSNorm + RoPE on the first half of the heads
+    (reference model.py:217-232, 199-202)."""
+    b, S, Dm, H = 3, 160, 512, 4
+    M = b * S
+    a = _rand((M, Dm), 31)
+    w = _rand((4 * Dm, Dm), 32, scale=Dm ** -0.5)
+    qn = (1 + 0.1 * _rand((Dm,), 33, dtype=torch.float32))
+    kn = (1 + 0.1 * _rand((Dm,), 34, dtype=torch.float32))
+    cos, sin = _rope_tables(S + 7, 128)
+    outs = [torch.empty(M, Dm, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+    ops.gemm_qkv(a, w, outs, [qn, kn, None, None], [H // 2, H // 2, 0, 0], [0, 0, 0, 1], Dm, cos, sin, 128,
+                 pos_period=S, pos_offset=7, eps=1e-5)
+    y = (a.float() @ w.float().T).view(M, 4, H, 128)
+    pos = (torch.arange(M, device="cuda") % S) + 7
+
+    def norm(v, wgt):
+        return v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + 1e-5) * wgt.view(H, 128)
+
+    def rope_half(v):
+        v = v.clone()
+        v[:, : H // 2] = _rope_ref(v[:, : H // 2], cos, sin, pos)
+        return v
+
+    q_ref = rope_half(norm(y[:, 0], qn)).reshape(M, Dm)
+    k_ref = rope_half(norm(y[:, 1], kn)).reshape(M, Dm)
+    assert rel_l2(outs[0], q_ref) < 3e-3
+    assert rel_l2(outs[1], k_ref) < 3e-3
+    assert rel_l2(outs[2], y[:, 2].reshape(M, Dm)) < 3e-3
+    assert rel_l2(outs[3], torch.sigmoid(y[:, 3].reshape(M, Dm))) < 3e-3
+
+
+def _sdpa_ref(q, ks, vs, masks, scale):
+    # q (b,S,H,D); ks/vs list of (b,L,H,D); masks list of (b,S,L) bool
+    k = torch.cat(ks, 1).float()
+    v = torch.cat(vs, 1).float()
+    m = torch.cat(masks, 2)
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k) * scale
+    s = s.masked_fill(~m[:, None], float("-inf"))
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhqk,bkhd->bqhd", p, v)
+
+
+@pytest.mark.parametrize("S,Lt,Ls,D,H", [(640, 768, 53, 128, 4), (160, 100, 1600, 128, 2), (100, 37, 4, 128, 2)])
+def test_attention_joint(ops, S, Lt, Ls, D, H):
+    """[self | latent | text | speaker] keys with the CFG mask pattern (reference model.py:246-261,
+    inference.py:474-475): branch 1 has no text, branch 2 no speaker; caches are shared, not copied."""
+    b = 3
+    Pl = 40
+    start_pos = 64
+    q = _rand((b, S, H, D), 41)
+    k_self, v_self = _rand((b, S, H, D), 42), _rand((b, S, H, D), 43)
+    k_lat, v_lat = _rand((b, Pl, H, D), 44), _rand((b, Pl, H, D), 45)
+    k_t, v_t = _rand((1, Lt, H, D), 46), _rand((1, Lt, H, D), 47)
+    k_s, v_s = _rand((1, Ls, H, D), 48), _rand((1, Ls, H, D), 49)
+    gate = torch.sigmoid(_rand((b, S, H * D), 50).float()).to(torch.bfloat16)
+    nt = max(1, Lt // 3)
+    tmask = torch.zeros(b, Lt, dtype=torch.bool, device="cuda")
+    tmask[0, :nt] = True
+    tmask[2, :nt] = True
+    smask = torch.zeros(b, Ls, dtype=torch.bool, device="cuda")
+    smask[0] = True
+    smask[1] = True
+    smask[0, Ls // 2] = False  # a hole, to exercise per-key masking
+    eff_t = torch.tensor([nt, 0, nt], dtype=torch.int32, device="cuda")
+    out = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
+    segs = [dict(k=k_self, v=v_self),
+            dict(k=k_lat, v=v_lat, pos_limit_mult=4, pos_limit=start_pos),
+            dict(k=k_t, v=v_t, mask=tmask, eff_len=eff_t),
+            dict(k=k_s, v=v_s, mask=smask)]
+    ops.attention(q, segs, out, gate=gate)
+    lat_mask = (torch.arange(Pl, device="cuda") * 4 < start_pos)[None, None].expand(b, S, Pl)
+    masks = [torch.ones(b, S, S, dtype=torch.bool, device="cuda"), lat_mask,
+             tmask[:, None].expand(b, S, Lt), smask[:, None].expand(b, S, Ls)]
+    ref = _sdpa_ref(q, [k_self, k_lat, k_t.expand(b, -1, -1, -1), k_s.expand(b, -1, -1, -1)],
+                    [v_self, v_lat, v_t.expand(b, -1, -1, -1), v_s.expand(b, -1, -1, -1)], masks, D ** -0.5)
+    ref = ref.reshape(b, S, H * D) * gate.float()
+    assert rel_l2(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("S,D,H,window", [(200, 128, 2, 0), (640, 64, 4, 128), (53, 128, 10, 0)])
+def test_attention_causal_window(ops, S, D, H, window):
+    """Causal (speaker/latent encoders, model.py:148-154) and window-limited causal (DAC post_module,
+    autoencoder.py:762-773) self attention."""
+    b = 2
+    q, k, v = _rand((b, S, H, D), 51), _rand((b, S, H, D), 52), _rand((b, S, H, D), 53)
+    out = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, [dict(k=k, v=v, causal=1, window=window)], out)
+    i = torch.arange(S, device="cuda")
+    m = i[None, :] <= i[:, None]
+    if window:
+        m = m & (i[None, :] > i[:, None] - window)
+    ref = _sdpa_ref(q, [k], [v], [m[None].expand(b, S, S)], D ** -0.5).reshape(b, S, H * D)
+    assert rel_l2(out, ref) < 6e-3
