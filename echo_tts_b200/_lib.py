@@ -44,6 +44,7 @@ class SamplerArgs(C.Structure):
         ("has_kv_scale", C.c_int), ("speaker_kv_scale", C.c_float), ("speaker_kv_max_layers", C.c_int),
         ("speaker_kv_min_t", C.c_float),
         ("sequence_length", C.c_int), ("round_t_to_bf16", C.c_int),
+        ("t_schedule", C.POINTER(C.c_float)),
     ]
 
 
@@ -70,6 +71,7 @@ class GemmDesc(C.Structure):
 class AttnSegment(C.Structure):
     _fields_ = [
         ("K", C.c_void_p), ("V", C.c_void_p), ("batch_stride", C.c_int64), ("row_stride", C.c_int64),
+        ("batch_mod", C.c_int),
         ("len", C.c_int), ("eff_len", C.c_void_p),
         ("mask", C.c_void_p), ("mask_ld", C.c_int), ("mask_stride", C.c_int),
         ("pos_limit_mult", C.c_int), ("pos_limit", C.c_int), ("causal", C.c_int), ("window", C.c_int),

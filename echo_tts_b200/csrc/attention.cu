@@ -13,6 +13,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "counters.h"
+
 namespace echo {
 
 typedef __nv_bfloat16 bf16;
@@ -118,8 +120,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const echo_attn_desc 
     const int n0 = e & 0xFFFFFF;
     int len = sg.len;
     if (sg.eff_len) { int el = sg.eff_len[b]; len = el < len ? el : len; }
-    const bf16* kb = static_cast<const bf16*>(sg.K) + (size_t)b * sg.batch_stride + (size_t)h * D;
-    const bf16* vb = static_cast<const bf16*>(sg.V) + (size_t)b * sg.batch_stride + (size_t)h * D;
+    const int cb = sg.batch_mod > 0 ? b % sg.batch_mod : b;
+    const bf16* kb = static_cast<const bf16*>(sg.K) + (size_t)cb * sg.batch_stride + (size_t)h * D;
+    const bf16* vb = static_cast<const bf16*>(sg.V) + (size_t)cb * sg.batch_stride + (size_t)h * D;
     bf16* dk = sK + stage * ATT_BN * D;
     bf16* dv = sV + stage * ATT_BN * D;
     for (int c = tid; c < ATT_BN * CH; c += ATT_THREADS) {
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const echo_attn_desc 
     if (tid < ATT_BN) {
       const int j = n0 + tid;
       bool ok = j < len;
-      if (ok && sg.mask) ok = sg.mask[(size_t)b * sg.mask_ld + (size_t)j * sg.mask_stride] != 0;
+      if (ok && sg.mask) ok = sg.mask[(size_t)cb * sg.mask_ld + (size_t)j * sg.mask_stride] != 0;
       if (ok && sg.pos_limit_mult > 0) ok = (j * sg.pos_limit_mult) < sg.pos_limit;
       sValid[stage * ATT_BN + tid] = ok ? 1 : 0;
     }
@@ -323,6 +326,7 @@ cudaError_t launch(const echo_attn_desc& d, cudaStream_t s) {
   }
   dim3 grid((d.S + ATT_BM - 1) / ATT_BM, d.H, d.b);
   attn_kernel<D><<<grid, ATT_THREADS, smem, s>>>(d);
+  count_launch();
   return cudaGetLastError();
 }
 

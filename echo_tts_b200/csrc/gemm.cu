@@ -5,6 +5,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "counters.h"
 #include "gemm_tc.cuh"
 
 namespace echo {
@@ -102,6 +103,7 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.batches * ((p.N + BN - 1) / BN);
   const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
   kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -1,0 +1,130 @@
+// Internal state behind the opaque echo_handle: packed weights, tables and a growable device workspace.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "echo_b200.h"
+#include "errors.h"
+
+namespace echo {
+
+typedef __nv_bfloat16 bf16;
+
+#define ECHO_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+      return ECHO_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+#define ECHO_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != ECHO_OK) return _rc; \
+  } while (0)
+
+struct EncoderLayerW {
+  bf16 *wqkvg, *wo, *w13, *w2;
+  float *q_norm, *k_norm, *attn_norm, *mlp_norm;
+};
+struct EncoderW {
+  int E = 0, heads = 0, inter = 0, layers = 0;
+  bf16* embed = nullptr;      // text only (vocab, E)
+  bf16* in_proj_w = nullptr;  // speaker / latent (E, patch*latent)
+  float* in_proj_b = nullptr;
+  float* final_norm = nullptr;
+  std::vector<EncoderLayerW> L;
+};
+struct BlockW {
+  bf16 *wqkvg, *wo, *w13, *w2, *wkv_text, *wkv_speaker, *wkv_latent;
+  float *q_norm, *k_norm;
+};
+
+struct RawTensor {  // DAC tensors are stashed as fp32 until finalize (weight-norm folding needs g and v together)
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct DacConvW {   // one (transposed) conv lowered to a tap GEMM
+  bf16* w = nullptr;  // [N][taps*Cin]
+  float* bias = nullptr;
+  int cin = 0, n = 0, taps = 0;
+};
+struct DacPostLayerW {
+  bf16 *wqkv, *wo, *w13, *w2;
+  float *attn_norm, *ffn_norm, *attn_gamma, *ffn_gamma;
+};
+struct DacUpW {
+  DacConvW convt;  // ConvTranspose k2 s2 as a 1-tap GEMM with N = 2*C
+  float *dw_w, *dw_b, *ln_w, *ln_b, *b1, *b2, *gamma;
+  bf16 *w1, *w2;
+};
+struct DacResUnitW {
+  float *alpha1, *alpha2;
+  DacConvW conv7, conv1;
+};
+struct DacStageW {
+  float* alpha_in;
+  DacConvW convt;
+  int stride = 0, cin = 0, cout = 0;
+  DacResUnitW ru[3];
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace echo
+
+struct echo_handle {
+  int device = 0;
+  int num_sms = 148;
+  std::vector<void*> owned;  // every cudaMalloc'ed weight block
+  std::map<std::string, echo::DevBuf> ws;
+
+  // ---- EchoDiT
+  bool dit_configured = false, dit_ready = false, has_latent = false;
+  echo_dit_config cfg{};
+  echo::EncoderW enc[3];  // text, speaker, latent
+  std::vector<echo::BlockW> blk;
+  echo::bf16 *ada_down = nullptr, *ada_up = nullptr;
+  float* ada_up_bias = nullptr;
+  echo::bf16 *cond_w0 = nullptr, *cond_w2 = nullptr, *cond_w4 = nullptr;
+  echo::bf16 *in_proj_w = nullptr, *out_proj_w = nullptr;
+  float *in_proj_b = nullptr, *out_norm = nullptr, *out_proj_b = nullptr;
+  float *rope_cos = nullptr, *rope_sin = nullptr, *temb_freqs = nullptr;
+  int rope_positions = 0;
+  std::set<std::string> got;
+
+  // ---- DAC
+  bool dac_configured = false, dac_ready = false;
+  echo_dac_config dcfg{};
+  std::map<std::string, echo::RawTensor> dac_raw;
+  std::vector<echo::DacPostLayerW> post;
+  float* post_final_norm = nullptr;
+  float *dac_rope_cos = nullptr, *dac_rope_sin = nullptr;
+  std::vector<echo::DacUpW> up;
+  echo::DacConvW dec_conv0;
+  std::vector<echo::DacStageW> stage;
+  float* final_alpha = nullptr;
+  float* final_w = nullptr;  // [7][C] fp32
+  float final_b = 0.f;
+
+  void* wsget(const char* name, size_t bytes, cudaStream_t s);
+  void* dalloc(size_t bytes);
+};
+
+namespace echo {
+// dac.cu
+int dac_set_weight(echo_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype,
+                   cudaStream_t s);
+}  // namespace echo

@@ -1,0 +1,150 @@
+"""Samplers with the reference's call signatures, executed by libecho_b200.so.
+
+`sample_euler_cfg_independent_guidances` mirrors reference inference.py:427-517 and
+`sample_blockwise_euler_cfg_independent_guidances` mirrors inference_blockwise.py:15-123: same positional and keyword
+arguments, same fp32 (B, S, 80) result, so `functools.partial(...)` objects built by handler._build_sample_fn
+(handler.py:426-443) work unchanged as the `sample_fn` of inference.sample_pipeline.
+
+The initial noise is drawn exactly as the reference draws it (`torch.Generator(device).manual_seed(seed)` +
+`torch.randn`, inference.py:457,477), so seeds stay compatible on the same device; the optional keyword-only `noise`
+lets tests inject a tensor (the CPU and CUDA generators differ).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from .model import B200EchoDiT, _stream, _u8
+
+
+def _args(model: B200EchoDiT, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor,
+          rescale_k, rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, sequence_length):
+    a = _lib.SamplerArgs()
+    a.num_steps = int(num_steps)
+    a.cfg_scale_text, a.cfg_scale_speaker = float(cfg_scale_text), float(cfg_scale_speaker)
+    a.cfg_min_t, a.cfg_max_t = float(cfg_min_t), float(cfg_max_t)
+    a.has_truncation = int(truncation_factor is not None)
+    a.truncation_factor = float(truncation_factor or 0.0)
+    a.has_rescale = int(rescale_k is not None and rescale_sigma is not None)
+    a.rescale_k, a.rescale_sigma = float(rescale_k or 0.0), float(rescale_sigma or 0.0)
+    a.has_kv_scale = int(speaker_kv_scale is not None)
+    if speaker_kv_scale is not None and speaker_kv_min_t is None:
+        # the reference evaluates `t_next < None` and raises (inference.py:511)
+        raise TypeError("'<' not supported between instances of 'Tensor' and 'NoneType' (speaker_kv_min_t is None)")
+    a.speaker_kv_scale = float(speaker_kv_scale or 0.0)
+    a.speaker_kv_max_layers = int(speaker_kv_max_layers) if speaker_kv_max_layers is not None else 0
+    a.speaker_kv_min_t = float(speaker_kv_min_t or 0.0)
+    a.sequence_length = int(sequence_length)
+    a.round_t_to_bf16 = int(model.round_t_to_model_dtype)
+    # the schedule is computed by torch on the model's device, exactly as the reference does (inference.py:459)
+    INIT_SCALE = 0.999
+    sched = (torch.linspace(1., 0., a.num_steps + 1, device=model.device) * INIT_SCALE).cpu().contiguous()
+    a._sched_keepalive = sched
+    a.t_schedule = C.cast(sched.data_ptr(), C.POINTER(C.c_float))
+    return a
+
+
+def _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask):
+    dev = model.device
+    spk = speaker_latent.to(dev, torch.bfloat16).contiguous()  # reference: speaker_latent.to(dtype) (inference.py:465)
+    sm = _u8(speaker_mask.to(dev))
+    ids = text_input_ids.to(dev, torch.int32).contiguous()
+    tm = _u8(text_mask.to(dev))
+    return spk, sm, ids, tm
+
+
+@torch.inference_mode()
+def sample_euler_cfg_independent_guidances(
+    model: B200EchoDiT,
+    speaker_latent: torch.Tensor,
+    speaker_mask: torch.Tensor,
+    text_input_ids: torch.Tensor,
+    text_mask: torch.Tensor,
+    rng_seed: int,
+    num_steps: int,
+    cfg_scale_text: float,
+    cfg_scale_speaker: float,
+    cfg_min_t: float,
+    cfg_max_t: float,
+    truncation_factor: Optional[float],
+    rescale_k: Optional[float],
+    rescale_sigma: Optional[float],
+    speaker_kv_scale: Optional[float],
+    speaker_kv_max_layers: Optional[int],
+    speaker_kv_min_t: Optional[float],
+    sequence_length: Optional[int] = None,
+    *,
+    noise: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    if sequence_length is None:
+        sequence_length = 640  # max sequence length during training (inference.py:449-450)
+    dev = model.device
+    B = text_input_ids.shape[0]
+    C_lat = model.cfg.latent_size
+    if noise is None:
+        rng = torch.Generator(device=dev).manual_seed(rng_seed)
+        noise = torch.randn((B, sequence_length, C_lat), device=dev, dtype=torch.float32, generator=rng)
+    noise = noise.to(dev, torch.float32).contiguous()
+    assert noise.shape == (B, sequence_length, C_lat)
+    a = _args(model, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor, rescale_k,
+              rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, sequence_length)
+    spk, sm, ids, tm = _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask)
+    out = torch.empty_like(noise)
+    with torch.cuda.device(dev):
+        _lib.check(model.lib.echo_sample_euler(model.h.ptr, C.byref(a), spk.data_ptr(), sm.data_ptr(), sm.shape[1],
+                                               ids.data_ptr(), tm.data_ptr(), tm.shape[1], B, noise.data_ptr(),
+                                               out.data_ptr(), _stream(dev)), "echo_sample_euler")
+    return out
+
+
+@torch.inference_mode()
+def sample_blockwise_euler_cfg_independent_guidances(
+    model: B200EchoDiT,
+    speaker_latent: torch.Tensor,
+    speaker_mask: torch.Tensor,
+    text_input_ids: torch.Tensor,
+    text_mask: torch.Tensor,
+    rng_seed: int,
+    block_sizes: List[int],
+    num_steps: int,
+    cfg_scale_text: float,
+    cfg_scale_speaker: float,
+    cfg_min_t: float,
+    cfg_max_t: float,
+    truncation_factor: Optional[float],
+    rescale_k: Optional[float],
+    rescale_sigma: Optional[float],
+    speaker_kv_scale: Optional[float],
+    speaker_kv_max_layers: Optional[int],
+    speaker_kv_min_t: Optional[float],
+    continuation_latent: Optional[torch.Tensor] = None,
+    *,
+    noise_blocks: Optional[List[torch.Tensor]] = None,
+) -> torch.Tensor:
+    dev = model.device
+    B = text_input_ids.shape[0]
+    C_lat = model.cfg.latent_size
+    if noise_blocks is None:  # one generator, one draw per block, in block order (inference_blockwise.py:42,76)
+        rng = torch.Generator(device=dev).manual_seed(rng_seed)
+        noise_blocks = [torch.randn((B, bs, C_lat), device=dev, dtype=torch.float32, generator=rng) for bs in block_sizes]
+    noise = torch.cat([n.to(dev, torch.float32).reshape(-1) for n in noise_blocks]).contiguous()
+    Lc = 0
+    cont = None
+    if continuation_latent is not None:
+        cont = continuation_latent.to(dev, torch.float32).contiguous()
+        Lc = cont.shape[1]
+    total = Lc + sum(block_sizes)
+    a = _args(model, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor, rescale_k,
+              rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, max(block_sizes))
+    spk, sm, ids, tm = _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask)
+    out = torch.empty(B, total, C_lat, device=dev, dtype=torch.float32)
+    blocks = (C.c_int * len(block_sizes))(*[int(b) for b in block_sizes])
+    with torch.cuda.device(dev):
+        _lib.check(model.lib.echo_sample_blockwise(
+            model.h.ptr, C.byref(a), blocks, len(block_sizes), spk.data_ptr(), sm.data_ptr(), sm.shape[1],
+            ids.data_ptr(), tm.data_ptr(), tm.shape[1], B, None if cont is None else cont.data_ptr(), Lc,
+            noise.data_ptr(), out.data_ptr(), _stream(dev)), "echo_sample_blockwise")
+    return out

@@ -86,6 +86,8 @@ typedef struct echo_sampler_args {
   int sequence_length;   /* latents to generate (<= 640 in the reference) */
   int round_t_to_bf16;   /* 1: t is rounded to bf16 before the timestep embedding, as the reference does when
                             model.dtype is bfloat16 (inference.py:489); 0: fp32 t */
+  const float* t_schedule; /* optional HOST array of num_steps+1 floats (torch.linspace(1,0,n+1)*0.999 as the caller's
+                              torch computes it, inference.py:459); NULL: the library's own fp32 closed form */
 } echo_sampler_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
@@ -170,6 +172,7 @@ int echo_op_gemm(const echo_gemm_desc* d, void* stream);
 typedef struct echo_attn_segment {
   const void* K; const void* V;   /* bf16, key j of batch b at K + (b*batch_stride + j*row_stride) elements */
   int64_t batch_stride; int64_t row_stride;
+  int batch_mod;                  /* >0: K/V/mask are indexed by (b % batch_mod): CFG branches share one cache */
   int len;                        /* keys in this segment */
   const int32_t* eff_len;         /* optional device (b): keys >= eff_len[batch] are all invalid (tile skipping) */
   const uint8_t* mask;            /* (batch, mask_ld) bool per key, or NULL = all valid */
