@@ -87,6 +87,11 @@ class AttnDesc(C.Structure):
     ]
 
 
+class ProfileReport(C.Structure):
+    _fields_ = [("launches", C.c_int64 * 3), ("ms", C.c_double * 3), ("flops", C.c_double * 3),
+                ("bytes", C.c_double * 3)]
+
+
 EPI_GENERIC, EPI_SWIGLU, EPI_QKV = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SNAKE, ACT_TANH, ACT_SIGMOID, ACT_SILU = 0, 1, 2, 3, 4, 5
 DTYPE_F32, DTYPE_BF16 = 0, 1
@@ -114,6 +119,8 @@ SYMBOLS = {
     "echo_dac_decode": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),
     "echo_dac_decode_zq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "echo_sample_euler_host": (C.c_int, [_P, C.POINTER(SamplerArgs), _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "echo_profile_start": (C.c_int, [_P]),
+    "echo_profile_stop": (C.c_int, [_P, C.POINTER(ProfileReport)]),
     "echo_op_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "echo_op_attention": (C.c_int, [C.POINTER(AttnDesc), _P]),
 }

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "counters.h"
+#include "profiler.h"
 
 namespace echo {
 
@@ -325,7 +326,10 @@ cudaError_t launch(const echo_attn_desc& d, cudaStream_t s) {
     configured = true;
   }
   dim3 grid((d.S + ATT_BM - 1) / ATT_BM, d.H, d.b);
-  attn_kernel<D><<<grid, ATT_THREADS, smem, s>>>(d);
+  {
+    ProfScope ps(PROF_ATTN, 0.0, 0.0, s);
+    attn_kernel<D><<<grid, ATT_THREADS, smem, s>>>(d);
+  }
   count_launch();
   return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 #include <unordered_map>
 
 #include "counters.h"
+#include "profiler.h"
 #include "gemm_tc.cuh"
 
 namespace echo {
@@ -102,7 +103,10 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
   }
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.batches * ((p.N + BN - 1) / BN);
   const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
-  kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
+  {
+    ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s);
+    kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
+  }
   count_launch();
   return cudaGetLastError();
 }

@@ -149,6 +149,16 @@ int echo_sample_euler_host(echo_handle* h, const echo_sampler_args* a, const flo
                            const uint8_t* text_mask_host, int Lt, int B, const float* noise_host,
                            float* x_out_host);
 
+/* ---- per-launch CUDA-event timing for the roofline report (bench.py); off unless started -------------------- */
+typedef struct echo_profile_report {   /* index 0: tcgen05 GEMM launches, 1: attention, 2: bandwidth-bound glue */
+  int64_t launches[3];
+  double ms[3];      /* summed CUDA-event durations on the launching stream */
+  double flops[3];   /* algorithmic FLOPs (2*M*N*K per GEMM) */
+  double bytes[3];   /* algorithmic bytes (glue kernels) */
+} echo_profile_report;
+int echo_profile_start(echo_handle* h);
+int echo_profile_stop(echo_handle* h, echo_profile_report* out); /* synchronises the device */
+
 /* ---- op-level entry points (used by the parity tests; same kernels the calls above launch) -------------- */
 typedef struct echo_gemm_desc {
   const void* A; int64_t lda; int64_t a_batch_stride; /* bf16 [batches][M][lda] */

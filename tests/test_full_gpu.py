@@ -1,0 +1,67 @@
+"""Full-size (echo-tts-base dimensions) GPU parity against goldens produced by the REAL reference in fp32 on CPU
+(oracle/pin_reference.py --full cfg1|cfg2): BASELINE.json configs[0] and configs[1].
+
+North-star tolerances: per-layer outputs rel-L2 <= 1e-2, final latents rel-L2 <= 2e-2 vs the fp32 reference.
+"""
+import os
+
+import pytest
+import torch
+
+from echo_tts_b200.config import DitConfig
+from echo_tts_b200.weights import iter_dit_weights
+from tests.util import GOLD, HANDLER_KNOBS, byte_tokens, gold, rel_l2
+
+pytestmark = pytest.mark.gpu
+PROMPT = "[S1] Hello from Echo-TTS on B200."
+
+
+@pytest.fixture(scope="module")
+def base_model():
+    from echo_tts_b200.model import B200EchoDiT
+    cfg = DitConfig.base()
+    model = B200EchoDiT(cfg, "cuda:0").load_state_dict(iter_dit_weights(cfg, 1234, include_latent=False))
+    model.round_t_to_model_dtype = False  # goldens are the fp32 reference (fp32 t)
+    return model
+
+
+def _inputs(which):
+    ids, mask = byte_tokens([PROMPT], 768)  # sample_pipeline pads to 768 (reference inference.py:327)
+    if which == "cfg1":
+        return ids, mask, torch.zeros(1, 4, 80), torch.zeros(1, 4, dtype=torch.bool)
+    spk = torch.randn(1, 212, 80, generator=torch.Generator().manual_seed(1))
+    return ids, mask, spk, torch.ones(1, 212, dtype=torch.bool)
+
+
+@pytest.mark.parametrize("which", ["cfg1", "cfg2"])
+def test_full_size_sampler_and_layers(base_model, which):
+    path = os.path.join(GOLD, f"dit_full_{which}.pt")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    from echo_tts_b200.sampler import sample_euler_cfg_independent_guidances as sample
+    g = gold(f"dit_full_{which}.pt")
+    model = base_model
+    ids, mask, spk, smask = _inputs(which)
+    noise = torch.randn((1, 640, 80), generator=torch.Generator().manual_seed(0))  # the reference's CPU draw, seed 0
+
+    # step 0 of the sampler = one forward with the CFG batch layout: per-layer outputs on three probe rows
+    kt = model.get_kv_cache_text(ids, mask)
+    ks = model.get_kv_cache_speaker(spk)
+    rep3 = lambda c: [(k.repeat(3, 1, 1, 1), v.repeat(3, 1, 1, 1)) for k, v in c]
+    mt = torch.cat([mask, torch.zeros_like(mask), mask])
+    ms = torch.cat([smask, smask, torch.zeros_like(smask)])
+    t0 = (torch.linspace(1., 0., 41) * 0.999)[0]
+    layers = []
+    v = model(x=noise.repeat(3, 1, 1), t=torch.ones(3) * t0, text_mask=mt, speaker_mask=ms, kv_cache_text=rep3(kt),
+              kv_cache_speaker=rep3(ks), layer_outputs=layers)
+    ref_rows = g["step0_layers_rows"]  # (24, 3, 3, 2048): rows 0, 319, 639 of each branch
+    errs = [rel_l2(l[:, [0, 319, 639]], ref_rows[i]) for i, l in enumerate(layers)]
+    print(which, "per-layer rel-L2 max", max(errs), "v", rel_l2(v, g["step0_v"]))
+    assert max(errs) < 1e-2, errs
+    assert rel_l2(v, g["step0_v"]) < 1e-2
+    del layers
+
+    out = sample(model, spk, smask, ids, mask, 0, sequence_length=640, noise=noise, **HANDLER_KNOBS)
+    e = rel_l2(out, g["latent"])
+    print(which, "final latent rel-L2", e)
+    assert tuple(out.shape) == (1, 640, 80) and e < 2e-2, e
