@@ -13,6 +13,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <cstdio>
+
 #include "counters.h"
 #include "profiler.h"
 
@@ -327,7 +329,9 @@ cudaError_t launch(const echo_attn_desc& d, cudaStream_t s) {
   }
   dim3 grid((d.S + ATT_BM - 1) / ATT_BM, d.H, d.b);
   {
-    ProfScope ps(PROF_ATTN, 0.0, 0.0, s);
+    char tag[64];
+    snprintf(tag, sizeof(tag), "attn D=%d b=%d S=%d H=%d nseg=%d", D, d.b, d.S, d.H, d.nseg);
+    ProfScope ps(PROF_ATTN, 0.0, 0.0, s, tag);
     attn_kernel<D><<<grid, ATT_THREADS, smem, s>>>(d);
   }
   count_launch();

@@ -71,6 +71,11 @@ __global__ void pack_convt_kernel(const float* __restrict__ v, const float* __re
   }
 }
 
+__global__ void alpha_inv_kernel(const float* __restrict__ a, float* __restrict__ inv, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[i] = 1.f / (a[i] + 1e-9f);
+}
+
 // final conv (1, C, 7) -> [7][C] fp32
 __global__ void pack_final_kernel(const float* __restrict__ v, const float* __restrict__ scale, float* __restrict__ out,
                                   int C, int k) {
@@ -267,6 +272,14 @@ struct Packer {
     cudaMemcpyAsync(d, r->p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s);
     return d;
   }
+  float* alpha(const std::string& k, int64_t n) {  // snake alpha + its reciprocal
+    float* a = vecf(k, n);
+    if (!a) return nullptr;
+    float* inv = (float*)h->dalloc((size_t)n * 4);
+    alpha_inv_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(a, inv, (int)n);
+    h->dac_alpha_inv[a] = inv;
+    return a;
+  }
   bf16* matb(const std::string& k, int64_t rows, int64_t cols, bf16* dst = nullptr, int64_t blk = 0, int64_t blk_stride = 0,
              int64_t blk_off = 0) {
     const RawTensor* r = get(k);
@@ -363,19 +376,19 @@ extern "C" int echo_dac_finalize(echo_handle* h, void* stream) {
     const std::string p = "decoder.model." + std::to_string(b + 1) + ".block";
     DacStageW& st = h->stage[b];
     st.stride = c.rates[b]; st.cin = ch; st.cout = ch / 2;
-    st.alpha_in = pk.vecf(p + ".0.alpha", st.cin);
+    st.alpha_in = pk.alpha(p + ".0.alpha", st.cin);
     st.convt = pk.convt(p + ".1", st.cin, st.cout, st.stride, 2, true);
     for (int u = 0; u < 3; ++u) {
       const std::string q = p + "." + std::to_string(u + 2) + ".block";
-      st.ru[u].alpha1 = pk.vecf(q + ".0.alpha", st.cout);
+      st.ru[u].alpha1 = pk.alpha(q + ".0.alpha", st.cout);
       st.ru[u].conv7 = pk.conv(q + ".1", st.cout, st.cout, 7, true);
-      st.ru[u].alpha2 = pk.vecf(q + ".2.alpha", st.cout);
+      st.ru[u].alpha2 = pk.alpha(q + ".2.alpha", st.cout);
       st.ru[u].conv1 = pk.conv(q + ".3", st.cout, st.cout, 1, true);
     }
     ch /= 2;
   }
   const int n = c.num_rates;
-  h->final_alpha = pk.vecf("decoder.model." + std::to_string(n + 1) + ".alpha", ch);
+  h->final_alpha = pk.alpha("decoder.model." + std::to_string(n + 1) + ".alpha", ch);
   {
     const std::string p = "decoder.model." + std::to_string(n + 2);
     const RawTensor* v = pk.get(p + ".conv.parametrizations.weight.original1");
@@ -552,7 +565,7 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
   // ---- decoder (autoencoder.py:984-998)
   {
     GemmCall g = conv_gemm(h->dec_conv0, cur, B, Tc, 1);
-    g.p.out_bf16 = nxt; g.p.ld_bf16 = h->dec_conv0.n; g.p.act = ACT_SNAKE; g.p.alpha = h->stage[0].alpha_in;
+    g.p.out_bf16 = nxt; g.p.ld_bf16 = h->dec_conv0.n; g.p.act = ACT_SNAKE; g.p.alpha = h->stage[0].alpha_in; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
     DAC_GEMM(g);
   }
   std::swap(cur, nxt);  // cur = snake(conv0 out), channels decoder_dim
@@ -561,7 +574,7 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
     {
       GemmCall g = convt_gemm(st.convt, cur, B, Tc, st.cout);
       g.p.out_f32 = xa; g.p.ld_f32 = st.stride * st.cout;
-      g.p.out_bf16 = nxt; g.p.ld_bf16 = st.stride * st.cout; g.p.act = ACT_SNAKE; g.p.alpha = st.ru[0].alpha1;
+      g.p.out_bf16 = nxt; g.p.ld_bf16 = st.stride * st.cout; g.p.act = ACT_SNAKE; g.p.alpha = st.ru[0].alpha1; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
       DAC_GEMM(g);
     }
     Tc *= st.stride;
@@ -571,7 +584,7 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
       const DacResUnitW& ru = st.ru[u];
       {
         GemmCall g = conv_gemm(ru.conv7, cur, B, Tc, dil[u]);
-        g.p.out_bf16 = hb; g.p.ld_bf16 = st.cout; g.p.act = ACT_SNAKE; g.p.alpha = ru.alpha2;
+        g.p.out_bf16 = hb; g.p.ld_bf16 = st.cout; g.p.act = ACT_SNAKE; g.p.alpha = ru.alpha2; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
         DAC_GEMM(g);
       }
       {
@@ -579,7 +592,7 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
                                   : (b + 1 < c.num_rates ? h->stage[b + 1].alpha_in : h->final_alpha);
         GemmCall g = conv_gemm(ru.conv1, hb, B, Tc, 1);
         g.p.resid = xa; g.p.out_f32 = xa; g.p.ld_f32 = st.cout;
-        g.p.out_bf16 = cur; g.p.ld_bf16 = st.cout; g.p.act = ACT_SNAKE; g.p.alpha = next_alpha;
+        g.p.out_bf16 = cur; g.p.ld_bf16 = st.cout; g.p.act = ACT_SNAKE; g.p.alpha = next_alpha; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
         DAC_GEMM(g);
       }
     }

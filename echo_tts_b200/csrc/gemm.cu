@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction (cached), tile-shape selection, launch.
 #include "gemm.h"
 
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -104,7 +105,11 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.batches * ((p.N + BN - 1) / BN);
   const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
   {
-    ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s);
+    char tag[96];
+    if (prof_enabled())
+      snprintf(tag, sizeof(tag), "gemm epi=%d M=%d x%d N=%d K=%d taps=%d bn=%d", EPI, p.M, p.batches, p.N, p.Kc, p.taps, BN);
+    else tag[0] = 0;
+    ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s, tag);
     kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
   }
   count_launch();

@@ -44,6 +44,7 @@ struct GemmParams {
   int ld_bf16;
   int act;             // ActMode applied to the bf16 output only
   const float* alpha;  // snake alpha [col_mod]
+  const float* alpha_inv;  // optional 1 / (alpha + 1e-9) [col_mod]
   int col_mod;
   // ---- EPI_SWIGLU: tile columns [0,BN/2) hold w1 rows, [BN/2,BN) the matching w3 rows;
   //      out_bf16[r, n0/2 + c] = silu(a) * b.     (uses out_bf16 / ld_bf16)

@@ -183,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
 
       if constexpr (EPI == EPI_GENERIC) {
-        const int cmod = p.col_mod > 0 ? p.col_mod : p.N;
+        const int cmod = p.col_mod > 0 ? p.col_mod : p.N;  // multiple of 32, so a 32-column chunk never wraps
         const size_t grow = (p.gate && p.rows_per_gate > 0) ? (row / p.rows_per_gate) * (size_t)p.gate_ld : 0;
         for (int ch = half; ch < BN / 32; ch += 2) {
           float v[32];
@@ -191,20 +191,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_wait_ld();
           const int c0 = n0 + ch * 32;
           if (row_ok && c0 < p.N) {
+            const int cb = c0 % cmod;  // one modulo per chunk (warp-uniform)
+            if (p.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int cm = (c0 + j) % cmod;
-              float x = v[j];
-              if (p.bias) x += __ldg(p.bias + bt * p.bias_bstride + cm);
-              x *= p.scale;
-              if (p.gate) x *= __ldg(p.gate + grow + cm);
-              v[j] = x;
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(bp + j);
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            }
+            if (p.scale != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+            }
+            if (p.gate) {
+              const float4* gp = reinterpret_cast<const float4*>(p.gate + grow + cb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 g4 = __ldg(gp + j);
+                v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+              }
             }
             if (p.resid) {
               const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ld_f32 + c0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                float4 r = rp[j];
+                const float4 r = rp[j];
                 v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
               }
             }
@@ -214,21 +226,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             if (p.out_bf16) {
-              uint32_t pk[16];
+              if (p.act == ACT_SNAKE) {
+                // snake(x) = x + sin^2(alpha x) / (alpha + 1e-9)   (autoencoder.py:96-102); the result is rounded to
+                // bf16, so the SFU sine (abs err ~|x| 2^-22) is far below the output quantum
+                const float4* ap = reinterpret_cast<const float4*>(p.alpha + cb);
+                const float4* ip = p.alpha_inv ? reinterpret_cast<const float4*>(p.alpha_inv + cb) : nullptr;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float a0 = v[2 * j], a1 = v[2 * j + 1];
-                if (p.act != ACT_NONE) {
-                  const float al0 = p.alpha ? __ldg(p.alpha + (c0 + 2 * j) % cmod) : 1.f;
-                  const float al1 = p.alpha ? __ldg(p.alpha + (c0 + 2 * j + 1) % cmod) : 1.f;
-                  a0 = apply_act(a0, p.act, al0);
-                  a1 = apply_act(a1, p.act, al1);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 a4 = __ldg(ap + j);
+                  float4 i4;
+                  if (ip) i4 = __ldg(ip + j);
+                  else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
+                  float s0 = __sinf(a4.x * v[4 * j]), s1 = __sinf(a4.y * v[4 * j + 1]);
+                  float s2 = __sinf(a4.z * v[4 * j + 2]), s3 = __sinf(a4.w * v[4 * j + 3]);
+                  v[4 * j] = fmaf(s0 * s0, i4.x, v[4 * j]);
+                  v[4 * j + 1] = fmaf(s1 * s1, i4.y, v[4 * j + 1]);
+                  v[4 * j + 2] = fmaf(s2 * s2, i4.z, v[4 * j + 2]);
+                  v[4 * j + 3] = fmaf(s3 * s3, i4.w, v[4 * j + 3]);
                 }
-                pk[j] = pack_bf16(a0, a1);
+              } else if (p.act != ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, 1.f);
               }
               uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_bf16 + c0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              for (int j = 0; j < 4; ++j)
+                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
             }
           }
         }
@@ -283,19 +307,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (row_ok) {
               const int cc = cs + ch * 32;
               if (sec.norm_w) {
+                const float4* wp = reinterpret_cast<const float4*>(sec.norm_w + cc);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = v[j] * rstd * __ldg(sec.norm_w + cc + j);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w4 = __ldg(wp + j);
+                  v[4 * j] *= rstd * w4.x; v[4 * j + 1] *= rstd * w4.y; v[4 * j + 2] *= rstd * w4.z; v[4 * j + 3] *= rstd * w4.w;
+                }
               }
               if (do_rope) {
                 const int pi0 = ((cc % p.head_dim) >> 1);
-                const float* cp = p.rope_cos + (size_t)pos * hd2 + pi0;
-                const float* sp = p.rope_sin + (size_t)pos * hd2 + pi0;
+                const float4* cp = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * hd2 + pi0);
+                const float4* sp = reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * hd2 + pi0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float c = __ldg(cp + j), s = __ldg(sp + j);
-                  const float a = v[2 * j], b = v[2 * j + 1];
-                  v[2 * j] = a * c - b * s;
-                  v[2 * j + 1] = a * s + b * c;
+                for (int j = 0; j < 4; ++j) {
+                  const float4 c4 = __ldg(cp + j), s4 = __ldg(sp + j);
+                  const float cc4[4] = {c4.x, c4.y, c4.z, c4.w}, ss4[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float a = v[8 * j + 2 * q], b = v[8 * j + 2 * q + 1];
+                    v[8 * j + 2 * q] = a * cc4[q] - b * ss4[q];
+                    v[8 * j + 2 * q + 1] = a * ss4[q] + b * cc4[q];
+                  }
                 }
               }
               uint32_t pk[16];

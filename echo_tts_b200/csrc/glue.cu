@@ -298,74 +298,74 @@ inline int grid_for(int64_t n, int threads = 256) {
 }  // namespace
 
 void embed_rows(const int32_t* ids, const bf16* table, float* X, int rows, int E, int vocab, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   embed_kernel<<<rows, 128, 0, s>>>(ids, table, X, E, vocab);
   count_launch();
 }
 void rmsnorm_affine(const float* X, bf16* out, const float* a, const float* c0, int rows, int W, int rows_per_group,
                     int64_t group_ld, float eps, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   rmsnorm_affine_kernel<<<rows, 256, 0, s>>>(X, out, a, c0, W, rows_per_group, group_ld, eps);
   count_launch();
 }
 void in_proj(const float* x, const bf16* W, const float* bias, float* X, int rows, int K, int D, int copies,
              cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   in_proj_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, W, bias, X, rows, K, D, copies);
   count_launch();
 }
 void out_norm_proj(const float* X, const float* wn, const bf16* Wout, const float* bias, float* v, int rows, int D,
                    int Nout, float eps, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   constexpr int RB = 4;
   out_norm_proj_kernel<RB><<<(rows + RB - 1) / RB, 256, RB * D * sizeof(float), s>>>(X, wn, Wout, bias, v, rows, D, Nout,
                                                                                     eps);
   count_launch();
 }
 void timestep_embed(const float* t, const float* freqs, bf16* emb, int n, int half, int round_t_bf16, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   timestep_embed_kernel<<<n, 128, 0, s>>>(t, freqs, emb, half, round_t_bf16);
   count_launch();
 }
 void adaln_prep(const float* cond, bf16* scond, int n, int D, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   adaln_prep_kernel<<<grid_for((int64_t)3 * n * D), 256, 0, s>>>(cond, scond, n, D);
   count_launch();
 }
 void adaln_finish(const float* up, const float* cond, float* mod, int n, int D, int Q, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   adaln_finish_kernel<<<grid_for((int64_t)3 * Q * n * D), 256, 0, s>>>(up, cond, mod, n, D, Q);
   count_launch();
 }
 void cfg_euler_update(float* x, const float* v, int64_t n, int has_cfg, float s_text, float s_spk, int has_rescale,
                       float one_minus_t, float ratio, float dt, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   cfg_euler_kernel<<<grid_for(n), 256, 0, s>>>(x, v, n, has_cfg, s_text, s_spk, has_rescale, one_minus_t, ratio, dt);
   count_launch();
 }
 void scale_bf16(bf16* p, int64_t n, float sc, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   scale_bf16_kernel<<<grid_for(n), 256, 0, s>>>(p, n, sc);
   count_launch();
 }
 void scale_copy_f32(const float* src, float* dst, int64_t n, float sc, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   scale_copy_kernel<<<grid_for(n), 256, 0, s>>>(src, dst, n, sc);
   count_launch();
 }
 void cast_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   cast_bf16_kernel<<<grid_for(n), 256, 0, s>>>(src, dst, n);
   count_launch();
 }
 void mask_eff_len(const uint8_t* mask, int32_t* eff, int n, int len, int ld, int stride, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   mask_eff_len_kernel<<<n, 256, 0, s>>>(mask, eff, len, ld, stride);
   count_launch();
 }
 void pack_rows(const void* src, int src_is_bf16, void* dst, int dst_is_bf16, int64_t rows, int64_t cols, int64_t dst_ld,
                int64_t blk, int64_t blk_stride, int64_t blk_off, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s);
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   pack_rows_kernel<<<grid_for(rows * cols), 256, 0, s>>>(src, src_is_bf16, dst, dst_is_bf16, rows, cols, dst_ld, blk,
                                                          blk_stride, blk_off);
   count_launch();

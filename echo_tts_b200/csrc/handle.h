@@ -118,6 +118,7 @@ struct echo_handle {
   float* final_alpha = nullptr;
   float* final_w = nullptr;  // [7][C] fp32
   float final_b = 0.f;
+  std::map<const float*, float*> dac_alpha_inv;  // snake alpha -> 1 / (alpha + 1e-9)
 
   void* wsget(const char* name, size_t bytes, cudaStream_t s);
   void* dalloc(size_t bytes);

@@ -8,13 +8,13 @@
 namespace echo {
 enum ProfClass : int { PROF_GEMM = 0, PROF_ATTN = 1, PROF_GLUE = 2, PROF_NCLASS = 3 };
 bool prof_enabled();
-void prof_begin(int cls, double flops, double bytes, cudaStream_t s);
+void prof_begin(int cls, double flops, double bytes, cudaStream_t s, const char* tag);
 void prof_end(cudaStream_t s);
 struct ProfScope {
   cudaStream_t s;
   bool on;
-  ProfScope(int cls, double flops, double bytes, cudaStream_t st) : s(st), on(prof_enabled()) {
-    if (on) prof_begin(cls, flops, bytes, s);
+  ProfScope(int cls, double flops, double bytes, cudaStream_t st, const char* tag = "") : s(st), on(prof_enabled()) {
+    if (on) prof_begin(cls, flops, bytes, s, tag);
   }
   ~ProfScope() {
     if (on) prof_end(s);
