@@ -33,6 +33,7 @@ extern "C" int echo_op_gemm(const echo_gemm_desc* d, void* stream) {
   c.ldb = d->ldb;
   c.b_rows = d->b_rows;
   c.bn = d->bn;
+  c.cg = d->cg;
   GemmParams& p = c.p;
   p.M = d->M; p.N = d->N; p.Kc = d->Kc; p.batches = d->batches; p.taps = d->taps;
   for (int i = 0; i < 8; ++i) p.tap_shift[i] = d->tap_shift[i];
@@ -53,6 +54,8 @@ extern "C" int echo_op_gemm(const echo_gemm_desc* d, void* stream) {
   p.head_dim = d->head_dim ? d->head_dim : 128;
   p.pos_period = d->pos_period; p.pos_offset = d->pos_offset; p.pos_mult = d->pos_mult ? d->pos_mult : 1;
   p.eps = d->eps;
+  p.trace = d->trace;
+  p.dbg = d->dbg;
   cudaError_t e = gemm_launch(c, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) {
     set_error("echo_op_gemm: %s (M=%d N=%d Kc=%d taps=%d epi=%d)", cudaGetErrorString(e), d->M, d->N, d->Kc, d->taps,

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction (cached), tile-shape selection, launch.
 #include "gemm.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -92,53 +93,85 @@ int gemm_num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int BK, int ATOMS, int EPI>
+template <int BN, int BK, int ATOMS, int EPI, int CG>
 static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
   static bool configured = false;
-  constexpr int SMEM = gemm_smem_bytes(BN, BK, ATOMS);
-  auto kern = gemm_tc_kernel<BN, BK, ATOMS, EPI>;
+  constexpr int SMEM = gemm_smem_bytes(BN, BK, ATOMS, CG);
+  auto kern = gemm_tc_kernel<BN, BK, ATOMS, EPI, CG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * p.batches * ((p.N + BN - 1) / BN);
-  const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
+  const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * p.batches * ((p.N + BN - 1) / BN);
+  const int slots = gemm_num_sms() / CG;
+  const int grid = (tiles < slots ? tiles : slots) * CG;
+  cudaError_t err;
   {
     char tag[96];
     if (prof_enabled())
-      snprintf(tag, sizeof(tag), "gemm epi=%d M=%d x%d N=%d K=%d taps=%d bn=%d", EPI, p.M, p.batches, p.N, p.Kc, p.taps, BN);
+      snprintf(tag, sizeof(tag), "gemm epi=%d M=%d x%d N=%d K=%d taps=%d bn=%d cg=%d", EPI, p.M, p.batches, p.N, p.Kc,
+               p.taps, BN, CG);
     else tag[0] = 0;
     ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s, tag);
-    kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
+    if constexpr (CG == 1) {
+      kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
+      err = cudaGetLastError();
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = SMEM;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      err = cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
+    }
   }
   count_launch();
-  return cudaGetLastError();
+  return err;
 }
 
-static int pick_bn(const GemmCall& c) {
+// Tile-shape choice. Cost model per K=16 slice, in SM cycles: the MMA needs BN/2 cycles (128 x BN per CTA), operand
+// ingest (~64 B/clk/SM) needs (128 + BN/CG)/2, whichever is larger; times the number of waves over the 148 SMs.
+struct TileCfg { int bn, cg; };
+static TileCfg pick_cfg(const GemmCall& c) {
   const GemmParams& p = c.p;
-  if (p.epi != EPI_GENERIC) return 256;
-  if (c.bn) return c.bn;
-  if (p.N % 64 != 0) {
-    if (p.N % 96 == 0 && p.N <= 192) return p.N;  // 96 or 192
-    return 0;
-  }
-  if (p.N == 192 || p.N == 384) return 192;
   const int sms = gemm_num_sms();
-  const long mt = (long)((p.M + GEMM_BM - 1) / GEMM_BM) * p.batches;
-  const int cand[3] = {256, 128, 64};
-  const double mma_eff[3] = {1.0, 0.85, 0.6};
-  double best = -1;
-  int best_bn = 0;
-  for (int i = 0; i < 3; ++i) {
-    if (p.N % cand[i] != 0 && !(p.N > cand[i] && i == 2)) continue;
-    const long tiles = mt * ((p.N + cand[i] - 1) / cand[i]);
-    const long waves = (tiles + sms - 1) / sms;
-    const double eff = (double)tiles / (double)(waves * sms) * mma_eff[i];
-    if (eff > best + 1e-9) { best = eff; best_bn = cand[i]; }
+  // CTA pairs are opt-in (cg == 2): measured on B200 they lose 3-8 % at the DiT shapes (M = 640 / 1920 wastes half a
+  // pair tile per column and the wave count does not drop), see profiles/r01_gemm_cta_pair_vs_single.txt
+  const bool allow_pair = c.cg == 2 && (p.N % 128 == 0);
+  auto cost = [&](int bn, int cg) -> double {
+    const long units = (long)((p.M + 128 * cg - 1) / (128 * cg)) * p.batches * ((p.N + bn - 1) / bn);
+    const long slots = sms / cg;
+    const long waves = (units + slots - 1) / slots;
+    const double per = std::max(bn / 2.0, (128.0 + bn / (double)cg) / 2.0);
+    return waves * per + 12.0;  // small constant: prefer fewer, larger tiles on ties
+  };
+  if (p.epi != EPI_GENERIC) {
+    if (c.cg == 2 || (allow_pair && cost(256, 2) < cost(256, 1))) return {256, 2};
+    return {256, 1};
   }
-  return best_bn;
+  if (c.bn) return {c.bn, (c.cg == 2 && (c.bn == 256 || c.bn == 128)) ? 2 : 1};
+  if (p.N % 64 != 0) {
+    if (p.N % 96 == 0 && p.N <= 192) return {p.N, 1};  // 96 or 192
+    return {0, 1};
+  }
+  if (p.N == 192 || p.N == 384) return {192, 1};
+  TileCfg best = {0, 1};
+  double bc = 1e30;
+  const int cand[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    if (p.N % cand[i] != 0) continue;
+    for (int cg = 1; cg <= 2; ++cg) {
+      if (cg == 2 && (!allow_pair || cand[i] == 64)) continue;
+      const double cs = cost(cand[i], cg);
+      if (cs < bc - 1e-9) { bc = cs; best = {cand[i], cg}; }
+    }
+  }
+  return best;
 }
 
 cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
@@ -152,7 +185,8 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   if (p.N % 32 != 0 || (c.lda % 8) != 0 || (c.ldb % 8) != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15)) return cudaErrorInvalidValue;
 
-  const int bn = pick_bn(c);
+  const TileCfg tc = pick_cfg(c);
+  const int bn = tc.bn, cg = tc.cg;
   if (bn == 0) return cudaErrorInvalidValue;
   const bool small_k = (p.Kc % 64 != 0) && (p.Kc % 96 == 0) && bn == 96;  // DAC last stage: 96 channels / tap
   const int bk = small_k ? 32 : 64;
@@ -164,23 +198,23 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
                       (uint64_t)a_bstride * 2, bk, GEMM_BM, bk * 2))
     return cudaErrorInvalidValue;
   const uint64_t b_rows = c.b_rows ? (uint64_t)c.b_rows : (uint64_t)p.N * (p.b_batch_rows ? p.batches : 1);
-  if (!get_tensor_map(&mb, c.B, 2, (uint64_t)p.taps * p.Kc, b_rows, 1, (uint64_t)c.ldb * 2, 0, bk, bn, bk * 2))
+  if (!get_tensor_map(&mb, c.B, 2, (uint64_t)p.taps * p.Kc, b_rows, 1, (uint64_t)c.ldb * 2, 0, bk, bn / cg, bk * 2))
     return cudaErrorInvalidValue;
 
   switch (p.epi) {
     case EPI_SWIGLU:
       if (p.N % 256 != 0) return cudaErrorInvalidValue;
-      return launch_inst<256, 64, 1, EPI_SWIGLU>(ma, mb, p, s);
+      return cg == 2 ? launch_inst<256, 64, 1, EPI_SWIGLU, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_SWIGLU, 1>(ma, mb, p, s);
     case EPI_QKV:
       if (p.sec_width % 128 != 0 || p.N % 128 != 0) return cudaErrorInvalidValue;
-      return launch_inst<256, 64, 1, EPI_QKV>(ma, mb, p, s);
+      return cg == 2 ? launch_inst<256, 64, 1, EPI_QKV, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_QKV, 1>(ma, mb, p, s);
     case EPI_GENERIC:
-      if (small_k) return launch_inst<96, 32, 3, EPI_GENERIC>(ma, mb, p, s);
+      if (small_k) return launch_inst<96, 32, 3, EPI_GENERIC, 1>(ma, mb, p, s);
       switch (bn) {
-        case 256: return launch_inst<256, 64, 1, EPI_GENERIC>(ma, mb, p, s);
-        case 192: return launch_inst<192, 64, 1, EPI_GENERIC>(ma, mb, p, s);
-        case 128: return launch_inst<128, 64, 1, EPI_GENERIC>(ma, mb, p, s);
-        case 64: return launch_inst<64, 64, 1, EPI_GENERIC>(ma, mb, p, s);
+        case 256: return cg == 2 ? launch_inst<256, 64, 1, EPI_GENERIC, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_GENERIC, 1>(ma, mb, p, s);
+        case 192: return launch_inst<192, 64, 1, EPI_GENERIC, 1>(ma, mb, p, s);
+        case 128: return cg == 2 ? launch_inst<128, 64, 1, EPI_GENERIC, 2>(ma, mb, p, s) : launch_inst<128, 64, 1, EPI_GENERIC, 1>(ma, mb, p, s);
+        case 64: return launch_inst<64, 64, 1, EPI_GENERIC, 1>(ma, mb, p, s);
         default: return cudaErrorInvalidValue;
       }
     default: return cudaErrorInvalidValue;

@@ -58,6 +58,9 @@ struct GemmParams {
   int pos_offset;
   int pos_mult;
   float eps;
+  // optional debug trace: 8 clock64 stamps per CTA (see gemm_tc.cuh); null in production
+  long long* trace;
+  int dbg;  // tuning only: bit0 skip resid load, bit1 skip global stores, bit2 skip gate, bit3 skip whole chunk body
 };
 
 struct GemmCall {
@@ -69,6 +72,7 @@ struct GemmCall {
   int64_t b_rows;  // 0 -> N (or N*batches when b_batch_rows is set)
   GemmParams p;
   int bn;  // tile N override (0 = auto)
+  int cg;  // CTA-group override: 0 = auto, 1 = single CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2)
 };
 
 cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s);

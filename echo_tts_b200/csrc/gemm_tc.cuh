@@ -20,26 +20,42 @@
 
 namespace echo {
 
+#ifndef ECHO_EPI_UNROLL
+#define ECHO_EPI_UNROLL 1   // 1: fully unroll the per-warp chunk loops of the SwiGLU / QKV epilogues (more ILP)
+#endif
+#ifndef ECHO_MAX_STAGES
+#define ECHO_MAX_STAGES 8
+#endif
+#if ECHO_EPI_UNROLL
+#define ECHO_CHUNK_UNROLL _Pragma("unroll")
+#else
+#define ECHO_CHUNK_UNROLL _Pragma("unroll 1")
+#endif
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
 constexpr int GEMM_EPI_WARPS = 8;
 
 __host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
-__host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS) { return (GEMM_BM + BN) * BK * 2 * ATOMS; }
-__host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS) {
-  int s = (200 * 1024) / gemm_stage_bytes(BN, BK, ATOMS);
-  return s > 8 ? 8 : s;
+// per-CTA bytes of one pipeline stage; with a CTA pair (CG = 2) each CTA holds its 128 A rows and HALF of the B rows
+__host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS, int CG) {
+  return (GEMM_BM + BN / CG) * BK * 2 * ATOMS;
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int BN, int BK, int ATOMS) {
-  return gemm_stages(BN, BK, ATOMS) * gemm_stage_bytes(BN, BK, ATOMS) + 1024 /*align slack*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS, int CG) {
+  int s = (227 * 1024 - 1024 - 256) / gemm_stage_bytes(BN, BK, ATOMS, CG);
+  return s > ECHO_MAX_STAGES ? ECHO_MAX_STAGES : s;
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int BN, int BK, int ATOMS, int CG) {
+  return gemm_stages(BN, BK, ATOMS, CG) * gemm_stage_bytes(BN, BK, ATOMS, CG) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-ECHO_DEVICE float apply_act(float v, int act, float alpha) {
+// Rare activations (cond_module SiLU, ConvNeXt GELU, ...). Deliberately NOT inlined: inlining erff/tanhf 32x per
+// chunk blew the generic kernel up to 1 MB of SASS and the epilogue became instruction-fetch bound.
+__device__ __noinline__ float apply_act(float v, int act, float alpha) {
   switch (act) {
     case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
     case ACT_SNAKE: {
-      float s = sinf(alpha * v);
+      float s = __sinf(alpha * v);
       return v + s * s / (alpha + 1e-9f);
     }
     case ACT_TANH: return tanhf(v);
@@ -49,12 +65,16 @@ ECHO_DEVICE float apply_act(float v, int act, float alpha) {
   }
 }
 
-template <int BN, int BK, int ATOMS, int EPI>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
+// each CTA stages its own 128 A rows and half of the B rows, the even CTA issues M=256 MMAs that read both CTAs'
+// shared memory and write both CTAs' TMEM, so the per-SM operand ingest drops from (128+BN) to (128+BN/2) rows per K.
+template <int BN, int BK, int ATOMS, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  constexpr int STAGES = gemm_stages(BN, BK, ATOMS);
+  constexpr int STAGES = gemm_stages(BN, BK, ATOMS, CG);
   constexpr int A_ATOM = GEMM_BM * BK * 2;
-  constexpr int B_ATOM = BN * BK * 2;
+  constexpr int BNH = BN / CG;  // B rows staged by this CTA
+  constexpr int B_ATOM = BNH * BK * 2;
   constexpr int STAGE_BYTES = (A_ATOM + B_ATOM) * ATOMS;
   constexpr int ACC_STRIDE = gemm_acc_stride(BN);
   constexpr int ROW_BYTES = BK * 2;
@@ -73,8 +93,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* trace = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
 
-  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  uint32_t cta_rank = 0;
+  if constexpr (CG == 2) cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
+  const int tiles_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * p.batches * tiles_n;
   const int kb_per_tap = (p.Kc + BK * ATOMS - 1) / (BK * ATOMS);
@@ -91,51 +117,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * CG);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<2 * ACC_STRIDE>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair<2 * ACC_STRIDE>(tmem_slot);
+    else tmem_alloc<2 * ACC_STRIDE>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int mt = tile % tiles_m;
         const int rest = tile / tiles_m;
         const int bt = rest % p.batches;
         const int nt = rest / p.batches;
-        const int m0 = mt * GEMM_BM, n0 = nt * BN;
+        const int m0 = (mt * CG + (int)cta_rank) * GEMM_BM, n0 = nt * BN + (int)cta_rank * BNH;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / kb_per_tap;
           const int kc0 = (kb - tap * kb_per_tap) * (BK * ATOMS);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (leader) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);  // counts both CTAs' bytes
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_ATOM * ATOMS;
 #pragma unroll
           for (int a = 0; a < ATOMS; ++a) {
-            tma_load_3d(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
-            tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+            if constexpr (CG == 2) {
+              tma_load_3d_pair(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
+              tma_load_2d_pair(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+            } else {
+              tma_load_3d(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
+              tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+            }
           }
+          if (trace && kb == 0 && tile == tile0) trace[2] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -143,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (trace && kb == 0 && tile == tile0) trace[3] = clock64();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_ATOM * ATOMS;
 #pragma unroll
@@ -152,13 +190,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 bf16 (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-              tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | a | k) != 0 ? 1u : 0u);
+              if constexpr (CG == 2) tc_mma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | a | k) != 0 ? 1u : 0u);
+              else tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | a | k) != 0 ? 1u : 0u);
             }
           }
-          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+          if constexpr (CG == 2) tc_commit_pair(&empty_bar[stage]);
+          else tc_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if constexpr (CG == 2) tc_commit_pair(&tfull_bar[as]);
+        else tc_commit(&tfull_bar[as]);
+        if (trace) trace[4] = clock64();
       }
     }
   } else if (warp >= GEMM_EPI_WARP0) {
@@ -166,113 +210,152 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - GEMM_EPI_WARP0;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int half = ew >> 2;      // which half of the column chunks
-    const int r_in_tile = quarter * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int mt = tile % tiles_m;
       const int rest = tile / tiles_m;
       const int bt = rest % p.batches;
       const int nt = rest / p.batches;
-      const int m = mt * GEMM_BM + r_in_tile;
+      const int mbase = (mt * CG + (int)cta_rank) * GEMM_BM + quarter * 32;  // first row of this warp's 32-row slab
+      const int m = mbase + lane;
       const int n0 = nt * BN;
       const bool row_ok = m < p.M;
       const size_t row = (size_t)bt * p.M + m;
       const int as = it & 1;
-      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
-      tc_fence_after();
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+      if constexpr (EPI != EPI_GENERIC) {
+        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        tc_fence_after();
+        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) trace[5] = clock64();
+      }
+
+      // store of one 32-column bf16 chunk held as 16 packed words per thread (row = lane): 64 contiguous bytes / thread.
+      // (A shared-memory transpose to coalesce these was measured SLOWER: the stores are fire-and-forget and the
+      // staging traffic competes with the UMMA operand reads of the next tile.)
+      auto store_bf16_chunk = [&](const uint32_t* pk, bf16* out, size_t ld, int col0) {
+        if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(out + row * ld + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+      };
 
       if constexpr (EPI == EPI_GENERIC) {
+        // Software-pipelined: the fp32 residual of chunk c+1 is requested while chunk c is processed, and the
+        // first chunk's residual before the accumulator barrier, so the epilogue is not a chain of exposed latencies.
+        constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (this warp takes ch = half, half + 2, ...)
         const int cmod = p.col_mod > 0 ? p.col_mod : p.N;  // multiple of 32, so a 32-column chunk never wraps
-        const size_t grow = (p.gate && p.rows_per_gate > 0) ? (row / p.rows_per_gate) * (size_t)p.gate_ld : 0;
-        for (int ch = half; ch < BN / 32; ch += 2) {
-          float v[32];
-          tc_ld_32x32(tbase + ch * 32, v);
-          tc_wait_ld();
+        const bool has_res = p.resid != nullptr && row_ok;
+        float4 rcur[8], rnext[8];
+        auto load_resid = [&](int ch, float4* r) {
           const int c0 = n0 + ch * 32;
-          if (row_ok && c0 < p.N) {
-            const int cb = c0 % cmod;  // one modulo per chunk (warp-uniform)
-            if (p.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb);
+          if (has_res && ch < BN / 32 && c0 < p.N) {
+            const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ld_f32 + c0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(bp + j);
-                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-              }
-            }
-            if (p.scale != 1.f) {
+            for (int j = 0; j < 8; ++j) r[j] = rp[j];
+          }
+        };
+        load_resid(half, rcur);
+        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        tc_fence_after();
+        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) trace[5] = clock64();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= p.scale;
-            }
-            if (p.gate) {
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int ch = half + 2 * ci;
+          if (ch < BN / 32) {
+            float v[32];
+            tc_ld_32x32(tbase + ch * 32, v);
+            load_resid(ch + 2, rnext);
+            const int c0 = n0 + ch * 32;
+            const bool col_ok = c0 < p.N;  // warp-uniform
+            const int cb = col_ok ? c0 % cmod : 0;  // one modulo per chunk
+            float4 g4[8];
+            if (p.gate && col_ok) {
+              const size_t grow = (p.rows_per_gate > 0) ? (row / p.rows_per_gate) * (size_t)p.gate_ld : 0;
               const float4* gp = reinterpret_cast<const float4*>(p.gate + grow + cb);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 g4 = __ldg(gp + j);
-                v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
-              }
+              for (int j = 0; j < 8; ++j) g4[j] = __ldg(gp + j);
             }
-            if (p.resid) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ld_f32 + c0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = rp[j];
-                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-              }
-            }
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + c0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (p.out_bf16) {
-              if (p.act == ACT_SNAKE) {
-                // snake(x) = x + sin^2(alpha x) / (alpha + 1e-9)   (autoencoder.py:96-102); the result is rounded to
-                // bf16, so the SFU sine (abs err ~|x| 2^-22) is far below the output quantum
-                const float4* ap = reinterpret_cast<const float4*>(p.alpha + cb);
-                const float4* ip = p.alpha_inv ? reinterpret_cast<const float4*>(p.alpha_inv + cb) : nullptr;
+            tc_wait_ld();
+            if (col_ok && !(p.dbg & 8)) {
+              if (p.bias) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float4 a4 = __ldg(ap + j);
-                  float4 i4;
-                  if (ip) i4 = __ldg(ip + j);
-                  else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
-                  float s0 = __sinf(a4.x * v[4 * j]), s1 = __sinf(a4.y * v[4 * j + 1]);
-                  float s2 = __sinf(a4.z * v[4 * j + 2]), s3 = __sinf(a4.w * v[4 * j + 3]);
-                  v[4 * j] = fmaf(s0 * s0, i4.x, v[4 * j]);
-                  v[4 * j + 1] = fmaf(s1 * s1, i4.y, v[4 * j + 1]);
-                  v[4 * j + 2] = fmaf(s2 * s2, i4.z, v[4 * j + 2]);
-                  v[4 * j + 3] = fmaf(s3 * s3, i4.w, v[4 * j + 3]);
+                  const float4 b4 = __ldg(bp + j);
+                  v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
                 }
-              } else if (p.act != ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, 1.f);
               }
-              uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_bf16 + c0);
+              if (p.scale != 1.f) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+              }
+              if (p.gate) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] *= g4[j].x; v[4 * j + 1] *= g4[j].y; v[4 * j + 2] *= g4[j].z; v[4 * j + 3] *= g4[j].w;
+                }
+              }
+              if (row_ok) {
+                if (p.resid) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    v[4 * j] += rcur[j].x; v[4 * j + 1] += rcur[j].y; v[4 * j + 2] += rcur[j].z; v[4 * j + 3] += rcur[j].w;
+                  }
+                }
+                if (p.out_f32) {
+                  float4* op = reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + c0);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (p.out_bf16) {
+                  if (p.act == ACT_SNAKE) {
+                    // snake(x) = x + sin^2(alpha x) / (alpha + 1e-9)   (autoencoder.py:96-102); the result is rounded
+                    // to bf16, so the SFU sine (abs err ~|x| 2^-22) is far below the output quantum
+                    const float4* ap = reinterpret_cast<const float4*>(p.alpha + cb);
+                    const float4* ip = p.alpha_inv ? reinterpret_cast<const float4*>(p.alpha_inv + cb) : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float4 a4 = __ldg(ap + j);
+                      float4 i4;
+                      if (ip) i4 = __ldg(ip + j);
+                      else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
+                      const float s0 = __sinf(a4.x * v[4 * j]), s1 = __sinf(a4.y * v[4 * j + 1]);
+                      const float s2 = __sinf(a4.z * v[4 * j + 2]), s3 = __sinf(a4.w * v[4 * j + 3]);
+                      v[4 * j] = fmaf(s0 * s0, i4.x, v[4 * j]);
+                      v[4 * j + 1] = fmaf(s1 * s1, i4.y, v[4 * j + 1]);
+                      v[4 * j + 2] = fmaf(s2 * s2, i4.z, v[4 * j + 2]);
+                      v[4 * j + 3] = fmaf(s3 * s3, i4.w, v[4 * j + 3]);
+                    }
+                  } else if (p.act != ACT_NONE) {
+#pragma unroll 4
+                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, 1.f);
+                  }
+                  uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_bf16 + c0);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                }
+              }
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
           }
         }
       } else if constexpr (EPI == EPI_SWIGLU) {
         constexpr int HALF_CH = BN / 64;  // chunks in the w1 half
+ECHO_CHUNK_UNROLL
         for (int ch = half; ch < HALF_CH; ch += 2) {
           float a[32], b[32];
           tc_ld_32x32(tbase + ch * 32, a);
           tc_ld_32x32(tbase + (ch + HALF_CH) * 32, b);
           tc_wait_ld();
-          const int c0 = n0 / 2 + ch * 32;
-          if (row_ok) {
-            uint32_t pk[16];
+          uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              pk[j] = pack_bf16(silu_f(a[2 * j]) * b[2 * j], silu_f(a[2 * j + 1]) * b[2 * j + 1]);
-            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_bf16 + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          for (int j = 0; j < 16; ++j)
+            pk[j] = pack_bf16(silu_f(a[2 * j]) * b[2 * j], silu_f(a[2 * j + 1]) * b[2 * j + 1]);
+          store_bf16_chunk(pk, p.out_bf16, (size_t)p.ld_bf16, n0 / 2 + ch * 32);
         }
       } else {  // EPI_QKV: this thread owns one row x 128 contiguous columns (group `half` of the 256-wide tile)
         static_assert(EPI != EPI_QKV || BN == 256, "QKV epilogue needs BN == 256");
@@ -286,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (sec.norm_w) {
             // RMSNorm over head_dim columns (reference model.py:99-104); head_dim == 128 whenever norm_w is set
             float ss = 0.f;
-#pragma unroll
+ECHO_CHUNK_UNROLL
             for (int ch = 0; ch < 4; ++ch) {
               float v[32];
               tc_ld_32x32(tbase + (half * 4 + ch) * 32, v);
@@ -299,13 +382,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool do_rope = grp < sec.rope_heads;
           const int pos = p.pos_offset + p.pos_mult * (int)(row % (size_t)p.pos_period);
           const int hd2 = p.head_dim >> 1;
-#pragma unroll
+ECHO_CHUNK_UNROLL
           for (int ch = 0; ch < 4; ++ch) {
             float v[32];
             tc_ld_32x32(tbase + (half * 4 + ch) * 32, v);
             tc_wait_ld();
+            const int cc = cs + ch * 32;
             if (row_ok) {
-              const int cc = cs + ch * 32;
               if (sec.norm_w) {
                 const float4* wp = reinterpret_cast<const float4*>(sec.norm_w + cc);
 #pragma unroll
@@ -330,29 +413,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                 }
               }
-              uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float a0 = v[2 * j], a1 = v[2 * j + 1];
-                if (sec.sigmoid) { a0 = sigmoid_f(a0); a1 = sigmoid_f(a1); }
-                pk[j] = pack_bf16(a0, a1);
-              }
-              uint4* op = reinterpret_cast<uint4*>(sec.out + row * p.sec_width + cc);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a0 = v[2 * j], a1 = v[2 * j + 1];
+              if (sec.sigmoid) { a0 = sigmoid_f(a0); a1 = sigmoid_f(a1); }
+              pk[j] = pack_bf16(a0, a1);
+            }
+            store_bf16_chunk(pk, sec.out, (size_t)p.sec_width, cc);
           }
         }
       }
+      if (trace && warp == GEMM_EPI_WARP0 && lane == 0) trace[6] = clock64();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_pair_leader(&tempty_bar[as]);  // the MMA issuer lives in the even CTA
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<2 * ACC_STRIDE>(tmem_base);
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may free TMEM / exit while the peer still uses it
+  else __syncthreads();
+  if (trace && threadIdx.x == 0) trace[7] = clock64();
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_dealloc_pair<2 * ACC_STRIDE>(tmem_base);
+    else tmem_dealloc<2 * ACC_STRIDE>(tmem_base);
+  }
 }
 
 }  // namespace echo

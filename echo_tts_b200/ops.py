@@ -23,7 +23,7 @@ def _stream() -> int:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence[int] = (0,), bias=None,
          scale: float = 1.0, gate=None, rows_per_gate: int = 0, resid=None, out_f32=None, out_bf16=None,
-         act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0) -> None:
+         act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0, cg: int = 0, trace=None, dbg: int = 0) -> None:
     """out = epilogue(sum_taps a[rows + shift] @ w[:, tap*Kc:(tap+1)*Kc].T).  a: (batches, M, Kc) or (M, Kc) bf16."""
     lib = _lib.load(strict=False)
     if a.dim() == 2:
@@ -43,11 +43,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence
     d.resid, d.out_f32 = _ptr(resid), _ptr(out_f32)
     d.ld_f32 = (out_f32 if out_f32 is not None else resid).stride(-2) if (out_f32 is not None or resid is not None) else 0
     d.out_bf16, d.ld_bf16 = _ptr(out_bf16), (out_bf16.stride(-2) if out_bf16 is not None else 0)
-    d.act, d.alpha, d.col_mod, d.bn = act, _ptr(alpha), col_mod, bn
+    d.act, d.alpha, d.col_mod, d.bn, d.cg = act, _ptr(alpha), col_mod, bn, cg
+    d.trace = _ptr(trace)
+    d.dbg = dbg
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm")
 
 
-def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor) -> None:
+def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor, cg: int = 0) -> None:
     """w13: (2*I, K) packed so that each 256-row tile is [128 rows of w1 | the matching 128 rows of w3]."""
     lib = _lib.load(strict=False)
     M, K = a.shape
@@ -56,13 +58,14 @@ def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor) -> N
     d.B, d.ldb, d.b_rows = w13.data_ptr(), w13.stride(0), w13.shape[0]
     d.M, d.N, d.Kc, d.batches, d.taps = M, w13.shape[0], K, 1, 1
     d.epi = EPI_SWIGLU
+    d.cg = cg
     d.out_bf16, d.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm(swiglu)")
 
 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoids, sec_width: int, rope_cos=None,
              rope_sin=None, head_dim: int = 128, pos_period: int = 1, pos_offset: int = 0, pos_mult: int = 1,
-             eps: float = 1e-5) -> None:
+             eps: float = 1e-5, cg: int = 0) -> None:
     lib = _lib.load(strict=False)
     M, K = a.shape
     d = GemmDesc()
@@ -70,6 +73,7 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoi
     d.B, d.ldb, d.b_rows = w.data_ptr(), w.stride(0), w.shape[0]
     d.M, d.N, d.Kc, d.batches, d.taps = M, w.shape[0], K, 1, 1
     d.epi = EPI_QKV
+    d.cg = cg
     for i, o in enumerate(outs):
         d.sec_out[i] = o.data_ptr()
         d.sec_norm_w[i] = _ptr(norm_ws[i])

@@ -176,6 +176,9 @@ typedef struct echo_gemm_desc {
   int sec_width; const float* rope_cos; const float* rope_sin; int head_dim; int pos_period; int pos_offset;
   int pos_mult; float eps;
   int bn; /* 0 = auto */
+  int cg; /* 0 = auto, 1 = one CTA per tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
+  int dbg;          /* tuning switches for the epilogue (0 in production) */
+  long long* trace; /* optional device buffer, 8 clock64 stamps per CTA (kernel timeline for tuning); NULL normally */
 } echo_gemm_desc;
 int echo_op_gemm(const echo_gemm_desc* d, void* stream);
 

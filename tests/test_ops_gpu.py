@@ -27,14 +27,17 @@ def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
     return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
 
 
-@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 0), (640, 2048, 2048, 0), (1920, 2048, 2048, 256),
-                                      (200, 512, 1280, 128), (77, 192, 320, 0), (300, 128, 80, 64),
-                                      (1920, 2048, 5888, 0)])
-def test_gemm_plain(ops, M, N, K, bn):
+@pytest.mark.parametrize("M,N,K,bn,cg", [(128, 256, 64, 0, 1), (640, 2048, 2048, 0, 0), (1920, 2048, 2048, 256, 1),
+                                         (200, 512, 1280, 128, 1), (77, 192, 320, 0, 0), (300, 128, 80, 64, 0),
+                                         (1920, 2048, 5888, 0, 0),
+                                         # CTA-pair (tcgen05 cta_group::2) tiles, incl. ragged M (odd number of 128-row halves)
+                                         (256, 256, 64, 256, 2), (1920, 2048, 2048, 256, 2), (640, 2048, 5888, 128, 2),
+                                         (200, 512, 1280, 256, 2), (77, 256, 320, 128, 2), (7680, 2048, 2048, 256, 2)])
+def test_gemm_plain(ops, M, N, K, bn, cg):
     a, w = _rand((M, K), 1), _rand((N, K), 2, scale=K ** -0.5)
     out32 = torch.empty(M, N, device="cuda")
     out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, w, out_f32=out32, out_bf16=out16, bn=bn)
+    ops.gemm(a, w, out_f32=out32, out_bf16=out16, bn=bn, cg=cg)
     ref = a.float() @ w.float().T
     assert rel_l2(out32, ref) < 1e-5
     assert rel_l2(out16, ref) < 3e-3
@@ -60,28 +63,29 @@ def test_gemm_epilogue_bias_gate_resid_act(ops):
     assert rel_l2(out16, ref) < 3e-3
 
 
-@pytest.mark.parametrize("C,Cout,T,B,dil", [(64, 64, 300, 2, 1), (192, 192, 1000, 1, 3), (96, 96, 777, 2, 9),
-                                            (384, 384, 512, 1, 9)])
-def test_gemm_causal_conv(ops, C, Cout, T, B, dil):
+@pytest.mark.parametrize("C,Cout,T,B,dil,cg", [(64, 64, 300, 2, 1, 0), (192, 192, 1000, 1, 3, 0), (96, 96, 777, 2, 9, 0),
+                                               (384, 384, 512, 1, 9, 0), (256, 256, 700, 2, 3, 2), (128, 512, 333, 3, 9, 2)])
+def test_gemm_causal_conv(ops, C, Cout, T, B, dil, cg):
     """Causal dilated conv k=7 as a 7-tap GEMM over time-major activations (reference autoencoder.py:285-289)."""
     x = _rand((B, T, C), 11)
     wt = _rand((Cout, C, 7), 12, scale=(7 * C) ** -0.5)  # torch conv1d weight layout (Cout, Cin, k)
     bias = _rand((Cout,), 13, dtype=torch.float32)
     w_packed = wt.permute(0, 2, 1).reshape(Cout, 7 * C).contiguous()  # [Cout][tap][Cin]
     out = torch.empty(B, T, Cout, device="cuda")
-    ops.gemm(x, w_packed, taps=7, tap_shift=[-(6 - j) * dil for j in range(7)], bias=bias, out_f32=out)
+    ops.gemm(x, w_packed, taps=7, tap_shift=[-(6 - j) * dil for j in range(7)], bias=bias, out_f32=out, cg=cg)
     xin = torch.nn.functional.pad(x.float().transpose(1, 2), (6 * dil, 0))
     ref = torch.nn.functional.conv1d(xin, wt.float(), bias, dilation=dil).transpose(1, 2)
     assert rel_l2(out, ref) < 1e-5
 
 
-def test_gemm_swiglu(ops):
-    M, K, I = 640, 512, 768
+@pytest.mark.parametrize("M,cg", [(640, 1), (640, 2), (1000, 2)])
+def test_gemm_swiglu(ops, M, cg):
+    K, I = 512, 768
     a = _rand((M, K), 21)
     w1, w3 = _rand((I, K), 22, scale=K ** -0.5), _rand((I, K), 23, scale=K ** -0.5)
     w13 = torch.stack([w1.view(I // 128, 128, K), w3.view(I // 128, 128, K)], 1).reshape(2 * I, K).contiguous()
     out = torch.empty(M, I, device="cuda", dtype=torch.bfloat16)
-    ops.gemm_swiglu(a, w13, out)
+    ops.gemm_swiglu(a, w13, out, cg=cg)
     ref = torch.nn.functional.silu(a.float() @ w1.float().T) * (a.float() @ w3.float().T)
     assert rel_l2(out, ref) < 3e-3
 
@@ -100,7 +104,8 @@ def _rope_ref(x, cos, sin, pos):
     return o.reshape(x.shape)
 
 
-def test_gemm_qkv_norm_rope(ops):
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_qkv_norm_rope(ops, cg):
     """Fused wq|wk|wv|gate projection + per-head RMSNorm + RoPE on the first half of the heads
     (reference model.py:217-232, 199-202)."""
     b, S, Dm, H = 3, 160, 512, 4
@@ -112,7 +117,7 @@ def test_gemm_qkv_norm_rope(ops):
     cos, sin = _rope_tables(S + 7, 128)
     outs = [torch.empty(M, Dm, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
     ops.gemm_qkv(a, w, outs, [qn, kn, None, None], [H // 2, H // 2, 0, 0], [0, 0, 0, 1], Dm, cos, sin, 128,
-                 pos_period=S, pos_offset=7, eps=1e-5)
+                 pos_period=S, pos_offset=7, eps=1e-5, cg=cg)
     y = (a.float() @ w.float().T).view(M, 4, H, 128)
     pos = (torch.arange(M, device="cuda") % S) + 7
 
