@@ -16,6 +16,7 @@
 #include <cstdio>
 
 #include "counters.h"
+#include "launch.h"
 #include "profiler.h"
 
 namespace echo {
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(const echo_attn_desc 
   const int h = blockIdx.y;
   const int b = blockIdx.z;
 
+  pdl_wait();
+  pdl_trigger();
   // ---- tile list over all segments (few dozen entries)
   if (tid == 0) {
     int n = 0;
@@ -328,14 +331,15 @@ cudaError_t launch(const echo_attn_desc& d, cudaStream_t s) {
     configured = true;
   }
   dim3 grid((d.S + ATT_BM - 1) / ATT_BM, d.H, d.b);
+  cudaError_t err;
   {
     char tag[64];
     snprintf(tag, sizeof(tag), "attn D=%d b=%d S=%d H=%d nseg=%d", D, d.b, d.S, d.H, d.nseg);
     ProfScope ps(PROF_ATTN, 0.0, 0.0, s, tag);
-    attn_kernel<D><<<grid, ATT_THREADS, smem, s>>>(d);
+    err = launch_k(attn_kernel<D>, grid, dim3(ATT_THREADS), (size_t)smem, s, 1, d);
   }
   count_launch();
-  return cudaGetLastError();
+  return err;
 }
 
 }  // namespace

@@ -14,6 +14,7 @@
 
 #include "attention.h"
 #include "counters.h"
+#include "launch.h"
 #include "gemm.h"
 #include "glue.h"
 #include "handle.h"
@@ -89,6 +90,8 @@ __global__ void pack_final_kernel(const float* __restrict__ v, const float* __re
 __global__ void pca_unproject_kernel(const float* __restrict__ z, const float* __restrict__ comps,
                                      const float* __restrict__ mean, float inv_is_div_scale, float* __restrict__ X,
                                      int K, int N) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sz[];
   const int r = blockIdx.x;
   for (int k = threadIdx.x; k < K; k += blockDim.x) sz[k] = z[(size_t)r * K + k] / inv_is_div_scale;
@@ -102,6 +105,8 @@ __global__ void pca_unproject_kernel(const float* __restrict__ z, const float* _
 
 // (B, C, T) fp32 -> (B, T, C) fp32
 __global__ void transpose_ct_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
@@ -122,6 +127,8 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
                                                         const float* __restrict__ wb, const float* __restrict__ lnw,
                                                         const float* __restrict__ lnb, bf16* __restrict__ out, int T,
                                                         int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sh[32];
   __shared__ float stat[2];
   const int row = blockIdx.x;
@@ -174,6 +181,8 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
 // final: audio[b, t] = tanh(bias + sum_j sum_c w[j][c] * sx[b, t - 6 + j, c])     (autoencoder.py:994)
 __global__ void __launch_bounds__(256) final_conv_tanh_kernel(const bf16* __restrict__ sx, const float* __restrict__ w,
                                                               float bias, float* __restrict__ audio, int T, int C) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sw[];  // [7][C]
   for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -546,7 +555,7 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
     }
     Tc *= 2;
     const int r2 = B * Tc;
-    dwconv_ln_kernel<<<r2, 256, 0, s>>>(xa, u.dw_w, u.dw_b, u.ln_w, u.ln_b, nxt, Tc, C);
+    launch_k(dwconv_ln_kernel, dim3(r2), dim3(256), 0, s, 1, xa, u.dw_w, u.dw_b, u.ln_w, u.ln_b, nxt, Tc, C);
     count_launch();
     {
       GemmCall g = base_gemm(nxt, C, u.w1, C, 1, r2, 4 * C, C, 1);
@@ -599,7 +608,7 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
   }
   const int Cl = h->stage.back().cout;
   dim3 grid((Tc + 255) / 256, B);
-  final_conv_tanh_kernel<<<grid, 256, 7 * Cl * sizeof(float), s>>>(cur, h->final_w, h->final_b, audio, Tc, Cl);
+  launch_k(final_conv_tanh_kernel, dim3(grid), dim3(256), 7 * Cl * sizeof(float), s, 1, cur, h->final_w, h->final_b, audio, Tc, Cl);
   count_launch();
   ECHO_CUDA(cudaGetLastError());
   return ECHO_OK;
@@ -622,7 +631,7 @@ extern "C" int echo_dac_decode(echo_handle* h, const float* z, const float* pca_
   const int C = h->dcfg.latent_dim, Kp = h->dcfg.pca_dim;
   float* X = (float*)h->wsget("dac.X", (size_t)B * T * C * 4, s);
   if (!X) { set_error("dac: out of memory"); return ECHO_ERR_CUDA; }
-  pca_unproject_kernel<<<B * T, 256, Kp * sizeof(float), s>>>(z, pca_components, pca_mean, latent_scale, X, Kp, C);
+  launch_k(pca_unproject_kernel, dim3(B * T), dim3(256), Kp * sizeof(float), s, 1, z, pca_components, pca_mean, latent_scale, X, Kp, C);
   count_launch();
   return dac_run(h, X, B, T, audio, s);
 }
@@ -635,7 +644,7 @@ extern "C" int echo_dac_decode_zq(echo_handle* h, const float* zq, int B, int T,
   float* X = (float*)h->wsget("dac.X", (size_t)B * T * C * 4, s);
   if (!X) { set_error("dac: out of memory"); return ECHO_ERR_CUDA; }
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  transpose_ct_kernel<<<grid, block, 0, s>>>(zq, X, C, T);
+  launch_k(transpose_ct_kernel, dim3(grid), dim3(block), 0, s, 1, zq, X, C, T);
   count_launch();
   return dac_run(h, X, B, T, audio, s);
 }

@@ -96,7 +96,7 @@ int gemm_num_sms() {
 template <int BN, int BK, int ATOMS, int EPI, int CG>
 static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
   static bool configured = false;
-  constexpr int SMEM = gemm_smem_bytes(BN, BK, ATOMS, CG);
+  constexpr int SMEM = gemm_smem_bytes(BN, BK, ATOMS, CG, EPI);
   auto kern = gemm_tc_kernel<BN, BK, ATOMS, EPI, CG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -114,21 +114,7 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
                p.taps, BN, CG);
     else tag[0] = 0;
     ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s, tag);
-    if constexpr (CG == 1) {
-      kern<<<grid, GEMM_THREADS, SMEM, s>>>(ma, mb, p);
-      err = cudaGetLastError();
-    } else {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(GEMM_THREADS);
-      cfg.dynamicSmemBytes = SMEM;
-      cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      err = cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
-    }
+    err = launch_k(kern, dim3(grid), dim3(GEMM_THREADS), SMEM, s, CG, ma, mb, p);
   }
   count_launch();
   return err;

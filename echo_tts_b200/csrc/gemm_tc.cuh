@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm.h"
+#include "launch.h"
 
 namespace echo {
 
@@ -41,12 +42,15 @@ __host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32
 __host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS, int CG) {
   return (GEMM_BM + BN / CG) * BK * 2 * ATOMS;
 }
-__host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS, int CG) {
-  int s = (227 * 1024 - 1024 - 256) / gemm_stage_bytes(BN, BK, ATOMS, CG);
+// the generic epilogue transposes 32 x 32 fp32 chunks through 4 KB of smem per epilogue warp
+__host__ __device__ constexpr int gemm_epi_bytes(int EPI) { return EPI == EPI_GENERIC ? GEMM_EPI_WARPS * 4096 : 0; }
+__host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS, int CG, int EPI) {
+  int s = (227 * 1024 - 1024 - 256 - gemm_epi_bytes(EPI)) / gemm_stage_bytes(BN, BK, ATOMS, CG);
   return s > ECHO_MAX_STAGES ? ECHO_MAX_STAGES : s;
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int BN, int BK, int ATOMS, int CG) {
-  return gemm_stages(BN, BK, ATOMS, CG) * gemm_stage_bytes(BN, BK, ATOMS, CG) + 1024 /*align slack*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int gemm_smem_bytes(int BN, int BK, int ATOMS, int CG, int EPI) {
+  return gemm_stages(BN, BK, ATOMS, CG, EPI) * gemm_stage_bytes(BN, BK, ATOMS, CG) + gemm_epi_bytes(EPI) +
+         1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 // Rare activations (cond_module SiLU, ConvNeXt GELU, ...). Deliberately NOT inlined: inlining erff/tanhf 32x per
@@ -71,7 +75,7 @@ __device__ __noinline__ float apply_act(float v, int act, float alpha) {
 template <int BN, int BK, int ATOMS, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  constexpr int STAGES = gemm_stages(BN, BK, ATOMS, CG);
+  constexpr int STAGES = gemm_stages(BN, BK, ATOMS, CG, EPI);
   constexpr int A_ATOM = GEMM_BM * BK * 2;
   constexpr int BNH = BN / CG;  // B rows staged by this CTA
   constexpr int B_ATOM = BNH * BK * 2;
@@ -84,7 +88,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [8 warps][32 x 32] (generic epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + gemm_epi_bytes(EPI));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -94,7 +99,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   long long* trace = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
-  if (trace && threadIdx.x == 0) trace[0] = clock64();
+  long long t_entry = 0;
+  if (trace && threadIdx.x == 0) t_entry = clock64();
 
   uint32_t cta_rank = 0;
   if constexpr (CG == 2) cta_rank = cluster_ctarank();
@@ -130,7 +136,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (trace && threadIdx.x == 0) trace[1] = clock64();
+  // everything above touched only shared memory / TMEM / the kernel parameters: it overlaps the predecessor's tail
+  pdl_wait();
+  pdl_trigger();
+  if (trace && threadIdx.x == 0) { trace[0] = t_entry; trace[1] = clock64(); }
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -241,18 +250,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
 
       if constexpr (EPI == EPI_GENERIC) {
-        // Software-pipelined: the fp32 residual of chunk c+1 is requested while chunk c is processed, and the
-        // first chunk's residual before the accumulator barrier, so the epilogue is not a chain of exposed latencies.
+        // tcgen05.ld hands every thread one ROW of the chunk (32 consecutive columns). Touching global memory in
+        // that shape costs 32 L1 wavefronts per 128-bit access (32 lines, 16 B each) and made this epilogue -- an
+        // fp32 read-modify-write of the residual stream -- longer than the K = 2048 mainloop (measured 14.8 us vs
+        // 10.4 us per 128 x 256 tile, profiles/r01_gemm_inkernel_timeline_v3.txt). Each warp therefore transposes
+        // its 32 x 32 chunk through a private XOR-swizzled 4 KB smem patch: afterwards a lane owns 4 consecutive
+        // columns of 8 rows, every 128-bit access covers 4 full 128 B lines, and the per-column operands
+        // (bias, gate, snake alpha) are one float4 per lane instead of 8 broadcast loads.
+        // Software-pipelined: the residual of chunk c+1 is requested while chunk c is processed, and the first
+        // chunk's residual before the accumulator barrier.
         constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (this warp takes ch = half, half + 2, ...)
+        float* stg = epi_stage + ew * 1024;
+        const int sub = lane >> 3;  // row inside a group of 4
+        const int c4 = lane & 7;    // float4 column of the chunk owned after the transpose
         const int cmod = p.col_mod > 0 ? p.col_mod : p.N;  // multiple of 32, so a 32-column chunk never wraps
-        const bool has_res = p.resid != nullptr && row_ok;
+        const size_t row0 = (size_t)bt * p.M + mbase;      // global row of this warp's slab
+        const int rows_left = p.M - mbase;                 // rows of the slab inside the matrix (may be <= 0)
         float4 rcur[8], rnext[8];
         auto load_resid = [&](int ch, float4* r) {
           const int c0 = n0 + ch * 32;
-          if (has_res && ch < BN / 32 && c0 < p.N) {
-            const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ld_f32 + c0);
+          if (p.resid != nullptr && ch < BN / 32 && c0 < p.N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = rp[j];
+            for (int i = 0; i < 8; ++i) {
+              const int rr = sub + 4 * i;
+              if (rr < rows_left) r[i] = *reinterpret_cast<const float4*>(p.resid + (row0 + rr) * p.ld_f32 + c0 + 4 * c4);
+            }
           }
         };
         load_resid(half, rcur);
@@ -267,78 +289,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_ld_32x32(tbase + ch * 32, v);
             load_resid(ch + 2, rnext);
             const int c0 = n0 + ch * 32;
-            const bool col_ok = c0 < p.N;  // warp-uniform
-            const int cb = col_ok ? c0 % cmod : 0;  // one modulo per chunk
-            float4 g4[8];
-            if (p.gate && col_ok) {
-              const size_t grow = (p.rows_per_gate > 0) ? (row / p.rows_per_gate) * (size_t)p.gate_ld : 0;
-              const float4* gp = reinterpret_cast<const float4*>(p.gate + grow + cb);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) g4[j] = __ldg(gp + j);
+            const bool col_ok = c0 < p.N;            // warp-uniform
+            const int cb = (col_ok ? c0 % cmod : 0) + 4 * c4;  // one modulo per chunk
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), a4 = g4, i4 = g4;
+            if (col_ok) {
+              if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb));
+              if (p.gate && p.rows_per_gate <= 0) g4 = __ldg(reinterpret_cast<const float4*>(p.gate + cb));
+              if (p.act == ACT_SNAKE && p.out_bf16) {
+                a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + cb));
+                if (p.alpha_inv) i4 = __ldg(reinterpret_cast<const float4*>(p.alpha_inv + cb));
+                else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
+              }
             }
             tc_wait_ld();
-            if (col_ok && !(p.dbg & 8)) {
-              if (p.bias) {
-                const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 b4 = __ldg(bp + j);
-                  v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-                }
-              }
-              if (p.scale != 1.f) {
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            if (col_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= p.scale;
-              }
-              if (p.gate) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  v[4 * j] *= g4[j].x; v[4 * j + 1] *= g4[j].y; v[4 * j + 2] *= g4[j].z; v[4 * j + 3] *= g4[j].w;
-                }
-              }
-              if (row_ok) {
-                if (p.resid) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    v[4 * j] += rcur[j].x; v[4 * j + 1] += rcur[j].y; v[4 * j + 2] += rcur[j].z; v[4 * j + 3] += rcur[j].w;
+              for (int i = 0; i < 8; ++i) {
+                const int rr = sub + 4 * i;
+                float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                if (rr < rows_left) {
+                  const size_t grow = row0 + rr;
+                  t.x = (t.x + b4.x) * p.scale; t.y = (t.y + b4.y) * p.scale;
+                  t.z = (t.z + b4.z) * p.scale; t.w = (t.w + b4.w) * p.scale;
+                  if (p.gate) {
+                    float4 g = g4;
+                    if (p.rows_per_gate > 0)
+                      g = __ldg(reinterpret_cast<const float4*>(p.gate + (grow / p.rows_per_gate) * (size_t)p.gate_ld + cb));
+                    t.x *= g.x; t.y *= g.y; t.z *= g.z; t.w *= g.w;
                   }
-                }
-                if (p.out_f32) {
-                  float4* op = reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + c0);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-                if (p.out_bf16) {
-                  if (p.act == ACT_SNAKE) {
-                    // snake(x) = x + sin^2(alpha x) / (alpha + 1e-9)   (autoencoder.py:96-102); the result is rounded
-                    // to bf16, so the SFU sine (abs err ~|x| 2^-22) is far below the output quantum
-                    const float4* ap = reinterpret_cast<const float4*>(p.alpha + cb);
-                    const float4* ip = p.alpha_inv ? reinterpret_cast<const float4*>(p.alpha_inv + cb) : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      const float4 a4 = __ldg(ap + j);
-                      float4 i4;
-                      if (ip) i4 = __ldg(ip + j);
-                      else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
-                      const float s0 = __sinf(a4.x * v[4 * j]), s1 = __sinf(a4.y * v[4 * j + 1]);
-                      const float s2 = __sinf(a4.z * v[4 * j + 2]), s3 = __sinf(a4.w * v[4 * j + 3]);
-                      v[4 * j] = fmaf(s0 * s0, i4.x, v[4 * j]);
-                      v[4 * j + 1] = fmaf(s1 * s1, i4.y, v[4 * j + 1]);
-                      v[4 * j + 2] = fmaf(s2 * s2, i4.z, v[4 * j + 2]);
-                      v[4 * j + 3] = fmaf(s3 * s3, i4.w, v[4 * j + 3]);
+                  if (p.resid) { t.x += rcur[i].x; t.y += rcur[i].y; t.z += rcur[i].z; t.w += rcur[i].w; }
+                  if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + c0 + 4 * c4) = t;
+                  if (p.out_bf16) {
+                    if (p.act == ACT_SNAKE) {
+                      // snake(x) = x + sin^2(alpha x) / (alpha + 1e-9)   (autoencoder.py:96-102); the result is
+                      // rounded to bf16, so the SFU sine (abs err ~|x| 2^-22) is far below the output quantum
+                      const float s0 = __sinf(a4.x * t.x), s1 = __sinf(a4.y * t.y);
+                      const float s2 = __sinf(a4.z * t.z), s3 = __sinf(a4.w * t.w);
+                      t.x = fmaf(s0 * s0, i4.x, t.x); t.y = fmaf(s1 * s1, i4.y, t.y);
+                      t.z = fmaf(s2 * s2, i4.z, t.z); t.w = fmaf(s3 * s3, i4.w, t.w);
+                    } else if (p.act != ACT_NONE) {
+                      t.x = apply_act(t.x, p.act, 1.f); t.y = apply_act(t.y, p.act, 1.f);
+                      t.z = apply_act(t.z, p.act, 1.f); t.w = apply_act(t.w, p.act, 1.f);
                     }
-                  } else if (p.act != ACT_NONE) {
-#pragma unroll 4
-                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, 1.f);
+                    *reinterpret_cast<uint2*>(p.out_bf16 + grow * p.ld_bf16 + c0 + 4 * c4) =
+                        make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
                   }
-                  uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_bf16 + c0);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
                 }
               }
             }
+            __syncwarp();  // the patch is rewritten by the next chunk
 #pragma unroll
             for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
           }

@@ -3,6 +3,7 @@
 #include "glue.h"
 
 #include "counters.h"
+#include "launch.h"
 #include "profiler.h"
 
 namespace echo {
@@ -43,6 +44,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __global__ void embed_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ table, float* __restrict__ X,
                              int E, int vocab) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   int id = ids[r];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -58,6 +61,8 @@ __global__ void embed_kernel(const int32_t* __restrict__ ids, const bf16* __rest
 __global__ void __launch_bounds__(256) rmsnorm_affine_kernel(const float* __restrict__ X, bf16* __restrict__ out,
                                                              const float* __restrict__ a, const float* __restrict__ c0,
                                                              int W, int rows_per_group, int64_t group_ld, float eps) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sh[32];
   const int r = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(X + (size_t)r * W);
@@ -98,6 +103,8 @@ __global__ void __launch_bounds__(256) rmsnorm_affine_kernel(const float* __rest
 __global__ void __launch_bounds__(256) in_proj_kernel(const float* __restrict__ x, const bf16* __restrict__ W,
                                                       const float* __restrict__ bias, float* __restrict__ X, int rows,
                                                       int K, int D, int copies) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sx[8][128];
   const int r0 = blockIdx.x * 8;
   for (int i = threadIdx.x; i < 8 * K; i += 256) {
@@ -140,6 +147,8 @@ template <int RB>
 __global__ void __launch_bounds__(256) out_norm_proj_kernel(const float* __restrict__ X, const float* __restrict__ wn,
                                                             const bf16* __restrict__ Wout, const float* __restrict__ bias,
                                                             float* __restrict__ v, int rows, int D, int Nout, float eps) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sxn[];  // [RB][D]
   __shared__ float sh[32];
   const int r0 = blockIdx.x * RB;
@@ -194,6 +203,8 @@ __global__ void __launch_bounds__(256) out_norm_proj_kernel(const float* __restr
 
 __global__ void timestep_embed_kernel(const float* __restrict__ t, const float* __restrict__ freqs, bf16* __restrict__ emb,
                                       int half, int round_t) {
+  pdl_wait();
+  pdl_trigger();
   const int j = blockIdx.x;
   float tv = t[j];
   if (round_t) tv = __bfloat162float(__float2bfloat16_rn(tv));
@@ -205,6 +216,8 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, const float* 
 }
 
 __global__ void adaln_prep_kernel(const float* __restrict__ cond, bf16* __restrict__ scond, int n, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = (int64_t)3 * n * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % D);
@@ -217,6 +230,8 @@ __global__ void adaln_prep_kernel(const float* __restrict__ cond, bf16* __restri
 
 __global__ void adaln_finish_kernel(const float* __restrict__ up, const float* __restrict__ cond, float* __restrict__ mod,
                                     int n, int D, int Q) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = (int64_t)3 * Q * n * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % D);
@@ -231,6 +246,8 @@ __global__ void adaln_finish_kernel(const float* __restrict__ up, const float* _
 
 __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ v, int64_t n, int has_cfg, float s_text,
                                  float s_spk, int has_rescale, float omt, float ratio, float dt) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float vp = v[i];
     if (has_cfg) {
@@ -244,6 +261,8 @@ __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict_
 }
 
 __global__ void scale_bf16_kernel(bf16* __restrict__ p, int64_t n, float sc) {
+  pdl_wait();
+  pdl_trigger();
   const bf16 s16 = __float2bfloat16_rn(sc);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     // torch mul_ on a bf16 tensor by a python scalar: computed in fp32 (opmath), rounded once to bf16
@@ -253,17 +272,23 @@ __global__ void scale_bf16_kernel(bf16* __restrict__ p, int64_t n, float sc) {
 }
 
 __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, float sc) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = src[i] * sc;
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 __global__ void mask_eff_len_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ eff, int len, int ld,
                                     int stride) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ int best;
   if (threadIdx.x == 0) best = 0;
   __syncthreads();
@@ -279,6 +304,8 @@ __global__ void mask_eff_len_kernel(const uint8_t* __restrict__ mask, int32_t* _
 __global__ void pack_rows_kernel(const void* __restrict__ src, int src_bf16, void* __restrict__ dst, int dst_bf16,
                                  int64_t rows, int64_t cols, int64_t dst_ld, int64_t blk, int64_t blk_stride,
                                  int64_t blk_off) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols, c = i % cols;
@@ -299,74 +326,74 @@ inline int grid_for(int64_t n, int threads = 256) {
 
 void embed_rows(const int32_t* ids, const bf16* table, float* X, int rows, int E, int vocab, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  embed_kernel<<<rows, 128, 0, s>>>(ids, table, X, E, vocab);
+  launch_k(embed_kernel, dim3(rows), dim3(128), 0, s, 1, ids, table, X, E, vocab);
   count_launch();
 }
 void rmsnorm_affine(const float* X, bf16* out, const float* a, const float* c0, int rows, int W, int rows_per_group,
                     int64_t group_ld, float eps, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  rmsnorm_affine_kernel<<<rows, 256, 0, s>>>(X, out, a, c0, W, rows_per_group, group_ld, eps);
+  launch_k(rmsnorm_affine_kernel, dim3(rows), dim3(256), 0, s, 1, X, out, a, c0, W, rows_per_group, group_ld, eps);
   count_launch();
 }
 void in_proj(const float* x, const bf16* W, const float* bias, float* X, int rows, int K, int D, int copies,
              cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  in_proj_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, W, bias, X, rows, K, D, copies);
+  launch_k(in_proj_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, 1, x, W, bias, X, rows, K, D, copies);
   count_launch();
 }
 void out_norm_proj(const float* X, const float* wn, const bf16* Wout, const float* bias, float* v, int rows, int D,
                    int Nout, float eps, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   constexpr int RB = 4;
-  out_norm_proj_kernel<RB><<<(rows + RB - 1) / RB, 256, RB * D * sizeof(float), s>>>(X, wn, Wout, bias, v, rows, D, Nout,
+  launch_k(out_norm_proj_kernel<RB>, dim3((rows + RB - 1) / RB), dim3(256), RB * D * sizeof(float), s, 1, X, wn, Wout, bias, v, rows, D, Nout,
                                                                                     eps);
   count_launch();
 }
 void timestep_embed(const float* t, const float* freqs, bf16* emb, int n, int half, int round_t_bf16, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  timestep_embed_kernel<<<n, 128, 0, s>>>(t, freqs, emb, half, round_t_bf16);
+  launch_k(timestep_embed_kernel, dim3(n), dim3(128), 0, s, 1, t, freqs, emb, half, round_t_bf16);
   count_launch();
 }
 void adaln_prep(const float* cond, bf16* scond, int n, int D, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  adaln_prep_kernel<<<grid_for((int64_t)3 * n * D), 256, 0, s>>>(cond, scond, n, D);
+  launch_k(adaln_prep_kernel, dim3(grid_for((int64_t)3 * n * D)), dim3(256), 0, s, 1, cond, scond, n, D);
   count_launch();
 }
 void adaln_finish(const float* up, const float* cond, float* mod, int n, int D, int Q, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  adaln_finish_kernel<<<grid_for((int64_t)3 * Q * n * D), 256, 0, s>>>(up, cond, mod, n, D, Q);
+  launch_k(adaln_finish_kernel, dim3(grid_for((int64_t)3 * Q * n * D)), dim3(256), 0, s, 1, up, cond, mod, n, D, Q);
   count_launch();
 }
 void cfg_euler_update(float* x, const float* v, int64_t n, int has_cfg, float s_text, float s_spk, int has_rescale,
                       float one_minus_t, float ratio, float dt, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  cfg_euler_kernel<<<grid_for(n), 256, 0, s>>>(x, v, n, has_cfg, s_text, s_spk, has_rescale, one_minus_t, ratio, dt);
+  launch_k(cfg_euler_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, x, v, n, has_cfg, s_text, s_spk, has_rescale, one_minus_t, ratio, dt);
   count_launch();
 }
 void scale_bf16(bf16* p, int64_t n, float sc, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  scale_bf16_kernel<<<grid_for(n), 256, 0, s>>>(p, n, sc);
+  launch_k(scale_bf16_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, p, n, sc);
   count_launch();
 }
 void scale_copy_f32(const float* src, float* dst, int64_t n, float sc, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  scale_copy_kernel<<<grid_for(n), 256, 0, s>>>(src, dst, n, sc);
+  launch_k(scale_copy_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, src, dst, n, sc);
   count_launch();
 }
 void cast_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  cast_bf16_kernel<<<grid_for(n), 256, 0, s>>>(src, dst, n);
+  launch_k(cast_bf16_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, src, dst, n);
   count_launch();
 }
 void mask_eff_len(const uint8_t* mask, int32_t* eff, int n, int len, int ld, int stride, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  mask_eff_len_kernel<<<n, 256, 0, s>>>(mask, eff, len, ld, stride);
+  launch_k(mask_eff_len_kernel, dim3(n), dim3(256), 0, s, 1, mask, eff, len, ld, stride);
   count_launch();
 }
 void pack_rows(const void* src, int src_is_bf16, void* dst, int dst_is_bf16, int64_t rows, int64_t cols, int64_t dst_ld,
                int64_t blk, int64_t blk_stride, int64_t blk_off, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  pack_rows_kernel<<<grid_for(rows * cols), 256, 0, s>>>(src, src_is_bf16, dst, dst_is_bf16, rows, cols, dst_ld, blk,
+  launch_k(pack_rows_kernel, dim3(grid_for(rows * cols)), dim3(256), 0, s, 1, src, src_is_bf16, dst, dst_is_bf16, rows, cols, dst_ld, blk,
                                                          blk_stride, blk_off);
   count_launch();
 }
