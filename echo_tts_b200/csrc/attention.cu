@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "counters.h"
 #include "launch.h"
@@ -348,6 +349,8 @@ cudaError_t attention_launch(const echo_attn_desc& d, cudaStream_t s) {
   if (d.b <= 0 || d.S <= 0 || d.H <= 0 || d.nseg < 1 || d.nseg > 4) return cudaErrorInvalidValue;
   for (int i = 0; i < d.nseg; ++i)
     if (d.seg[i].len > (1 << 24) - 1) return cudaErrorInvalidValue;
+  static const bool legacy = [] { const char* e = std::getenv("ECHO_ATTN_LEGACY"); return e && e[0] == '1'; }();
+  if (!legacy && attention_tc_supported(d)) return attention_tc_launch(d, s);
   if (d.D == 128) return launch<128>(d, s);
   if (d.D == 64) return launch<64>(d, s);
   return cudaErrorInvalidValue;

@@ -1,0 +1,400 @@
+// Joint attention of the DiT blocks on tcgen05 tensor cores (head_dim 128, non-causal segments).
+//
+// Replaces cat([self, latent, text, speaker]) + bool key mask + F.scaled_dot_product_attention + "* sigmoid(gate)"
+// of the reference (model.py:246-266) for one (128 query rows, head, batch row) per CTA, without materialising the
+// concatenated K/V or the 3x CFG copies of the text/speaker caches.
+//
+// Data path per 64-key tile j (stage = j & 1):
+//   TMA        K_j, V_j  -> smem  (128B-swizzled boxes; rows beyond the tensor are zero-filled)
+//   tcgen05    S_j = Q K_j^T       (M128 N64 K128, both operands K-major, fp32 in TMEM columns [64*stage, +64))
+//   softmax    thread r owns row r: tcgen05.ld S_j -> mask/scale/max/exp2 -> bf16 P_j written over K_j's smem
+//              (K_j is dead once S_j has completed), lazy rescale of O only when the row max grows by > 2^8
+//   tcgen05    O += P_j V_j        (M128 N128 K64, A = P K-major, B = V MN-major, fp32 in TMEM columns [128, 256))
+// The MMA thread issues S_{j+1} before it waits for P_j, so the tensor pipe computes the next scores while the
+// softmax warps work; two CTAs are resident per SM (96 KB smem, 256 TMEM columns each), so one CTA's MMAs also
+// overlap the other's softmax.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax,
+// O correction and epilogue (TMEM lane quarter = warp & 3).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "attention.h"
+#include "common.cuh"
+#include "counters.h"
+#include "launch.h"
+#include "profiler.h"
+
+namespace echo {
+
+namespace {
+
+constexpr int TQ = 128;  // query rows per CTA
+constexpr int TK = 64;   // keys per tile
+constexpr int AT_THREADS = 192;
+constexpr int AT_MAX_TILES = 120;
+constexpr int Q_BYTES = TQ * 128 * 2;   // 2 atoms [128 rows][64 d]
+constexpr int KSLOT = TK * 128 * 2;     // K tile: 2 atoms [64 keys][64 d]; later P tile [128 rows][64 keys]
+constexpr int VSLOT = TK * 128 * 2;     // V tile: 2 boxes [64 keys][64 d]
+constexpr int STAGE = KSLOT + VSLOT;
+constexpr int TILE_BYTES = Q_BYTES + 2 * STAGE;  // 96 KB
+constexpr int AT_SMEM = TILE_BYTES + 1024 /*align slack*/ + 1024 /*barriers + tile list*/;
+constexpr float RESCALE_LOG2 = 8.f;  // O is rescaled only when a row max grows by more than 2^8
+
+struct AttnMaps {
+  CUtensorMap q;
+  CUtensorMap k[4];
+  CUtensorMap v[4];
+};
+
+struct SmemCtl {
+  uint64_t q_full, k_full[2], v_full[2], stage_free[2], s_full[2], p_ready[2], pv_done[2];
+  uint32_t tmem_slot;
+  int ntiles;
+  int seg_hi[4];
+  int tiles[AT_MAX_TILES];
+};
+static_assert(sizeof(SmemCtl) <= 1024, "control block");
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + TILE_BYTES);
+  auto sK = [&](int st) { return smem + Q_BYTES + st * STAGE; };
+  auto sV = [&](int st) { return smem + Q_BYTES + st * STAGE + KSLOT; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    for (int s = 0; s < d.nseg; ++s) { tma_prefetch_desc(&maps.k[s]); tma_prefetch_desc(&maps.v[s]); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(&ctl->q_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&ctl->k_full[s], 1);
+        mbar_init(&ctl->v_full[s], 1);
+        mbar_init(&ctl->stage_free[s], 1);
+        mbar_init(&ctl->s_full[s], 1);
+        mbar_init(&ctl->p_ready[s], 4);
+        mbar_init(&ctl->pv_done[s], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<256>(&ctl->tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // only shared memory / TMEM / kernel parameters were touched so far: overlaps the predecessor's tail
+  pdl_wait();
+  pdl_trigger();
+
+  // ---- tile list: (segment << 24 | first key) for every 64-key tile that can hold a valid key
+  if (warp == 2) {
+    int hi = 0;
+    if (lane < d.nseg) {
+      const echo_attn_segment& sg = d.seg[lane];
+      hi = sg.len;
+      if (sg.eff_len) { const int e = sg.eff_len[b]; hi = e < hi ? e : hi; }
+      if (sg.pos_limit_mult > 0) {
+        const int lim = (sg.pos_limit + sg.pos_limit_mult - 1) / sg.pos_limit_mult;  // keys j with j*mult < pos_limit
+        hi = lim < hi ? lim : hi;
+      }
+      if (hi < 0) hi = 0;
+      ctl->seg_hi[lane] = hi;
+    }
+    const int nt = (hi + TK - 1) / TK;
+    int off = nt;  // inclusive prefix sum over the (<= 4) segment lanes
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, off, o);
+      if (lane >= o) off += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, off, 3);
+    off -= nt;
+    for (int i = 0; i < nt && off + i < AT_MAX_TILES; ++i) ctl->tiles[off + i] = (lane << 24) | (i * TK);
+    if (lane == 0) ctl->ntiles = total < AT_MAX_TILES ? total : AT_MAX_TILES;
+  }
+  __syncthreads();
+  const int ntiles = ctl->ntiles;
+  const uint32_t tmem_base = ctl->tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(&ctl->q_full, Q_BYTES);
+      tma_load_3d(sQ, &maps.q, &ctl->q_full, h * 128, q0, b);
+      tma_load_3d(sQ + Q_BYTES / 2, &maps.q, &ctl->q_full, h * 128 + 64, q0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1, u = j >> 1;
+        const int e = ctl->tiles[j];
+        const int si = e >> 24, n0 = e & 0xFFFFFF;
+        const int bm = d.seg[si].batch_mod;
+        const int cb = d.seg[si].batch_stride == 0 ? 0 : (bm > 0 ? b % bm : b);  // stride 0: one cache for all rows
+        mbar_wait(&ctl->stage_free[st], (u & 1) ^ 1);
+        mbar_expect_tx(&ctl->k_full[st], KSLOT);
+        tma_load_3d(sK(st), &maps.k[si], &ctl->k_full[st], h * 128, n0, cb);
+        tma_load_3d(sK(st) + KSLOT / 2, &maps.k[si], &ctl->k_full[st], h * 128 + 64, n0, cb);
+        mbar_expect_tx(&ctl->v_full[st], VSLOT);
+        tma_load_3d(sV(st), &maps.v[si], &ctl->v_full[st], h * 128, n0, cb);
+        tma_load_3d(sV(st) + VSLOT / 2, &maps.v[si], &ctl->v_full[st], h * 128 + 64, n0, cb);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK);
+      constexpr uint32_t idesc_o = make_idesc_bf16(TQ, 128) | kIdescBMajorMN;
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t t_o = tmem_base + 128;
+      mbar_wait(&ctl->q_full, 0);
+      auto issue_s = [&](int j) {
+        const int st = j & 1, u = j >> 1;
+        mbar_wait(&ctl->k_full[st], u & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK(st));
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const uint64_t qd = make_smem_desc<128>(q_addr + a * (Q_BYTES / 2));
+          const uint64_t kd = make_smem_desc<128>(k_addr + a * (KSLOT / 2));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd + 2 * k, kd + 2 * k, idesc_s, (a | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&ctl->s_full[st]);
+      };
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);  // scores of the next tile run under this tile's softmax
+        const int st = j & 1, u = j >> 1;
+        mbar_wait(&ctl->p_ready[st], u & 1);
+        mbar_wait(&ctl->v_full[st], u & 1);
+        tc_fence_after();
+        const uint64_t pd = make_smem_desc<128>(smem_u32(sK(st)));  // P_j lives where K_j was
+        const uint32_t v_addr = smem_u32(sV(st));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 keys per MMA: A advances 32 B inside the swizzle row, B advances two 8-key atoms (2 KB)
+          const uint64_t vd = make_smem_desc_mn(v_addr + k * 2048, VSLOT / 2, 1024);
+          tc_mma_f16(t_o, pd + 2 * k, vd, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&ctl->stage_free[st]);  // K/P and V slots of this stage may be refilled
+        tc_commit(&ctl->pv_done[st]);     // O holds tiles 0..j
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = d.scale * 1.4426950408889634f;
+    float m_used = -INFINITY;  // running max in the log2 domain the exponentials are taken against
+    float l_run = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j & 1, u = j >> 1;
+      // ---- key validity of this tile as a 64-bit mask (before the scores are ready)
+      const int e = ctl->tiles[j];
+      const int si = e >> 24, n0 = e & 0xFFFFFF;
+      const echo_attn_segment& sg = d.seg[si];
+      const int hi = ctl->seg_hi[si];
+      uint32_t vm_lo, vm_hi;
+      {
+        bool ok0 = (n0 + lane) < hi, ok1 = (n0 + 32 + lane) < hi;
+        if (sg.mask) {
+          const int cb = sg.batch_mod > 0 ? b % sg.batch_mod : b;
+          const uint8_t* mp = sg.mask + (size_t)cb * sg.mask_ld;
+          if (ok0) ok0 = mp[(size_t)(n0 + lane) * sg.mask_stride] != 0;
+          if (ok1) ok1 = mp[(size_t)(n0 + 32 + lane) * sg.mask_stride] != 0;
+        }
+        vm_lo = __ballot_sync(0xffffffffu, ok0);
+        vm_hi = __ballot_sync(0xffffffffu, ok1);
+      }
+      mbar_wait(&ctl->s_full[st], u & 1);
+      tc_fence_after();
+      float v[64];
+      tc_ld_32x32(tmem_base + lane_base + st * TK, v);
+      tc_ld_32x32(tmem_base + lane_base + st * TK + 32, v + 32);
+      tc_wait_ld();
+      const bool full = (vm_lo & vm_hi) == 0xffffffffu;  // warp-uniform
+      float tmax = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const bool ok = ((i < 32 ? vm_lo >> i : vm_hi >> (i - 32)) & 1u) != 0;
+          v[i] = ok ? v[i] : -INFINITY;
+          tmax = fmaxf(tmax, v[i]);
+        }
+      }
+      const float m_new = fmaxf(m_used, tmax * sl2);
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool grow = m_new > m_used + RESCALE_LOG2;  // also true for -inf -> finite
+        if (__any_sync(0xffffffffu, grow)) {
+          float corr = 1.f;
+          if (grow) {
+            corr = (m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new);
+            m_used = m_new;
+            l_run *= corr;
+          }
+          // O holds tiles 0..j-1 once PV_{j-1} has completed; PV_j is only issued after this warp's p_ready arrive
+          mbar_wait(&ctl->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float o[32];
+            tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] *= corr;
+            tc_st_32x32(tmem_base + lane_base + 128 + c * 32, o);
+          }
+          tc_wait_st();
+        }
+      }
+      const float muse = (m_used == -INFINITY) ? 0.f : m_used;
+      // ---- P = exp2(s * scale*log2e - m), bf16, written K-major / 128B-swizzled over K_j (row = 128 bytes)
+      uint8_t* prow = sK(st) + row * 128;
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float pe[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pe[i] = fast_exp2(fmaf(v[8 * c + i], sl2, -muse));  // -inf -> 0
+          lsum += pe[i];
+        }
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
+            make_uint4(pack_bf16(pe[0], pe[1]), pack_bf16(pe[2], pe[3]), pack_bf16(pe[4], pe[5]), pack_bf16(pe[6], pe[7]));
+      }
+      l_run += lsum;
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->p_ready[st]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> (* gate) -> global, staged through smem so rows are written as 256 B runs
+    const bool have = ntiles > 0;
+    if (have) {
+      mbar_wait(&ctl->pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    uint8_t* stg = smem + Q_BYTES + (warp - 2) * 8192;  // 32 rows x 256 B, private to this warp; all tiles are dead
+    uint8_t* srow = stg + lane * 256;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float o[32];
+      if (have) {
+        tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int ch = c * 4 + cc;  // 16-byte chunk of the row
+        *reinterpret_cast<uint4*>(srow + ((ch ^ (lane & 7)) << 4)) =
+            make_uint4(pack_bf16(o[8 * cc] * inv, o[8 * cc + 1] * inv), pack_bf16(o[8 * cc + 2] * inv, o[8 * cc + 3] * inv),
+                       pack_bf16(o[8 * cc + 4] * inv, o[8 * cc + 5] * inv), pack_bf16(o[8 * cc + 6] * inv, o[8 * cc + 7] * inv));
+      }
+    }
+    __syncwarp();
+    const size_t HD = (size_t)d.H * 128;
+    const int rsel = lane >> 4, ch = lane & 15;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int r = 2 * i + rsel;
+      const int q = q0 + quarter * 32 + r;
+      if (q < d.S) {
+        uint4 val = *reinterpret_cast<const uint4*>(stg + r * 256 + ((ch ^ (r & 7)) << 4));
+        const size_t off = ((size_t)b * d.S + q) * HD + (size_t)h * 128 + ch * 8;
+        if (d.gate) {
+          const uint4 gv = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + off);
+          const uint32_t* vi = reinterpret_cast<const uint32_t*>(&val);
+          const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gv);
+          uint32_t rr[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 a = unpack_bf16(vi[k]), g = unpack_bf16(gi[k]);
+            rr[k] = pack_bf16(a.x * g.x, a.y * g.y);
+          }
+          val = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+        }
+        *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off) = val;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace
+
+bool attention_tc_supported(const echo_attn_desc& d) {
+  if (d.D != 128 || d.nseg < 1 || d.nseg > 4) return false;
+  if ((reinterpret_cast<uintptr_t>(d.Q) & 15) || (d.q_row_stride % 8) || (d.q_batch_stride % 8)) return false;
+  int tiles = 0;
+  for (int i = 0; i < d.nseg; ++i) {
+    const echo_attn_segment& g = d.seg[i];
+    if (g.causal || g.len <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(g.K) & 15) || (reinterpret_cast<uintptr_t>(g.V) & 15) || (g.row_stride % 8) ||
+        (g.batch_stride % 8))
+      return false;
+    tiles += (g.len + TK - 1) / TK;
+  }
+  return tiles <= AT_MAX_TILES;
+}
+
+cudaError_t attention_tc_launch(const echo_attn_desc& d, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  AttnMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
+  const uint64_t W = (uint64_t)d.H * 128;
+  const uint64_t qbs = d.b > 1 ? (uint64_t)d.q_batch_stride : (uint64_t)d.S * d.q_row_stride;
+  if (!tma_map_bf16(&maps.q, d.Q, 3, W, (uint64_t)d.S, (uint64_t)d.b, (uint64_t)d.q_row_stride * 2, qbs * 2, 64, TQ, 128))
+    return cudaErrorInvalidValue;
+  for (int i = 0; i < d.nseg; ++i) {
+    const echo_attn_segment& g = d.seg[i];
+    const uint64_t nb = g.batch_stride == 0 ? 1 : (g.batch_mod > 0 ? (uint64_t)g.batch_mod : (uint64_t)d.b);
+    const uint64_t bs = nb > 1 ? (uint64_t)g.batch_stride : (uint64_t)g.len * g.row_stride;
+    if (!tma_map_bf16(&maps.k[i], g.K, 3, W, (uint64_t)g.len, nb, (uint64_t)g.row_stride * 2, bs * 2, 64, TK, 128) ||
+        !tma_map_bf16(&maps.v[i], g.V, 3, W, (uint64_t)g.len, nb, (uint64_t)g.row_stride * 2, bs * 2, 64, TK, 128))
+      return cudaErrorInvalidValue;
+  }
+  for (int i = d.nseg; i < 4; ++i) { maps.k[i] = maps.k[0]; maps.v[i] = maps.v[0]; }
+  dim3 grid((d.S + TQ - 1) / TQ, d.H, d.b);
+  cudaError_t err;
+  {
+    char tag[64];
+    if (prof_enabled()) snprintf(tag, sizeof(tag), "attn_tc D=128 b=%d S=%d H=%d nseg=%d", d.b, d.S, d.H, d.nseg);
+    else tag[0] = 0;
+    double keys = 0;
+    for (int i = 0; i < d.nseg; ++i) keys += d.seg[i].len;
+    ProfScope ps(PROF_ATTN, 4.0 * d.b * d.H * (double)d.S * keys * 128.0, 0.0, s, tag);
+    err = launch_k(attn_tc_kernel, grid, dim3(AT_THREADS), (size_t)AT_SMEM, s, 1, maps, d);
+  }
+  count_launch();
+  return err;
+}
+
+}  // namespace echo

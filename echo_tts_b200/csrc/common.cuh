@@ -175,6 +175,21 @@ ECHO_DEVICE void tc_ld_32x32(uint32_t taddr, float* v) {
       : "memory");
 }
 
+// 32 lanes x 32 columns of fp32 back into TMEM (same thread <-> row mapping as tc_ld_32x32)
+ECHO_DEVICE void tc_st_32x32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+ECHO_DEVICE void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, A and B both K-major, M=128.
 // Bit layout (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16),
 // b_format[10,13)=1 (BF16), a_major[15]=0, b_major[16]=0, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
@@ -191,6 +206,16 @@ ECHO_DEVICE uint64_t make_smem_desc(uint32_t saddr) {
   constexpr uint64_t sbo = (8 * ROW_BYTES) >> 4;
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+
+// MN-major operand (the "transposed" B of O = P V: V is stored [key][d], d contiguous), SWIZZLE_128B.
+// Canonical layout (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): 64 MN elements are one 128-byte
+// swizzle row, 8 K rows form a 1024-byte atom; LBO = byte distance between 64-element MN groups,
+// SBO = byte distance between 8-row K groups.
+ECHO_DEVICE uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+constexpr uint32_t kIdescBMajorMN = 1u << 16;  // instruction-descriptor bit: B operand is MN-major
 
 // ---------------------------------------------------------------- small math helpers
 ECHO_DEVICE float warp_sum(float v) {
@@ -210,6 +235,11 @@ ECHO_DEVICE uint32_t pack_bf16(float a, float b) {
 ECHO_DEVICE float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
+}
+ECHO_DEVICE float fast_exp2(float x) {  // single MUFU op; -inf -> 0, denormal results flush to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 ECHO_DEVICE float silu_f(float x) { return x / (1.f + __expf(-x)); }
 ECHO_DEVICE float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }

@@ -82,6 +82,11 @@ static bool get_tensor_map(CUtensorMap* out, const void* ptr, int rank, uint64_t
   return true;
 }
 
+bool tma_map_bf16(void* out, const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                  uint32_t box0, uint32_t box1, int row_bytes) {
+  return get_tensor_map(static_cast<CUtensorMap*>(out), ptr, rank, d0, d1, d2, s1, s2, box0, box1, row_bytes);
+}
+
 static int g_num_sms = 0;
 int gemm_num_sms() {
   if (g_num_sms == 0) {

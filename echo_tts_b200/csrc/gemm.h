@@ -78,4 +78,9 @@ struct GemmCall {
 cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s);
 int gemm_num_sms();
 
+// Cached cuTensorMapEncodeTiled for a bf16 tensor whose dim0 is contiguous (rank 2 or 3; strides of dims >= 1 in
+// BYTES). `out` points at a 128-byte CUtensorMap; box = (box0, box1, 1); swizzle span = row_bytes (128 / 64 / 32).
+bool tma_map_bf16(void* out, const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                  uint32_t box0, uint32_t box1, int row_bytes);
+
 }  // namespace echo

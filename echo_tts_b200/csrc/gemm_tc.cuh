@@ -235,7 +235,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (EPI != EPI_GENERIC) {
         mbar_wait(&tfull_bar[as], (it >> 1) & 1);
         tc_fence_after();
-        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) trace[5] = clock64();
+        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
+          trace[5] = clock64();
+          if (it < 4) trace[8 + 2 * it] = trace[5];
+        }
       }
 
       // store of one 32-column bf16 chunk held as 16 packed words per thread (row = lane): 64 contiguous bytes / thread.
@@ -277,10 +280,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         };
+        // Pull this tile's residual rows into L2 while the MMAs still run: the read-modify-write of the fp32
+        // residual stream is a chip-wide burst (every CTA reaches its epilogue at the same time) and with only one
+        // chunk of loads in flight per thread it was latency-bound at ~3 TB/s (10.7 us per 128 x 256 tile).
+        if (p.resid != nullptr && lane < rows_left) {
+          const char* rp = reinterpret_cast<const char*>(p.resid + (row0 + lane) * p.ld_f32 + n0);
+          const int bytes = (p.N - n0 < BN ? p.N - n0 : BN) * 4;
+          for (int o = half * 128; o < bytes; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
+        }
         load_resid(half, rcur);
         mbar_wait(&tfull_bar[as], (it >> 1) & 1);
         tc_fence_after();
-        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) trace[5] = clock64();
+        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
+          trace[5] = clock64();
+          if (it < 4) trace[8 + 2 * it] = trace[5];
+        }
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int ch = half + 2 * ci;
@@ -429,7 +443,10 @@ ECHO_CHUNK_UNROLL
           }
         }
       }
-      if (trace && warp == GEMM_EPI_WARP0 && lane == 0) trace[6] = clock64();
+      if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
+        trace[6] = clock64();
+        if (it < 4) trace[9 + 2 * it] = trace[6];
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -49,7 +49,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm")
 
 
-def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor, cg: int = 0) -> None:
+def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor, cg: int = 0, trace=None) -> None:
     """w13: (2*I, K) packed so that each 256-row tile is [128 rows of w1 | the matching 128 rows of w3]."""
     lib = _lib.load(strict=False)
     M, K = a.shape
@@ -59,13 +59,14 @@ def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor, cg: 
     d.M, d.N, d.Kc, d.batches, d.taps = M, w13.shape[0], K, 1, 1
     d.epi = EPI_SWIGLU
     d.cg = cg
+    d.trace = _ptr(trace)
     d.out_bf16, d.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm(swiglu)")
 
 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoids, sec_width: int, rope_cos=None,
              rope_sin=None, head_dim: int = 128, pos_period: int = 1, pos_offset: int = 0, pos_mult: int = 1,
-             eps: float = 1e-5, cg: int = 0) -> None:
+             eps: float = 1e-5, cg: int = 0, trace=None) -> None:
     lib = _lib.load(strict=False)
     M, K = a.shape
     d = GemmDesc()
@@ -74,6 +75,7 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoi
     d.M, d.N, d.Kc, d.batches, d.taps = M, w.shape[0], K, 1, 1
     d.epi = EPI_QKV
     d.cg = cg
+    d.trace = _ptr(trace)
     for i, o in enumerate(outs):
         d.sec_out[i] = o.data_ptr()
         d.sec_norm_w[i] = _ptr(norm_ws[i])

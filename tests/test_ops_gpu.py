@@ -199,3 +199,38 @@ def test_attention_causal_window(ops, S, D, H, window):
         m = m & (i[None, :] > i[:, None] - window)
     ref = _sdpa_ref(q, [k], [v], [m[None].expand(b, S, S)], D ** -0.5).reshape(b, S, H * D)
     assert rel_l2(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("b,S,H,L2", [(1, 640, 16, 53), (3, 640, 2, 300), (2, 130, 3, 64), (1, 64, 1, 1)])
+def test_attention_tc_growing_max(ops, b, S, H, L2):
+    """tcgen05 attention: later key tiles carry much larger scores than the first ones, so the lazy O rescale
+    (row max growing by > 2^8 in the log2 domain) must fire; a second, batch-shared segment follows the self keys."""
+    D = 128
+    q = _rand((b, S, H, D), 61, scale=2.0)
+    k_self, v_self = _rand((b, S, H, D), 62), _rand((b, S, H, D), 63)
+    ramp = torch.linspace(0.2, 3.0, S, device="cuda")[None, :, None, None]
+    k_self = (k_self.float() * ramp).to(torch.bfloat16)  # score spread grows with the key index
+    k2, v2 = _rand((1, L2, H, D), 64, scale=4.0), _rand((1, L2, H, D), 65)
+    out = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, [dict(k=k_self, v=v_self), dict(k=k2, v=v2, batch_mod=1)], out)
+    masks = [torch.ones(b, S, S, dtype=torch.bool, device="cuda"), torch.ones(b, S, L2, dtype=torch.bool, device="cuda")]
+    ref = _sdpa_ref(q, [k_self, k2.expand(b, -1, -1, -1)], [v_self, v2.expand(b, -1, -1, -1)], masks, D ** -0.5)
+    assert rel_l2(out, ref.reshape(b, S, H * D)) < 6e-3
+
+
+def test_attention_tc_matches_mma_sync_kernel(ops, monkeypatch):
+    """Both attention kernels (tcgen05 and the mma.sync one kept for causal / head_dim 64) agree on a joint-attention
+    case; the dispatch is decided once per process, so the mma.sync result is obtained through a causal-free D=128
+    call with a window that covers every key... not expressible -> compare both against the fp32 reference instead."""
+    b, S, H, D = 3, 256, 2, 128
+    q, k, v = _rand((b, S, H, D), 71), _rand((b, S, H, D), 72), _rand((b, S, H, D), 73)
+    out_tc = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, [dict(k=k, v=v)], out_tc)
+    out_causal = torch.empty_like(out_tc)
+    ops.attention(q, [dict(k=k, v=v, causal=1, window=0)], out_causal)  # mma.sync path
+    full = torch.ones(b, S, S, dtype=torch.bool, device="cuda")
+    ref = _sdpa_ref(q, [k], [v], [full], D ** -0.5).reshape(b, S, H * D)
+    assert rel_l2(out_tc, ref) < 6e-3
+    # the last query row of a causal attention sees every key: identical problem, different kernel
+    assert rel_l2(out_causal[:, -1], ref[:, -1]) < 6e-3
+    assert rel_l2(out_causal[:, -1], out_tc[:, -1].float()) < 8e-3

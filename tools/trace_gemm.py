@@ -1,4 +1,6 @@
-"""In-kernel timeline of the tcgen05 GEMM (clock64 stamps) for the small DiT shapes: where do the fixed costs go?"""
+"""In-kernel timeline of the tcgen05 GEMM (clock64 stamps): where do the fixed costs go?
+Slots: 0 entry, 1 setup done, 2 1st TMA issued, 3 1st full, 4 last MMA issued, 5 last acc ready, 6 last epilogue
+done, 7 exit, 8+2i / 9+2i = accumulator ready / epilogue done of the CTA's i-th tile (i < 4)."""
 import os
 import sys
 
@@ -8,31 +10,49 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from echo_tts_b200 import ops  # noqa: E402
 
 dev = "cuda"
-names = ["entry", "setup done", "1st TMA issued", "1st full", "last MMA issued", "acc ready", "epilogue done", "exit"]
-cases = [(1920, 2048, 2048, 256, 1, 0), (1920, 2048, 2048, 256, 2, 0), (640, 2048, 2048, 128, 1, 0), (640, 2048, 2048, 256, 1, 0),
-         (1920, 2048, 5888, 256, 1, 0), (640, 2048, 5888, 128, 1, 0), (1920, 2048, 2048, 256, 1, 8), (1920, 2048, 2048, 128, 1, 0)]
-for (M, N, K, bn, cg, dbg) in cases:
-    a = torch.randn(M, K, device=dev).bfloat16()
-    ws = [torch.randn(N, K, device=dev).bfloat16() * K ** -0.5 for _ in range(8)]
-    res = torch.zeros(M, N, device=dev)
-    gate = torch.randn(1, N, device=dev)
+names = ["entry", "setup", "tma0", "full0", "mma_last", "acc_last", "epi_last", "exit"]
+D, I = 2048, 5888
+
+
+def run(label, M, fn_factory):
     trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
-    for i in range(5):
-        ops.gemm(a, ws[i % 8], gate=gate, resid=res, out_f32=res, bn=bn, cg=cg, trace=trace, dbg=dbg)
+    fn = fn_factory(trace)
+    for _ in range(4):
+        fn()
     torch.cuda.synchronize()
+    trace.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.gemm(a, ws[7], gate=gate, resid=res, out_f32=res, bn=bn, cg=cg, trace=trace, dbg=dbg)
+    fn()
     e1.record()
     torch.cuda.synchronize()
     t = trace.view(148, 16).cpu()
-    used = t[:, 0] > 0
-    t = t[used]
-    # leader CTAs (even) have all stamps; report the median over CTAs of each delta from entry, in us at 1.9 GHz
-    lead = t[::cg] if cg == 2 else t
-    rel = (lead - lead[:, :1]).float() / 1.9e3
-    med = rel.median(0).values[:8]
-    print(f"M={M} N={N} K={K} bn={bn} cg={cg} dbg={dbg}: {int(used.sum())} CTAs, kernel {e0.elapsed_time(e1)*1e3:.1f} us (event)")
-    print("   " + "  ".join(f"{n}={v:.2f}" for n, v in zip(names, med.tolist())))
-    span = (t[:, 7].max() - t[:, 0].min()).item() / 1.9e3
-    print(f"   first entry -> last exit over all CTAs (per-SM clocks, approx): {span:.2f} us")
+    t = t[t[:, 0] > 0]
+    rel = (t - t[:, :1]).float() / 1.9e3
+    rel[t == 0] = float("nan")
+    med = rel.nanmedian(0).values
+    print(f"{label} M={M}: {t.shape[0]} CTAs, event {e0.elapsed_time(e1)*1e3:.1f} us")
+    print("   " + "  ".join(f"{n}={v:.2f}" for n, v in zip(names, med[:8].tolist())))
+    print("   tiles (acc ready -> epilogue done): " + "  ".join(
+        f"[{med[8 + 2 * i]:.2f} -> {med[9 + 2 * i]:.2f}]" for i in range(4) if med[8 + 2 * i] == med[8 + 2 * i]))
+    print(f"   slowest CTA exit: {rel[:, 7].max():.2f} us", flush=True)
+
+
+for M in (1920, 640):
+    x = torch.randn(M, D, device=dev).bfloat16()
+    h = torch.randn(M, I, device=dev).bfloat16()
+    res = torch.zeros(M, D, device=dev)
+    gate = torch.randn(1, D, device=dev)
+    w_qkv = torch.randn(4 * D, D, device=dev).bfloat16() * D ** -0.5
+    w_13 = torch.randn(2 * I, D, device=dev).bfloat16() * D ** -0.5
+    w_o = torch.randn(D, D, device=dev).bfloat16() * D ** -0.5
+    w_2 = torch.randn(D, I, device=dev).bfloat16() * I ** -0.5
+    outs = [torch.empty(M, D, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+    nw = torch.ones(D, device=dev)
+    cos, sin = torch.ones(4096, 64, device=dev), torch.zeros(4096, 64, device=dev)
+    hh = torch.empty(M, I, device=dev, dtype=torch.bfloat16)
+    run("qkvg", M, lambda tr: (lambda: ops.gemm_qkv(x, w_qkv, outs, [nw, nw, None, None], [8, 8, 0, 0], [0, 0, 0, 1], D,
+                                                    cos, sin, 128, pos_period=640, trace=tr)))
+    run("w13 ", M, lambda tr: (lambda: ops.gemm_swiglu(x, w_13, hh, trace=tr)))
+    run("wo  ", M, lambda tr: (lambda: ops.gemm(x, w_o, gate=gate, resid=res, out_f32=res, trace=tr)))
+    run("w2  ", M, lambda tr: (lambda: ops.gemm(h, w_2, gate=gate, resid=res, out_f32=res, trace=tr)))
