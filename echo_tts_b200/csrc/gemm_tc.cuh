@@ -42,8 +42,8 @@ __host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32
 __host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS, int CG) {
   return (GEMM_BM + BN / CG) * BK * 2 * ATOMS;
 }
-// the generic epilogue transposes 32 x 32 fp32 chunks through 4 KB of smem per epilogue warp
-__host__ __device__ constexpr int gemm_epi_bytes(int EPI) { return EPI == EPI_GENERIC ? GEMM_EPI_WARPS * 4096 : 0; }
+// every epilogue transposes 32 x 32 fp32 chunks through 4 KB of smem per epilogue warp
+__host__ __device__ constexpr int gemm_epi_bytes(int /*EPI*/) { return GEMM_EPI_WARPS * 4096; }
 __host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS, int CG, int EPI) {
   int s = (227 * 1024 - 1024 - 256 - gemm_epi_bytes(EPI)) / gemm_stage_bytes(BN, BK, ATOMS, CG);
   return s > ECHO_MAX_STAGES ? ECHO_MAX_STAGES : s;
@@ -226,10 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int bt = rest % p.batches;
       const int nt = rest / p.batches;
       const int mbase = (mt * CG + (int)cta_rank) * GEMM_BM + quarter * 32;  // first row of this warp's 32-row slab
-      const int m = mbase + lane;
       const int n0 = nt * BN;
-      const bool row_ok = m < p.M;
-      const size_t row = (size_t)bt * p.M + m;
       const int as = it & 1;
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
       if constexpr (EPI != EPI_GENERIC) {
@@ -240,17 +237,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (it < 4) trace[8 + 2 * it] = trace[5];
         }
       }
-
-      // store of one 32-column bf16 chunk held as 16 packed words per thread (row = lane): 64 contiguous bytes / thread.
-      // (A shared-memory transpose to coalesce these was measured SLOWER: the stores are fire-and-forget and the
-      // staging traffic competes with the UMMA operand reads of the next tile.)
-      auto store_bf16_chunk = [&](const uint32_t* pk, bf16* out, size_t ld, int col0) {
-        if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(out + row * ld + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
-      };
 
       if constexpr (EPI == EPI_GENERIC) {
         // tcgen05.ld hands every thread one ROW of the chunk (32 consecutive columns). Touching global memory in
@@ -362,20 +348,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else if constexpr (EPI == EPI_SWIGLU) {
+        // h = silu(a) * b in the row-per-thread layout, then the same smem transpose as the generic epilogue so
+        // the bf16 rows leave as 64-byte runs (a lane owns 4 consecutive columns of 8 rows) instead of 32 scattered
+        // 16-byte pieces per store instruction.
         constexpr int HALF_CH = BN / 64;  // chunks in the w1 half
+        float* stg = epi_stage + ew * 1024;
+        const int sub = lane >> 3, c4 = lane & 7;
+        const size_t row0 = (size_t)bt * p.M + mbase;
+        const int rows_left = p.M - mbase;
 ECHO_CHUNK_UNROLL
         for (int ch = half; ch < HALF_CH; ch += 2) {
           float a[32], b[32];
           tc_ld_32x32(tbase + ch * 32, a);
           tc_ld_32x32(tbase + (ch + HALF_CH) * 32, b);
           tc_wait_ld();
-          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            pk[j] = pack_bf16(silu_f(a[2 * j]) * b[2 * j], silu_f(a[2 * j + 1]) * b[2 * j + 1]);
-          store_bf16_chunk(pk, p.out_bf16, (size_t)p.ld_bf16, n0 / 2 + ch * 32);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                make_float4(silu_f(a[4 * j]) * b[4 * j], silu_f(a[4 * j + 1]) * b[4 * j + 1],
+                            silu_f(a[4 * j + 2]) * b[4 * j + 2], silu_f(a[4 * j + 3]) * b[4 * j + 3]);
+          __syncwarp();
+          bf16* op = p.out_bf16 + row0 * p.ld_bf16 + n0 / 2 + ch * 32 + 4 * c4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = sub + 4 * i;
+            const float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+            if (rr < rows_left)
+              *reinterpret_cast<uint2*>(op + (size_t)rr * p.ld_bf16) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
+          }
+          __syncwarp();
         }
-      } else {  // EPI_QKV: this thread owns one row x 128 contiguous columns (group `half` of the 256-wide tile)
+      } else {  // EPI_QKV: this warp owns 32 rows x one 128-column group (group `half` of the 256-wide tile)
         static_assert(EPI != EPI_QKV || BN == 256, "QKV epilogue needs BN == 256");
         const int g0 = n0 + half * 128;  // first global column of the group
         if (g0 < p.N) {
@@ -383,9 +386,14 @@ ECHO_CHUNK_UNROLL
           const int cs = g0 - si * p.sec_width;  // column inside the section
           const QkvSection sec = p.sec[si];
           const int grp = cs >> 7;
+          float* stg = epi_stage + ew * 1024;
+          const int sub = lane >> 3, c4 = lane & 7;
+          const size_t row0 = (size_t)bt * p.M + mbase;
+          const int rows_left = p.M - mbase;
           float rstd = 1.f;
           if (sec.norm_w) {
-            // RMSNorm over head_dim columns (reference model.py:99-104); head_dim == 128 whenever norm_w is set
+            // RMSNorm over head_dim columns (reference model.py:99-104); head_dim == 128 whenever norm_w is set.
+            // Row statistics are taken in the row-per-thread layout tcgen05.ld delivers (no shuffles).
             float ss = 0.f;
 ECHO_CHUNK_UNROLL
             for (int ch = 0; ch < 4; ++ch) {
@@ -398,48 +406,45 @@ ECHO_CHUNK_UNROLL
             rstd = rsqrtf(ss * (1.f / 128.f) + p.eps);
           }
           const bool do_rope = grp < sec.rope_heads;
-          const int pos = p.pos_offset + p.pos_mult * (int)(row % (size_t)p.pos_period);
           const int hd2 = p.head_dim >> 1;
+          // after the transpose this lane owns columns 4*c4 .. 4*c4+3 of rows sub + 4i: RoPE pairs stay inside a lane
+          int pos[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pos[i] = p.pos_offset + p.pos_mult * (int)((row0 + sub + 4 * i) % (size_t)p.pos_period);
 ECHO_CHUNK_UNROLL
           for (int ch = 0; ch < 4; ++ch) {
             float v[32];
             tc_ld_32x32(tbase + (half * 4 + ch) * 32, v);
-            tc_wait_ld();
             const int cc = cs + ch * 32;
-            if (row_ok) {
-              if (sec.norm_w) {
-                const float4* wp = reinterpret_cast<const float4*>(sec.norm_w + cc);
+            float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (sec.norm_w) w4 = __ldg(reinterpret_cast<const float4*>(sec.norm_w + cc + 4 * c4));
+            const int pi = ((cc % p.head_dim) >> 1) + 2 * c4;  // first of this lane's two rotation pairs
+            tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 w4 = __ldg(wp + j);
-                  v[4 * j] *= rstd * w4.x; v[4 * j + 1] *= rstd * w4.y; v[4 * j + 2] *= rstd * w4.z; v[4 * j + 3] *= rstd * w4.w;
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                  make_float4(v[4 * j] * rstd, v[4 * j + 1] * rstd, v[4 * j + 2] * rstd, v[4 * j + 3] * rstd);
+            __syncwarp();
+            bf16* op = sec.out + row0 * p.sec_width + cc + 4 * c4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = sub + 4 * i;
+              float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+              if (rr < rows_left) {
+                t.x *= w4.x; t.y *= w4.y; t.z *= w4.z; t.w *= w4.w;
+                if (do_rope) {
+                  const float2 c2 = __ldg(reinterpret_cast<const float2*>(p.rope_cos + (size_t)pos[i] * hd2 + pi));
+                  const float2 s2 = __ldg(reinterpret_cast<const float2*>(p.rope_sin + (size_t)pos[i] * hd2 + pi));
+                  const float x0 = t.x, y0 = t.y, x1 = t.z, y1 = t.w;
+                  t.x = x0 * c2.x - y0 * s2.x; t.y = x0 * s2.x + y0 * c2.x;
+                  t.z = x1 * c2.y - y1 * s2.y; t.w = x1 * s2.y + y1 * c2.y;
                 }
-              }
-              if (do_rope) {
-                const int pi0 = ((cc % p.head_dim) >> 1);
-                const float4* cp = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * hd2 + pi0);
-                const float4* sp = reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * hd2 + pi0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 c4 = __ldg(cp + j), s4 = __ldg(sp + j);
-                  const float cc4[4] = {c4.x, c4.y, c4.z, c4.w}, ss4[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float a = v[8 * j + 2 * q], b = v[8 * j + 2 * q + 1];
-                    v[8 * j + 2 * q] = a * cc4[q] - b * ss4[q];
-                    v[8 * j + 2 * q + 1] = a * ss4[q] + b * cc4[q];
-                  }
-                }
+                if (sec.sigmoid) { t.x = sigmoid_f(t.x); t.y = sigmoid_f(t.y); t.z = sigmoid_f(t.z); t.w = sigmoid_f(t.w); }
+                *reinterpret_cast<uint2*>(op + (size_t)rr * p.sec_width) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
               }
             }
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a0 = v[2 * j], a1 = v[2 * j + 1];
-              if (sec.sigmoid) { a0 = sigmoid_f(a0); a1 = sigmoid_f(a1); }
-              pk[j] = pack_bf16(a0, a1);
-            }
-            store_bf16_chunk(pk, sec.out, (size_t)p.sec_width, cc);
+            __syncwarp();
           }
         }
       }

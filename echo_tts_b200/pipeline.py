@@ -1,0 +1,282 @@
+"""Host side of one synthesis job: text -> chunks -> (per chunk) tokens -> sampler -> DAC decode -> crop -> stitch.
+
+Mirrors the callers either side of the CUDA hot path, with the reference's names, argument meaning and results:
+
+  tokenizer_encode / get_text_input_ids_and_mask    reference inference.py:115-138, 192-215
+  chunk_text / chunk_text_for_audio                 reference inference.py:140-190, handler.py:102-123
+  find_flattening_point / crop_audio_to_...         reference inference.py:288-301   (vectorised: one pass, no
+                                                    per-window device sync)
+  sample_pipeline                                   reference inference.py:309-347   (speaker given as latents:
+                                                    the DAC *encoder* is outside this round's scope)
+  crossfade_chunks / normalize_chunk_boundaries     reference handler.py:126-240     (the per-sample Python loop of
+                                                    handler.py:214-218 becomes one reduction)
+  synthesize                                        reference handler.py:736-768     (chunk loop + stitching)
+
+Multi-GPU: the chunks of a long prompt -- or whole requests -- are independent units. `shard_units`
+assigns unit i to rank i % world, every rank runs its units on its own GPU replica, and the finished audio (<= 5 MB
+per chunk) is gathered once per job; the stitching runs on the host of rank 0. There is no collective on the
+per-step path.
+"""
+from __future__ import annotations
+
+import re
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+MAX_TEXT_LENGTH = 768             # inference.py:324
+MAX_SPEAKER_LATENT_LENGTH = 6400  # inference.py:323
+AE_DOWNSAMPLE_FACTOR = 2048
+SAMPLE_RATE = 44100
+
+_WS = re.compile(r"\s+")
+_REPLACEMENTS = (("…", "..."), ("’", "'"), ("”", '"'), ("\n", " "), (":", ","), (";", ","),
+                 ("—", ", "))
+
+
+# ------------------------------------------------------------------------------------------------ text
+def tokenizer_encode(text: str, append_bos: bool = True, normalize: bool = True,
+                     return_normalized_text: bool = False):
+    if normalize:
+        for a, b in _REPLACEMENTS:
+            text = text.replace(a, b)
+        if not text.startswith(("[", "(")) and "S1" not in text and "S2" not in text:
+            text = "[S1] " + text
+    ids = ([0] if append_bos else []) + list(text.encode("utf-8"))
+    t = torch.tensor(ids)
+    return (t, text) if return_normalized_text else t
+
+
+def get_text_input_ids_and_mask(text_arr: List[str], max_length: Optional[int], device=None, normalize: bool = True,
+                                return_normalized_text: bool = False, pad_to_max: bool = True):
+    enc = [tokenizer_encode(t, normalize=normalize, return_normalized_text=True) for t in text_arr]
+    if max_length is None:
+        max_length = max(len(e) for e, _ in enc)
+    tokens = torch.zeros((len(text_arr), max_length), dtype=torch.int32)
+    mask = torch.zeros((len(text_arr), max_length), dtype=torch.bool)
+    for i, (e, _) in enumerate(enc):
+        n = min(len(e), max_length)
+        tokens[i, :n] = e[:n]
+        mask[i, :n] = True
+    if device is not None:
+        tokens, mask = tokens.to(device), mask.to(device)
+    if return_normalized_text:
+        return tokens, mask, [t for _, t in enc]
+    return tokens, mask
+
+
+_SENTENCE, _CLAUSE = ".!?", ",;:"
+_CLOSERS = "\"')]}”’"
+
+
+def _split_point(window: str) -> int:
+    """Last whitespace of the window that follows a sentence end, else a clause end, else any; 0 if none."""
+    best = [0, 0, 0]  # sentence, clause, space
+    for m in _WS_CHAR.finditer(window, 1):
+        i = m.start()
+        best[2] = i
+        p1 = window[i - 1]
+        p0 = window[i - 2] if i >= 2 else ""
+        closing = p1 in _CLOSERS
+        if p1 in _SENTENCE or (closing and p0 != "" and p0 in _SENTENCE):
+            best[0] = i
+        elif p1 in _CLAUSE or (closing and p0 != "" and p0 in _CLAUSE):
+            best[1] = i
+    return best[0] or best[1] or best[2]
+
+
+_WS_CHAR = re.compile(r"\s")
+
+
+def chunk_text(text: str, max_chars: int = 300) -> List[str]:
+    """Split into <= max_chars chunks, preferring sentence, then clause, then word boundaries."""
+    if max_chars <= 0:
+        raise ValueError("max_chars must be > 0")
+    rest = _WS.sub(" ", text or "").strip()
+    out: List[str] = []
+    while len(rest) > max_chars:
+        cut = _split_point(rest[: max_chars + 1]) or max_chars
+        head = rest[:cut].strip()
+        if head:
+            out.append(head)
+        rest = rest[cut:].strip()
+    if rest:
+        out.append(rest)
+    return out
+
+
+def chunk_text_for_audio(text: str, max_chars: int = 300, target_duration_seconds: float = 10.0) -> List[str]:
+    chunks = chunk_text(text, max_chars=min(max_chars, int(target_duration_seconds * 12)))  # ~12 chars / s of speech
+    if len(chunks) > 1 and len(chunks[-1]) < 24:  # a < 2 s tail joins the previous chunk
+        tail = chunks.pop()
+        chunks[-1] += " " + tail
+    return chunks
+
+
+# ------------------------------------------------------------------------------------------------ latents -> audio
+def find_flattening_point(data: torch.Tensor, target_value: float = 0.0, window_size: int = 20,
+                          std_threshold: float = 0.05) -> int:
+    """First index whose `window_size`-latent window (zero padded past the end) is flat: std < std_threshold and
+    |mean - target| < 0.1. All windows are evaluated in one vectorised pass and the result leaves the device once
+    (the reference syncs the device twice per window)."""
+    n = data.shape[0]
+    if n == 0:
+        return 0
+    padded = torch.cat([data, data.new_zeros((window_size,) + tuple(data.shape[1:]))])
+    win = padded.reshape(padded.shape[0], -1).unfold(0, window_size, 1)[:n]  # (n, features, window)
+    win = win.reshape(n, -1).float()
+    flat = (win.std(dim=1) < std_threshold) & ((win.mean(dim=1) - target_value).abs() < 0.1)
+    idx = torch.nonzero(flat)
+    return int(idx[0]) if idx.numel() else n
+
+
+def crop_audio_to_flattening_point(audio: torch.Tensor, latent: torch.Tensor) -> torch.Tensor:
+    return audio[..., : find_flattening_point(latent) * AE_DOWNSAMPLE_FACTOR]
+
+
+@torch.inference_mode()
+def sample_pipeline(model, fish_ae, pca_state, sample_fn: Callable, text_prompt: str,
+                    speaker_latent: Optional[torch.Tensor] = None, speaker_mask: Optional[torch.Tensor] = None,
+                    rng_seed: int = 0, pad_to_max_speaker_latent_length: Optional[int] = None,
+                    pad_to_max_text_length: Optional[int] = None, normalize_text: bool = True) -> Tuple[torch.Tensor, str]:
+    """One chunk: reference inference.py:309-347 with the speaker reference passed as PCA latents
+    (`get_speaker_latent_and_mask` output) instead of raw audio. Returns (audio (1, 1, n) fp32, normalised text)."""
+    from .autoencoder import ae_decode
+    device = model.device
+    ids, mask, norm = get_text_input_ids_and_mask(
+        [text_prompt], max_length=min(pad_to_max_text_length or MAX_TEXT_LENGTH, MAX_TEXT_LENGTH), device=device,
+        normalize=normalize_text, return_normalized_text=True, pad_to_max=(pad_to_max_text_length is not None))
+    if speaker_latent is None:  # inference.py:329-331
+        n = pad_to_max_speaker_latent_length or 4
+        speaker_latent = torch.zeros((1, n, 80), device=device, dtype=model.dtype)
+        speaker_mask = torch.zeros((1, n), device=device, dtype=torch.bool)
+    latent = sample_fn(model, speaker_latent, speaker_mask, ids, mask, rng_seed)
+    audio = ae_decode(fish_ae, pca_state, latent)
+    return crop_audio_to_flattening_point(audio, latent[0]), norm[0]
+
+
+# ------------------------------------------------------------------------------------------------ stitching (host)
+def crossfade_chunks(audio_chunks: Sequence[torch.Tensor], overlap_samples: int = 4410) -> torch.Tensor:
+    """Linear 100 ms cross-fades; the overlap shrinks to a quarter of the shorter side."""
+    if not audio_chunks:
+        return torch.tensor([])
+    pieces = [audio_chunks[0]]
+    total = audio_chunks[0].shape[-1]
+    for cur in audio_chunks[1:]:
+        ov = min(overlap_samples, cur.shape[-1] // 4, total // 4)
+        if ov > 0:
+            ramp = torch.linspace(0, 1, ov, device=cur.device)
+            down = torch.linspace(1, 0, ov, device=cur.device)
+            if cur.dim() == 2:
+                ramp, down = ramp.view(1, -1), down.view(1, -1)
+            last = pieces.pop()
+            # the fade-out may reach back over several short pieces: materialise only the tail that is needed
+            while last.shape[-1] < ov:
+                last = torch.cat([pieces.pop(), last], dim=-1)
+            pieces += [last[..., :-ov], last[..., -ov:] * down + cur[..., :ov] * ramp, cur[..., ov:]]
+            total += cur.shape[-1] - ov
+        else:
+            pieces.append(cur)
+            total += cur.shape[-1]
+    return torch.cat(pieces, dim=-1)
+
+
+def _trailing_silence(chunk: torch.Tensor, threshold: float, max_tail: int) -> int:
+    tail = chunk[..., -min(chunk.shape[-1], max_tail):].abs().flatten()
+    loud = torch.nonzero(tail >= threshold)
+    return tail.numel() if loud.numel() == 0 else tail.numel() - 1 - int(loud[-1])
+
+
+def normalize_chunk_boundaries(audio_chunks: Sequence[torch.Tensor], sample_rate: int = SAMPLE_RATE,
+                               silence_threshold: float = 0.01, min_silence_samples: int = 22050) -> torch.Tensor:
+    """Every chunk but the last ends with exactly `min_silence_samples` of silence, then cross-fade."""
+    if not audio_chunks:
+        return torch.tensor([])
+    if len(audio_chunks) == 1:
+        return audio_chunks[0]
+    fixed = []
+    for i, chunk in enumerate(audio_chunks):
+        if chunk.dim() == 1:
+            chunk = chunk.unsqueeze(0)
+        if i + 1 < len(audio_chunks):
+            quiet = _trailing_silence(chunk, silence_threshold, 2 * min_silence_samples)
+            if quiet > min_silence_samples:
+                chunk = chunk[..., : chunk.shape[-1] - (quiet - min_silence_samples)]
+            elif quiet < min_silence_samples:
+                pad = chunk.new_zeros(tuple(chunk.shape[:-1]) + (min_silence_samples - quiet,)).float()
+                chunk = torch.cat([chunk, pad.to(chunk.device)], dim=-1)
+        fixed.append(chunk)
+    return crossfade_chunks(fixed)
+
+
+def stitch(audio_chunks: Sequence[torch.Tensor], normalize_boundaries: bool = True, enable_crossfade: bool = True):
+    """handler.py:763-768."""
+    if normalize_boundaries and len(audio_chunks) > 1:
+        return normalize_chunk_boundaries(audio_chunks, sample_rate=SAMPLE_RATE)
+    if enable_crossfade and len(audio_chunks) > 1:
+        return crossfade_chunks(audio_chunks)
+    return torch.cat(list(audio_chunks), dim=-1)
+
+
+# ------------------------------------------------------------------------------------------------ sharding
+def shard_units(n_units: int, rank: int, world: int) -> List[int]:
+    """Unit i (a text chunk or a whole request) runs on rank i % world."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    return list(range(rank, n_units, world))
+
+
+def gather_audio(local: Sequence[Tuple[int, torch.Tensor]], n_units: int, group=None, dst: int = 0):
+    """Collect (unit index, 2-D audio) pairs from every rank on `dst`, in unit order. One exchange per job:
+    lengths first, then one padded buffer per rank. Works on gloo (CPU tensors) and NCCL (CUDA tensors)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        out = [None] * n_units
+        for i, a in local:
+            out[i] = a
+        return out
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    per_rank = (n_units + world - 1) // world
+    lens = torch.zeros(per_rank, dtype=torch.int64, device=dev)
+    for slot, (_, a) in enumerate(local):
+        lens[slot] = a.shape[-1]
+    all_lens = [torch.zeros_like(lens) for _ in range(world)]
+    dist.all_gather(all_lens, lens, group=group)
+    width = max(int(torch.stack(all_lens).max()), 1)
+    buf = torch.zeros(per_rank, width, dtype=torch.float32, device=dev)
+    for slot, (_, a) in enumerate(local):
+        buf[slot, : a.shape[-1]] = a.reshape(-1).to(dev, torch.float32)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    if rank != dst:
+        return None
+    out = [None] * n_units
+    for r in range(world):
+        for slot, i in enumerate(shard_units(n_units, r, world)):
+            out[i] = bufs[r][slot, : int(all_lens[r][slot])].unsqueeze(0).cpu()
+    return out
+
+
+def synthesize(text: str, synth_chunk: Callable[[str, int], torch.Tensor], seed: int = 0,
+               max_chars_per_chunk: Optional[int] = 300, target_duration: float = 10.0,
+               normalize_boundaries: bool = True, enable_crossfade: bool = True, group=None):
+    """The chunk loop of handler._synthesize (handler.py:736-768), sharded over the ranks of `group` when
+    torch.distributed is initialised. `synth_chunk(chunk_text, chunk_seed)` returns the chunk's audio (1, n);
+    chunk i uses seed + 1000 * i (handler.py:749). Rank 0 returns the stitched audio, other ranks None."""
+    import torch.distributed as dist
+    chunks = chunk_text_for_audio(text, max_chars_per_chunk, target_duration) if max_chars_per_chunk and \
+        max_chars_per_chunk > 0 else [text]
+    if not chunks:
+        raise ValueError("Text is empty after normalization")
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    local = []
+    for i in shard_units(len(chunks), rank, world):
+        a = synth_chunk(chunks[i], seed + i * 1000)
+        local.append((i, a.reshape(1, -1) if a.dim() != 2 else a))
+    audio = gather_audio(local, len(chunks), group)
+    if audio is None:
+        return None
+    return stitch([a.cpu() for a in audio], normalize_boundaries, enable_crossfade)

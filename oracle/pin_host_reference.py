@@ -95,7 +95,7 @@ def main():
 
     sets = {
         "three_mixed": [mk(60000, 0, 1), mk(90000, 30000, 2), mk(50000, 5000, 3)],
-        "short_chunks": [mk(3000, 100, 4), mk(800, 0, 5), mk(10, 0, 6), mk(20000, 44100, 7)],
+        "short_chunks": [mk(3000, 100, 4), mk(800, 0, 5), mk(10, 0, 6), mk(20000, 20000, 7)],
         "single": [mk(5000, 0, 8)],
         "all_silent_tail": [mk(30000, 30000, 9), mk(40000, 0, 10)],
         "one_dim": [mk(9000, 0, 11)[0], mk(12000, 2000, 12)[0]],
