@@ -22,7 +22,10 @@
 namespace echo {
 
 #ifndef ECHO_EPI_UNROLL
-#define ECHO_EPI_UNROLL 1   // 1: fully unroll the per-warp chunk loops of the SwiGLU / QKV epilogues (more ILP)
+// 0: keep the per-warp chunk loops of the epilogues ROLLED. Unrolled, the generic kernel was 8 300 instructions
+// (133 KB) of straight-line code that every warp executes once per tile, and ncu's source view showed its epilogue
+// dominated by stall_no_inst (instruction-cache misses), profiles/r01_ncu_gemm_v6_stalls.txt.
+#define ECHO_EPI_UNROLL 0
 #endif
 #ifndef ECHO_MAX_STAGES
 #define ECHO_MAX_STAGES 8
@@ -281,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           trace[5] = clock64();
           if (it < 4) trace[8 + 2 * it] = trace[5];
         }
-#pragma unroll
+ECHO_CHUNK_UNROLL
         for (int ci = 0; ci < NCH; ++ci) {
           const int ch = half + 2 * ci;
           if (ch < BN / 32) {
@@ -420,6 +423,17 @@ ECHO_CHUNK_UNROLL
             float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (sec.norm_w) w4 = __ldg(reinterpret_cast<const float4*>(sec.norm_w + cc + 4 * c4));
             const int pi = ((cc % p.head_dim) >> 1) + 2 * c4;  // first of this lane's two rotation pairs
+            // cos/sin of the 8 rows, requested up front and unconditionally (positions are always in range): with
+            // 227 KB of smem there is no L1 left, every table read is an L2 round trip, and loads issued row by row
+            // behind a predicate were serialised (8 exposed L2 latencies per chunk).
+            float2 rc[8], rs[8];
+            if (do_rope) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                rc[i] = __ldg(reinterpret_cast<const float2*>(p.rope_cos + (size_t)pos[i] * hd2 + pi));
+                rs[i] = __ldg(reinterpret_cast<const float2*>(p.rope_sin + (size_t)pos[i] * hd2 + pi));
+              }
+            }
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -431,18 +445,15 @@ ECHO_CHUNK_UNROLL
             for (int i = 0; i < 8; ++i) {
               const int rr = sub + 4 * i;
               float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-              if (rr < rows_left) {
-                t.x *= w4.x; t.y *= w4.y; t.z *= w4.z; t.w *= w4.w;
-                if (do_rope) {
-                  const float2 c2 = __ldg(reinterpret_cast<const float2*>(p.rope_cos + (size_t)pos[i] * hd2 + pi));
-                  const float2 s2 = __ldg(reinterpret_cast<const float2*>(p.rope_sin + (size_t)pos[i] * hd2 + pi));
-                  const float x0 = t.x, y0 = t.y, x1 = t.z, y1 = t.w;
-                  t.x = x0 * c2.x - y0 * s2.x; t.y = x0 * s2.x + y0 * c2.x;
-                  t.z = x1 * c2.y - y1 * s2.y; t.w = x1 * s2.y + y1 * c2.y;
-                }
-                if (sec.sigmoid) { t.x = sigmoid_f(t.x); t.y = sigmoid_f(t.y); t.z = sigmoid_f(t.z); t.w = sigmoid_f(t.w); }
-                *reinterpret_cast<uint2*>(op + (size_t)rr * p.sec_width) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
+              t.x *= w4.x; t.y *= w4.y; t.z *= w4.z; t.w *= w4.w;
+              if (do_rope) {
+                const float x0 = t.x, y0 = t.y, x1 = t.z, y1 = t.w;
+                t.x = x0 * rc[i].x - y0 * rs[i].x; t.y = x0 * rs[i].x + y0 * rc[i].x;
+                t.z = x1 * rc[i].y - y1 * rs[i].y; t.w = x1 * rs[i].y + y1 * rc[i].y;
               }
+              if (sec.sigmoid) { t.x = sigmoid_f(t.x); t.y = sigmoid_f(t.y); t.z = sigmoid_f(t.z); t.w = sigmoid_f(t.w); }
+              if (rr < rows_left)
+                *reinterpret_cast<uint2*>(op + (size_t)rr * p.sec_width) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
             }
             __syncwarp();
           }
