@@ -64,7 +64,7 @@ class GemmDesc(C.Structure):
         ("sec_sigmoid", C.c_int * 4),
         ("sec_width", C.c_int), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("head_dim", C.c_int),
         ("pos_period", C.c_int), ("pos_offset", C.c_int), ("pos_mult", C.c_int), ("eps", C.c_float),
-        ("bn", C.c_int), ("cg", C.c_int), ("dbg", C.c_int), ("trace", C.c_void_p),
+        ("bn", C.c_int), ("cg", C.c_int), ("dbg", C.c_int), ("trace", C.c_void_p), ("split_k", C.c_int),
     ]
 
 
@@ -83,7 +83,7 @@ class AttnDesc(C.Structure):
         ("Q", C.c_void_p), ("q_batch_stride", C.c_int64), ("q_row_stride", C.c_int64),
         ("gate", C.c_void_p), ("out", C.c_void_p),
         ("b", C.c_int), ("S", C.c_int), ("H", C.c_int), ("D", C.c_int), ("scale", C.c_float),
-        ("nseg", C.c_int), ("seg", AttnSegment * 4),
+        ("nseg", C.c_int), ("seg", AttnSegment * 4), ("trace", C.c_void_p),
     ]
 
 
@@ -121,8 +121,12 @@ SYMBOLS = {
     "echo_sample_euler_host": (C.c_int, [_P, C.POINTER(SamplerArgs), _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P]),
     "echo_profile_start": (C.c_int, [_P]),
     "echo_profile_stop": (C.c_int, [_P, C.POINTER(ProfileReport)]),
+    "echo_set_deterministic": (C.c_int, [C.c_int]),
     "echo_op_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "echo_op_attention": (C.c_int, [C.POINTER(AttnDesc), _P]),
+    "echo_op_rmsnorm_affine": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_float, _P]),
+    "echo_op_cfg_euler_update": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                          C.c_float, C.c_float, _P]),
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 #include "echo_b200.h"
 #include "errors.h"
 #include "gemm.h"
+#include "glue.h"
 
 using namespace echo;
 
@@ -34,6 +35,7 @@ extern "C" int echo_op_gemm(const echo_gemm_desc* d, void* stream) {
   c.b_rows = d->b_rows;
   c.bn = d->bn;
   c.cg = d->cg;
+  c.split_k = d->split_k;
   GemmParams& p = c.p;
   p.M = d->M; p.N = d->N; p.Kc = d->Kc; p.batches = d->batches; p.taps = d->taps;
   for (int i = 0; i < 8; ++i) p.tap_shift[i] = d->tap_shift[i];
@@ -73,5 +75,34 @@ extern "C" int echo_op_attention(const echo_attn_desc* d, void* stream) {
               d->nseg);
     return e == cudaErrorInvalidValue ? ECHO_ERR_ARG : ECHO_ERR_CUDA;
   }
+  return ECHO_OK;
+}
+
+extern "C" int echo_op_rmsnorm_affine(const float* x, void* out_bf16, const float* a, const float* c0, int rows, int W,
+                                      int rows_per_group, int64_t group_ld, float eps, void* stream) {
+  if (!x || !out_bf16 || !a || rows <= 0 || W <= 0 || W % 4 != 0 || W > 4096) {
+    set_error("echo_op_rmsnorm_affine: bad argument (rows=%d W=%d)", rows, W);
+    return ECHO_ERR_ARG;
+  }
+  rmsnorm_affine(x, static_cast<bf16*>(out_bf16), a, c0, rows, W, rows_per_group, group_ld, eps,
+                 static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("echo_op_rmsnorm_affine: %s", cudaGetErrorString(e)); return ECHO_ERR_CUDA; }
+  return ECHO_OK;
+}
+
+extern "C" int echo_op_cfg_euler_update(float* x, const float* v, int64_t n_per_branch, int has_cfg, float cfg_scale_text,
+                                        float cfg_scale_speaker, int has_rescale, float one_minus_t, float ratio, float dt,
+                                        void* stream) {
+  if (!x || !v || n_per_branch <= 0) { set_error("echo_op_cfg_euler_update: bad argument"); return ECHO_ERR_ARG; }
+  cfg_euler_update(x, v, n_per_branch, has_cfg, cfg_scale_text, cfg_scale_speaker, has_rescale, one_minus_t, ratio, dt,
+                   static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("echo_op_cfg_euler_update: %s", cudaGetErrorString(e)); return ECHO_ERR_CUDA; }
+  return ECHO_OK;
+}
+
+extern "C" int echo_set_deterministic(int on) {
+  gemm_set_deterministic(on);
   return ECHO_OK;
 }

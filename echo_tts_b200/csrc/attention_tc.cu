@@ -7,9 +7,12 @@
 // Data path per 64-key tile j (stage = j & 1):
 //   TMA        K_j, V_j  -> smem  (128B-swizzled boxes; rows beyond the tensor are zero-filled)
 //   tcgen05    S_j = Q K_j^T       (M128 N64 K128, both operands K-major, fp32 in TMEM columns [64*stage, +64))
-//   softmax    thread r owns row r: tcgen05.ld S_j -> mask/scale/max/exp2 -> bf16 P_j written over K_j's smem
-//              (K_j is dead once S_j has completed), lazy rescale of O only when the row max grows by > 2^8
-//   tcgen05    O += P_j V_j        (M128 N128 K64, A = P K-major, B = V MN-major, fp32 in TMEM columns [128, 256))
+//   softmax    thread r owns row r: tcgen05.ld S_j -> mask/scale/max/exp2 -> bf16 P_j stored back into TMEM over the
+//              first half of S_j's columns (tcgen05.st), lazy rescale of O only when the row max grows by > 2^8
+//   tcgen05    O += P_j V_j        (M128 N128 K64, A = P from TMEM, B = V MN-major, fp32 in TMEM columns [128, 256))
+// K_j's smem slot is released as soon as S_j has completed and V_j's when PV_j has, so the producer runs two tiles
+// ahead of the tensor pipe (with P staged in smem over K_j the ring was one tile deep and every tile paid a TMA
+// round trip: 21 us for 12 tiles at b = 1).
 // The MMA thread issues S_{j+1} before it waits for P_j, so the tensor pipe computes the next scores while the
 // softmax warps work; two CTAs are resident per SM (96 KB smem, 256 TMEM columns each), so one CTA's MMAs also
 // overlap the other's softmax.
@@ -36,7 +39,7 @@ constexpr int TK = 64;   // keys per tile
 constexpr int AT_THREADS = 192;
 constexpr int AT_MAX_TILES = 120;
 constexpr int Q_BYTES = TQ * 128 * 2;   // 2 atoms [128 rows][64 d]
-constexpr int KSLOT = TK * 128 * 2;     // K tile: 2 atoms [64 keys][64 d]; later P tile [128 rows][64 keys]
+constexpr int KSLOT = TK * 128 * 2;     // K tile: 2 atoms [64 keys][64 d]
 constexpr int VSLOT = TK * 128 * 2;     // V tile: 2 boxes [64 keys][64 d]
 constexpr int STAGE = KSLOT + VSLOT;
 constexpr int TILE_BYTES = Q_BYTES + 2 * STAGE;  // 96 KB
@@ -50,7 +53,7 @@ struct AttnMaps {
 };
 
 struct SmemCtl {
-  uint64_t q_full, k_full[2], v_full[2], stage_free[2], s_full[2], p_ready[2], pv_done[2];
+  uint64_t q_full, k_full[2], v_full[2], s_full[2], p_ready[2], pv_done[2];
   uint32_t tmem_slot;
   int ntiles;
   int seg_hi[4];
@@ -69,6 +72,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  // timeline (tuning): 0 entry, 1 setup done, 2 tile list done, 3 Q landed (MMA thread), 4+2j / 5+2j = softmax of
+  // tile j starts (scores ready) / ends (P published), 30 O complete, 31 epilogue done   -- stamps of warp 2 lane 0
+  long long* trace = d.trace ? d.trace + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
+  if (trace && threadIdx.x == 64) trace[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -80,7 +87,6 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       for (int s = 0; s < 2; ++s) {
         mbar_init(&ctl->k_full[s], 1);
         mbar_init(&ctl->v_full[s], 1);
-        mbar_init(&ctl->stage_free[s], 1);
         mbar_init(&ctl->s_full[s], 1);
         mbar_init(&ctl->p_ready[s], 4);
         mbar_init(&ctl->pv_done[s], 1);
@@ -96,6 +102,12 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   // only shared memory / TMEM / kernel parameters were touched so far: overlaps the predecessor's tail
   pdl_wait();
   pdl_trigger();
+  if (trace && threadIdx.x == 64) trace[1] = clock64();
+  if (warp == 0 && lane == 0) {  // Q does not depend on the tile list: get it moving first
+    mbar_expect_tx(&ctl->q_full, Q_BYTES);
+    tma_load_3d(sQ, &maps.q, &ctl->q_full, h * 128, q0, b);
+    tma_load_3d(sQ + Q_BYTES / 2, &maps.q, &ctl->q_full, h * 128 + 64, q0, b);
+  }
 
   // ---- tile list: (segment << 24 | first key) for every 64-key tile that can hold a valid key
   if (warp == 2) {
@@ -126,49 +138,66 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   __syncthreads();
   const int ntiles = ctl->ntiles;
   const uint32_t tmem_base = ctl->tmem_slot;
+  if (trace && threadIdx.x == 64) trace[2] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(&ctl->q_full, Q_BYTES);
-      tma_load_3d(sQ, &maps.q, &ctl->q_full, h * 128, q0, b);
-      tma_load_3d(sQ + Q_BYTES / 2, &maps.q, &ctl->q_full, h * 128 + 64, q0, b);
-      for (int j = 0; j < ntiles; ++j) {
+      auto load_kv = [&](int j, bool is_v) {
         const int st = j & 1, u = j >> 1;
         const int e = ctl->tiles[j];
         const int si = e >> 24, n0 = e & 0xFFFFFF;
         const int bm = d.seg[si].batch_mod;
         const int cb = d.seg[si].batch_stride == 0 ? 0 : (bm > 0 ? b % bm : b);  // stride 0: one cache for all rows
-        mbar_wait(&ctl->stage_free[st], (u & 1) ^ 1);
-        mbar_expect_tx(&ctl->k_full[st], KSLOT);
-        tma_load_3d(sK(st), &maps.k[si], &ctl->k_full[st], h * 128, n0, cb);
-        tma_load_3d(sK(st) + KSLOT / 2, &maps.k[si], &ctl->k_full[st], h * 128 + 64, n0, cb);
-        mbar_expect_tx(&ctl->v_full[st], VSLOT);
-        tma_load_3d(sV(st), &maps.v[si], &ctl->v_full[st], h * 128, n0, cb);
-        tma_load_3d(sV(st) + VSLOT / 2, &maps.v[si], &ctl->v_full[st], h * 128 + 64, n0, cb);
+        if (!is_v) {
+          if (u > 0) mbar_wait(&ctl->s_full[st], (u - 1) & 1);  // S_{j-2} has consumed the slot
+          mbar_expect_tx(&ctl->k_full[st], KSLOT);
+          tma_load_3d(sK(st), &maps.k[si], &ctl->k_full[st], h * 128, n0, cb);
+          tma_load_3d(sK(st) + KSLOT / 2, &maps.k[si], &ctl->k_full[st], h * 128 + 64, n0, cb);
+        } else {
+          if (u > 0) mbar_wait(&ctl->pv_done[st], (u - 1) & 1);  // PV_{j-2} has consumed the slot
+          mbar_expect_tx(&ctl->v_full[st], VSLOT);
+          tma_load_3d(sV(st), &maps.v[si], &ctl->v_full[st], h * 128, n0, cb);
+          tma_load_3d(sV(st) + VSLOT / 2, &maps.v[si], &ctl->v_full[st], h * 128 + 64, n0, cb);
+        }
+      };
+      // issue order K0 K1 V0 K2 V1 K3 ...: K_{j+2} only waits for S_j, which completes two tiles before S_{j+2} is issued
+      if (ntiles > 0) load_kv(0, false);
+      if (ntiles > 1) load_kv(1, false);
+      for (int j = 0; j < ntiles; ++j) {
+        load_kv(j, true);
+        if (j + 2 < ntiles) load_kv(j + 2, false);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && ntiles > 0) {
+    // The whole warp runs the (warp-uniform) control flow and one elected lane issues each tcgen05 instruction: the
+    // descriptors then live in uniform registers. With N = 64 an MMA occupies the tensor pipe for only 32 cycles,
+    // so the issue path -- not the pipe -- bounds a tile (0.9 us per tile before this was trimmed:
+    // profiles/r01_attn_tc_timeline.txt); per tile it is now 12 MMAs, 2 commits and 3 barrier waits.
+    if (ntiles > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK);
       constexpr uint32_t idesc_o = make_idesc_bf16(TQ, 128) | kIdescBMajorMN;
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t t_o = tmem_base + 128;
+      const uint64_t qd0 = make_smem_desc<128>(q_addr), qd1 = make_smem_desc<128>(q_addr + Q_BYTES / 2);
       mbar_wait(&ctl->q_full, 0);
+      if (trace && lane == 0) trace[3] = clock64();
       auto issue_s = [&](int j) {
         const int st = j & 1, u = j >> 1;
         mbar_wait(&ctl->k_full[st], u & 1);
         tc_fence_after();
+        if (trace && lane == 0 && j < 13) trace[32 + j] = clock64();
         const uint32_t k_addr = smem_u32(sK(st));
+        const uint64_t kd0 = make_smem_desc<128>(k_addr), kd1 = make_smem_desc<128>(k_addr + KSLOT / 2);
+        if (elect_one()) {
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const uint64_t qd = make_smem_desc<128>(q_addr + a * (Q_BYTES / 2));
-          const uint64_t kd = make_smem_desc<128>(k_addr + a * (KSLOT / 2));
+          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd0 + 2 * k, kd0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd + 2 * k, kd + 2 * k, idesc_s, (a | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd1 + 2 * k, kd1 + 2 * k, idesc_s, 1u);
+          tc_commit(&ctl->s_full[st]);  // scores ready; also releases K_j's smem slot to the producer
         }
-        tc_commit(&ctl->s_full[st]);
+        __syncwarp();
       };
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
@@ -177,16 +206,18 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         mbar_wait(&ctl->p_ready[st], u & 1);
         mbar_wait(&ctl->v_full[st], u & 1);
         tc_fence_after();
-        const uint64_t pd = make_smem_desc<128>(smem_u32(sK(st)));  // P_j lives where K_j was
-        const uint32_t v_addr = smem_u32(sV(st));
+        if (trace && lane == 0 && j < 13) trace[48 + j] = clock64();
+        const uint32_t p_tmem = tmem_base + st * TK;  // bf16 P_j, packed 2 keys per column over S_j's first 32 columns
+        const uint64_t vd = make_smem_desc_mn(smem_u32(sV(st)), VSLOT / 2, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // 16 keys per MMA: A advances 32 B inside the swizzle row, B advances two 8-key atoms (2 KB)
-          const uint64_t vd = make_smem_desc_mn(v_addr + k * 2048, VSLOT / 2, 1024);
-          tc_mma_f16(t_o, pd + 2 * k, vd, idesc_o, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // 16 keys per MMA: A advances 8 TMEM columns, B advances two 8-key atoms (2 KB = 128 x 16 B)
+            tc_mma_f16_ts(t_o, p_tmem + 8 * k, vd + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&ctl->pv_done[st]);  // O holds tiles 0..j; also releases V_j's smem slot
         }
-        tc_commit(&ctl->stage_free[st]);  // K/P and V slots of this stage may be refilled
-        tc_commit(&ctl->pv_done[st]);     // O holds tiles 0..j
+        __syncwarp();
       }
     }
   } else {
@@ -218,6 +249,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       }
       mbar_wait(&ctl->s_full[st], u & 1);
       tc_fence_after();
+      if (trace && threadIdx.x == 64 && j < 13) trace[4 + 2 * j] = clock64();
       float v[64];
       tc_ld_32x32(tmem_base + lane_base + st * TK, v);
       tc_ld_32x32(tmem_base + lane_base + st * TK + 32, v + 32);
@@ -263,33 +295,44 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         }
       }
       const float muse = (m_used == -INFINITY) ? 0.f : m_used;
-      // ---- P = exp2(s * scale*log2e - m), bf16, written K-major / 128B-swizzled over K_j (row = 128 bytes)
-      uint8_t* prow = sK(st) + row * 128;
+      // ---- P = exp2(s * scale*log2e - m) as bf16 pairs, stored over the first 32 columns of this row's S_j
       float lsum = 0.f;
+      float pk[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float pe[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          pe[i] = fast_exp2(fmaf(v[8 * c + i], sl2, -muse));  // -inf -> 0
-          lsum += pe[i];
-        }
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
-            make_uint4(pack_bf16(pe[0], pe[1]), pack_bf16(pe[2], pe[3]), pack_bf16(pe[4], pe[5]), pack_bf16(pe[6], pe[7]));
+      for (int c = 0; c < 32; ++c) {
+        const float p0 = fast_exp2(fmaf(v[2 * c], sl2, -muse));  // -inf -> 0
+        const float p1 = fast_exp2(fmaf(v[2 * c + 1], sl2, -muse));
+        lsum += p0 + p1;
+        pk[c] = __uint_as_float(pack_bf16(p0, p1));
       }
       l_run += lsum;
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_st_32x32(tmem_base + lane_base + st * TK, pk);
+      tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->p_ready[st]);
+      if (trace && threadIdx.x == 64 && j < 13) trace[5 + 2 * j] = clock64();
     }
 
-    // ---- epilogue: O / l -> bf16 -> (* gate) -> global, staged through smem so rows are written as 256 B runs
+    // ---- epilogue: O / l -> bf16 -> (* gate) -> global, staged through smem so rows are written as 256 B runs.
+    // The 16 gate vectors this lane needs are requested BEFORE waiting for the last PV (4.3 us of exposed L2 round
+    // trips otherwise: the loop below was load -> multiply -> store, one row pair at a time).
     const bool have = ntiles > 0;
+    const size_t HD = (size_t)d.H * 128;
+    const int rsel = lane >> 4, ch = lane & 15;
+    const size_t off0 = ((size_t)b * d.S + q0 + quarter * 32 + rsel) * HD + (size_t)h * 128 + ch * 8;
+    const int rows_ok = d.S - (q0 + quarter * 32);  // rows of this warp's slab inside the sequence
+    uint4 gv[16];
+    if (d.gate) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (2 * i + rsel < rows_ok) gv[i] = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + off0 + (size_t)(2 * i) * HD);
+    }
     if (have) {
       mbar_wait(&ctl->pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
       tc_fence_after();
     }
+    if (trace && threadIdx.x == 64) trace[30] = clock64();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     uint8_t* stg = smem + Q_BYTES + (warp - 2) * 8192;  // 32 rows x 256 B, private to this warp; all tiles are dead
     uint8_t* srow = stg + lane * 256;
@@ -305,26 +348,21 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       }
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        const int ch = c * 4 + cc;  // 16-byte chunk of the row
-        *reinterpret_cast<uint4*>(srow + ((ch ^ (lane & 7)) << 4)) =
+        const int chk = c * 4 + cc;  // 16-byte chunk of the row
+        *reinterpret_cast<uint4*>(srow + ((chk ^ (lane & 7)) << 4)) =
             make_uint4(pack_bf16(o[8 * cc] * inv, o[8 * cc + 1] * inv), pack_bf16(o[8 * cc + 2] * inv, o[8 * cc + 3] * inv),
                        pack_bf16(o[8 * cc + 4] * inv, o[8 * cc + 5] * inv), pack_bf16(o[8 * cc + 6] * inv, o[8 * cc + 7] * inv));
       }
     }
     __syncwarp();
-    const size_t HD = (size_t)d.H * 128;
-    const int rsel = lane >> 4, ch = lane & 15;
-#pragma unroll 4
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int r = 2 * i + rsel;
-      const int q = q0 + quarter * 32 + r;
-      if (q < d.S) {
+      if (r < rows_ok) {
         uint4 val = *reinterpret_cast<const uint4*>(stg + r * 256 + ((ch ^ (r & 7)) << 4));
-        const size_t off = ((size_t)b * d.S + q) * HD + (size_t)h * 128 + ch * 8;
         if (d.gate) {
-          const uint4 gv = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + off);
           const uint32_t* vi = reinterpret_cast<const uint32_t*>(&val);
-          const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gv);
+          const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gv[i]);
           uint32_t rr[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -333,11 +371,12 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
           }
           val = make_uint4(rr[0], rr[1], rr[2], rr[3]);
         }
-        *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off) = val;
+        *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off0 + (size_t)(2 * i) * HD) = val;
       }
     }
   }
 
+  if (trace && threadIdx.x == 64) trace[31] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<256>(tmem_base);

@@ -137,6 +137,14 @@ ECHO_DEVICE void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM (bf16 pairs packed in 32-bit columns, row i = lane i), B from shared memory.
+ECHO_DEVICE void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // CTA-pair MMA: M = 256 (128 rows from each CTA's smem / TMEM), B is split in two N halves across the CTAs.
 ECHO_DEVICE void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

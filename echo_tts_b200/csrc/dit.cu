@@ -148,8 +148,11 @@ extern "C" int echo_dit_configure(echo_handle* h, const echo_dit_config* c) {
   h->in_proj_w = (bf16*)h->dalloc((size_t)D * c->latent_size * 2);
   h->in_proj_b = (float*)h->dalloc((size_t)D * 4);
   h->out_norm = (float*)h->dalloc((size_t)D * 4);
-  h->out_proj_w = (bf16*)h->dalloc((size_t)c->latent_size * D * 2);
-  h->out_proj_b = (float*)h->dalloc((size_t)c->latent_size * 4);
+  // out_proj runs on the tcgen05 GEMM: N = latent_size is padded to 128 zero rows (only latent_size columns are stored)
+  h->out_proj_w = (bf16*)h->dalloc((size_t)128 * D * 2);
+  h->out_proj_b = (float*)h->dalloc((size_t)128 * 4);
+  if (h->out_proj_w) cudaMemset(h->out_proj_w, 0, (size_t)128 * D * 2);
+  if (h->out_proj_b) cudaMemset(h->out_proj_b, 0, (size_t)128 * 4);
   for (void* p : h->owned) if (!p) { set_error("echo_dit_configure: out of device memory"); return ECHO_ERR_CUDA; }
   h->dit_configured = true;
   return ECHO_OK;
@@ -561,6 +564,32 @@ int build_mod_tables(echo_handle* h, const float* t_dev, int n, int round_t, flo
   return ECHO_OK;
 }
 
+// EchoDiT.in_proj (model.py:586) for `copies` stacked CFG branches: X[c*rows + r, :] = bf16(x[r, :]) W^T + b.
+// x is rounded to bf16 first, exactly as the reference casts the sampler state to the model dtype (inference.py:488);
+// the K = 80 contraction is one zero-padded K block of the tcgen05 GEMM, the copies are GEMM batches sharing A.
+int dit_in_proj(echo_handle* h, const float* x, float* X, int rows, int copies, cudaStream_t s) {
+  const echo_dit_config& c = h->cfg;
+  bf16* x16 = (bf16*)h->wsget("dit.x16", (size_t)rows * c.latent_size * 2, s);
+  if (!x16) { set_error("out of memory"); return ECHO_ERR_CUDA; }
+  cast_f32_to_bf16(x, x16, (int64_t)rows * c.latent_size, s);
+  GemmCall g = plain_gemm(x16, c.latent_size, h->in_proj_w, c.latent_size, rows, c.model_size, c.latent_size);
+  g.p.batches = copies; g.p.a_batch_div = copies; g.a_batch_stride = (int64_t)rows * c.latent_size;
+  g.p.bias = h->in_proj_b; g.p.out_f32 = X; g.p.ld_f32 = c.model_size;
+  ECHO_GEMM(g);
+  return ECHO_OK;
+}
+
+// out_norm + out_proj (model.py:601-604): RMSNorm with weight -> bf16, then a GEMM whose N is padded to 128.
+int dit_out_proj(echo_handle* h, const float* X, bf16* XN, float* v_out, int rows, cudaStream_t s) {
+  const echo_dit_config& c = h->cfg;
+  rmsnorm_affine(X, XN, h->out_norm, nullptr, rows, c.model_size, 0, 0, c.norm_eps, s);
+  GemmCall g = plain_gemm(XN, c.model_size, h->out_proj_w, c.model_size, rows, 128, c.model_size);
+  g.p.bias = h->out_proj_b; g.p.out_f32 = v_out; g.p.ld_f32 = c.latent_size; g.p.n_valid = c.latent_size;
+  g.bn = 64;  // 2 x more CTAs than one 128-wide tile per row block; the GEMM is latency-bound either way
+  ECHO_GEMM(g);
+  return ECHO_OK;
+}
+
 struct KvSide {  // one cached key/value segment as the DiT layers see it
   void* const* K = nullptr;
   void* const* V = nullptr;
@@ -650,7 +679,7 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
     if (f.layer_out && f.layer_out[i])
       ECHO_CUDA(cudaMemcpyAsync(f.layer_out[i], sc.X, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, s));
   }
-  out_norm_proj(sc.X, h->out_norm, h->out_proj_w, h->out_proj_b, v_out, rows, D, c.latent_size, eps, s);
+  ECHO_TRY(dit_out_proj(h, sc.X, sc.XN, v_out, rows, s));
   ECHO_CUDA(cudaGetLastError());
   return ECHO_OK;
 }
@@ -710,7 +739,7 @@ extern "C" int echo_dit_forward(echo_handle* h, const float* x, const float* t, 
   const int Ps = Ls / c.speaker_patch_size;
   mask_eff_len(text_mask, eff, b, Lt, Lt, 1, s);
   mask_eff_len(speaker_mask, eff + b, b, Ps, Ls, c.speaker_patch_size, s);
-  in_proj(x, h->in_proj_w, h->in_proj_b, sc.X, rows, c.latent_size, D, 1, s);
+  ECHO_TRY(dit_in_proj(h, x, sc.X, rows, 1, s));
   FwdCtx f;
   f.nb = b; f.S = S; f.start_pos = start_pos; f.mod = mod; f.mod_n = b; f.mod_j = 0; f.rows_per_group = S;
   f.text.K = Kt; f.text.V = Vt; f.text.len = Lt; f.text.mask = text_mask; f.text.mask_ld = Lt; f.text.mask_stride = 1;
@@ -821,7 +850,7 @@ int euler_loop(echo_handle* h, const echo_sampler_args* a, SamplerState* st, flo
     const float t = st->t[i], t_next = st->t[i + 1];
     const bool has_cfg = (t >= a->cfg_min_t) && (t <= a->cfg_max_t);
     const int nbr = has_cfg ? 3 : 1;
-    in_proj(x, h->in_proj_w, h->in_proj_b, sc.X, B * S, C, D, nbr, s);
+    ECHO_TRY(dit_in_proj(h, x, sc.X, B * S, nbr, s));
     FwdCtx f;
     f.nb = nbr * B; f.S = S; f.start_pos = start_pos; f.mod = st->mod; f.mod_n = a->num_steps; f.mod_j = i;
     f.rows_per_group = 0;

@@ -2,7 +2,9 @@
 #include "gemm.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -87,6 +89,10 @@ bool tma_map_bf16(void* out, const void* ptr, int rank, uint64_t d0, uint64_t d1
   return get_tensor_map(static_cast<CUtensorMap*>(out), ptr, rank, d0, d1, d2, s1, s2, box0, box1, row_bytes);
 }
 
+static std::atomic<int> g_deterministic{0};
+void gemm_set_deterministic(int on) { g_deterministic.store(on ? 1 : 0); }
+int gemm_get_deterministic() { return g_deterministic.load(); }
+
 static int g_num_sms = 0;
 int gemm_num_sms() {
   if (g_num_sms == 0) {
@@ -108,7 +114,8 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * p.batches * ((p.N + BN - 1) / BN);
+  const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * p.batches * ((p.N + BN - 1) / BN) *
+                    (p.split_k > 1 ? p.split_k : 1);
   const int slots = gemm_num_sms() / CG;
   const int grid = (tiles < slots ? tiles : slots) * CG;
   cudaError_t err;
@@ -117,6 +124,7 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
     if (prof_enabled())
       snprintf(tag, sizeof(tag), "gemm epi=%d M=%d x%d N=%d K=%d taps=%d bn=%d cg=%d", EPI, p.M, p.batches, p.N, p.Kc,
                p.taps, BN, CG);
+    if (prof_enabled() && p.split_k > 1) snprintf(tag + strlen(tag), sizeof(tag) - strlen(tag), " sk=%d", p.split_k);
     else tag[0] = 0;
     ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s, tag);
     err = launch_k(kern, dim3(grid), dim3(GEMM_THREADS), SMEM, s, CG, ma, mb, p);
@@ -131,9 +139,15 @@ struct TileCfg { int bn, cg; };
 static TileCfg pick_cfg(const GemmCall& c) {
   const GemmParams& p = c.p;
   const int sms = gemm_num_sms();
-  // CTA pairs are opt-in (cg == 2): measured on B200 they lose 3-8 % at the DiT shapes (M = 640 / 1920 wastes half a
-  // pair tile per column and the wave count does not drop), see profiles/r01_gemm_cta_pair_vs_single.txt
-  const bool allow_pair = c.cg == 2 && (p.N % 128 == 0);
+  // CTA pairs (cta_group::2, 256-row tiles, B split across the pair) cut the per-SM operand ingest from 48 KB to
+  // 32 KB per K block. Measured on B200 (profiles/r01_gemm_cta_pair_vs_single.txt): +6-7 % for the multi-tile QKV and
+  // SwiGLU GEMMs, neutral-to-negative for the single-wave generic GEMMs (M = 640 / 1920 wastes half a pair tile
+  // per column), so those stay opt-in.
+  static const int env_cg_generic = [] { const char* e = std::getenv("ECHO_GEMM_CG_GENERIC"); return e ? atoi(e) : 0; }();
+  // generic GEMMs: pairs pay off once there are enough rows to fill pair tiles (M = 1920: w2 48.0 -> 42.6 us,
+  // wo 24.3 -> 23.1 us); at M = 640 they lose ~2-4 % (2.5 pair rows), so auto keeps single CTAs below 1024 rows
+  const bool allow_pair = (c.cg == 2 || (c.cg == 0 && env_cg_generic != 1 && (env_cg_generic == 2 || p.M >= 1024))) &&
+                          (p.N % 128 == 0);
   auto cost = [&](int bn, int cg) -> double {
     const long units = (long)((p.M + 128 * cg - 1) / (128 * cg)) * p.batches * ((p.N + bn - 1) / bn);
     const long slots = sms / cg;
@@ -142,8 +156,9 @@ static TileCfg pick_cfg(const GemmCall& c) {
     return waves * per + 12.0;  // small constant: prefer fewer, larger tiles on ties
   };
   if (p.epi != EPI_GENERIC) {
-    if (c.cg == 2 || (allow_pair && cost(256, 2) < cost(256, 1))) return {256, 2};
-    return {256, 1};
+    static const int env_cg = [] { const char* e = std::getenv("ECHO_GEMM_CG"); return e ? atoi(e) : 0; }();  // tuning only
+    if (c.cg == 1 || env_cg == 1 || p.N % 256 != 0 || p.M <= 128) return {256, 1};
+    return {256, 2};
   }
   if (c.bn) return {c.bn, (c.cg == 2 && (c.bn == 256 || c.bn == 128)) ? 2 : 1};
   if (p.N % 64 != 0) {
@@ -176,7 +191,37 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   if (p.N % 32 != 0 || (c.lda % 8) != 0 || (c.ldb % 8) != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15)) return cudaErrorInvalidValue;
 
-  const TileCfg tc = pick_cfg(c);
+  // Split-K: a single-wave GEMM whose tiles cover well under the 148 SMs (wo / w2 at M = 640: 40 tiles of 128 x 256)
+  // is bound by the per-SM operand ingest of its few CTAs. When the epilogue is a pure accumulate into the fp32
+  // residual stream (out = resid + gate * acc, resid aliasing out) the K blocks are split over several CTAs per
+  // tile and the partial sums meet in the residual through fp32 vector atomics. The sum order then varies from run
+  // to run in the last fp32 bit; after a few bf16 re-quantisations that decorrelates two runs down to the bf16
+  // rounding-noise floor (same size as the error against the fp32 reference).
+  // echo_set_deterministic(1) switches it off (bit-reproducible, ~4 % slower at batch 1).
+  GemmCall cc = c;
+  p.split_k = 1;
+  {
+    static const int env_sk = [] { const char* e = std::getenv("ECHO_SPLIT_K"); return e ? atoi(e) : 0; }();
+    const bool eligible = p.epi == EPI_GENERIC && p.resid != nullptr && p.resid == p.out_f32 && p.out_bf16 == nullptr &&
+                          p.taps == 1 && p.batches == 1 && p.N % 256 == 0;
+    int want = c.split_k ? c.split_k : (g_deterministic.load() ? 1 : env_sk);
+    if (eligible && want == 0) {
+      const int tiles256 = ((p.M + 127) / 128) * (p.N / 256);
+      const int kb = (p.Kc + 63) / 64;
+      if (tiles256 * 2 <= gemm_num_sms() && kb >= 16) {
+        want = gemm_num_sms() / tiles256;
+        if (want > 4) want = 4;
+        while (want > 1 && kb / want < 8) --want;
+      }
+    }
+    if (eligible && want > 1) {
+      p.split_k = want;
+      cc.bn = 256;
+      cc.cg = 1;
+    }
+  }
+  cc.p = p;
+  const TileCfg tc = pick_cfg(cc);
   const int bn = tc.bn, cg = tc.cg;
   if (bn == 0) return cudaErrorInvalidValue;
   const bool small_k = (p.Kc % 64 != 0) && (p.Kc % 96 == 0) && bn == 96;  // DAC last stage: 96 channels / tap

@@ -46,6 +46,8 @@ struct GemmParams {
   const float* alpha;  // snake alpha [col_mod]
   const float* alpha_inv;  // optional 1 / (alpha + 1e-9) [col_mod]
   int col_mod;
+  int split_k;  // EPI_GENERIC with resid == out_f32 only: > 1 splits the K blocks over that many CTAs per tile (atomic adds)
+  int n_valid;  // EPI_GENERIC: output columns >= n_valid are computed but not stored (N padded to a tile multiple); 0 = N
   // ---- EPI_SWIGLU: tile columns [0,BN/2) hold w1 rows, [BN/2,BN) the matching w3 rows;
   //      out_bf16[r, n0/2 + c] = silu(a) * b.     (uses out_bf16 / ld_bf16)
   // ---- EPI_QKV: N = nsec * sec_width, each 128-column group is normalised / rotated independently.
@@ -73,10 +75,13 @@ struct GemmCall {
   GemmParams p;
   int bn;  // tile N override (0 = auto)
   int cg;  // CTA-group override: 0 = auto, 1 = single CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2)
+  int split_k;  // 0 = auto, 1 = off, n = force n splits (ignored unless the epilogue is a pure residual accumulate)
 };
 
 cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s);
 int gemm_num_sms();
+void gemm_set_deterministic(int on);  // 1: never use atomic split-K (bit-reproducible results)
+int gemm_get_deterministic();
 
 // Cached cuTensorMapEncodeTiled for a bf16 tensor whose dim0 is contiguous (rank 2 or 3; strides of dims >= 1 in
 // BYTES). `out` points at a 128-byte CUtensorMap; box = (box0, box1, 1); swizzle span = row_bytes (128 / 64 / 32).

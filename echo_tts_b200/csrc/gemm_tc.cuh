@@ -111,9 +111,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   const int tiles_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * p.batches * tiles_n;
   const int kb_per_tap = (p.Kc + BK * ATOMS - 1) / (BK * ATOMS);
   const int num_kb = kb_per_tap * p.taps;
+  // split-K (EPI_GENERIC accumulate mode only): `splits` consecutive work units share one output tile and each
+  // reduces a contiguous slice of the K blocks; partial sums meet in out_f32 through fp32 vector atomics
+  const int splits = p.split_k > 1 ? p.split_k : 1;
+  const int num_tiles = tiles_m * p.batches * tiles_n * splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -149,13 +152,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int unit = tile0; unit < num_tiles; unit += tile_step) {
+        const int sk = unit % splits, tile = unit / splits;
         const int mt = tile % tiles_m;
         const int rest = tile / tiles_m;
         const int bt = rest % p.batches;
         const int nt = rest / p.batches;
         const int m0 = (mt * CG + (int)cta_rank) * GEMM_BM, n0 = nt * BN + (int)cta_rank * BNH;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           const int tap = kb / kb_per_tap;
           const int kc0 = (kb - tap * kb_per_tap) * (BK * ATOMS);
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -172,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
             }
           }
-          if (trace && kb == 0 && tile == tile0) trace[2] = clock64();
+          if (trace && kb == kb_lo && unit == tile0) trace[2] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -184,15 +189,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      for (int unit = tile0; unit < num_tiles; unit += tile_step, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int sk = unit % splits;
+        const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (trace && kb == 0 && tile == tile0) trace[3] = clock64();
+          if (trace && kb == kb_lo && unit == tile0) trace[3] = clock64();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_ATOM * ATOMS;
 #pragma unroll
@@ -202,8 +209,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 bf16 (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-              if constexpr (CG == 2) tc_mma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | a | k) != 0 ? 1u : 0u);
-              else tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | a | k) != 0 ? 1u : 0u);
+              if constexpr (CG == 2) tc_mma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
+              else tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
             }
           }
           // smem slot reusable (in both CTAs of a pair) once these MMAs retire
@@ -223,7 +230,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int half = ew >> 2;      // which half of the column chunks
     int it = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+    for (int unit = tile0; unit < num_tiles; unit += tile_step, ++it) {
+      const int sk = unit % splits, tile = unit / splits;
       const int mt = tile % tiles_m;
       const int rest = tile / tiles_m;
       const int bt = rest % p.batches;
@@ -258,22 +266,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cmod = p.col_mod > 0 ? p.col_mod : p.N;  // multiple of 32, so a 32-column chunk never wraps
         const size_t row0 = (size_t)bt * p.M + mbase;      // global row of this warp's slab
         const int rows_left = p.M - mbase;                 // rows of the slab inside the matrix (may be <= 0)
+        // split-K: out_f32 already holds the residual; every split adds its gated partial sum atomically
+        const float* resid = splits > 1 ? nullptr : p.resid;
         float4 rcur[8], rnext[8];
         auto load_resid = [&](int ch, float4* r) {
           const int c0 = n0 + ch * 32;
-          if (p.resid != nullptr && ch < BN / 32 && c0 < p.N) {
+          if (resid != nullptr && ch < BN / 32 && c0 < p.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = sub + 4 * i;
-              if (rr < rows_left) r[i] = *reinterpret_cast<const float4*>(p.resid + (row0 + rr) * p.ld_f32 + c0 + 4 * c4);
+              if (rr < rows_left) r[i] = *reinterpret_cast<const float4*>(resid + (row0 + rr) * p.ld_f32 + c0 + 4 * c4);
             }
           }
         };
         // Pull this tile's residual rows into L2 while the MMAs still run: the read-modify-write of the fp32
         // residual stream is a chip-wide burst (every CTA reaches its epilogue at the same time) and with only one
         // chunk of loads in flight per thread it was latency-bound at ~3 TB/s (10.7 us per 128 x 256 tile).
-        if (p.resid != nullptr && lane < rows_left) {
-          const char* rp = reinterpret_cast<const char*>(p.resid + (row0 + lane) * p.ld_f32 + n0);
+        if (resid != nullptr && lane < rows_left) {
+          const char* rp = reinterpret_cast<const char*>(resid + (row0 + lane) * p.ld_f32 + n0);
           const int bytes = (p.N - n0 < BN ? p.N - n0 : BN) * 4;
           for (int o = half * 128; o < bytes; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
         }
@@ -292,11 +302,12 @@ ECHO_CHUNK_UNROLL
             tc_ld_32x32(tbase + ch * 32, v);
             load_resid(ch + 2, rnext);
             const int c0 = n0 + ch * 32;
-            const bool col_ok = c0 < p.N;            // warp-uniform
+            const int nstore = p.n_valid > 0 ? p.n_valid : p.N;
+            const bool col_ok = c0 < nstore;         // warp-uniform
             const int cb = (col_ok ? c0 % cmod : 0) + 4 * c4;  // one modulo per chunk
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), a4 = g4, i4 = g4;
             if (col_ok) {
-              if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb));
+              if (p.bias && sk == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb));
               if (p.gate && p.rows_per_gate <= 0) g4 = __ldg(reinterpret_cast<const float4*>(p.gate + cb));
               if (p.act == ACT_SNAKE && p.out_bf16) {
                 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + cb));
@@ -315,7 +326,7 @@ ECHO_CHUNK_UNROLL
               for (int i = 0; i < 8; ++i) {
                 const int rr = sub + 4 * i;
                 float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-                if (rr < rows_left) {
+                if (rr < rows_left && c0 + 4 * c4 < nstore) {
                   const size_t grow = row0 + rr;
                   t.x = (t.x + b4.x) * p.scale; t.y = (t.y + b4.y) * p.scale;
                   t.z = (t.z + b4.z) * p.scale; t.w = (t.w + b4.w) * p.scale;
@@ -325,8 +336,12 @@ ECHO_CHUNK_UNROLL
                       g = __ldg(reinterpret_cast<const float4*>(p.gate + (grow / p.rows_per_gate) * (size_t)p.gate_ld + cb));
                     t.x *= g.x; t.y *= g.y; t.z *= g.z; t.w *= g.w;
                   }
-                  if (p.resid) { t.x += rcur[i].x; t.y += rcur[i].y; t.z += rcur[i].z; t.w += rcur[i].w; }
-                  if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + c0 + 4 * c4) = t;
+                  if (resid) { t.x += rcur[i].x; t.y += rcur[i].y; t.z += rcur[i].z; t.w += rcur[i].w; }
+                  if (p.out_f32) {
+                    float4* dst = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + c0 + 4 * c4);
+                    if (splits > 1) atomicAdd(dst, t);  // RED.ADD.F32x4
+                    else *dst = t;
+                  }
                   if (p.out_bf16) {
                     if (p.act == ACT_SNAKE) {
                       // snake(x) = x + sin^2(alpha x) / (alpha + 1e-9)   (autoencoder.py:96-102); the result is

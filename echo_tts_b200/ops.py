@@ -23,7 +23,8 @@ def _stream() -> int:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence[int] = (0,), bias=None,
          scale: float = 1.0, gate=None, rows_per_gate: int = 0, resid=None, out_f32=None, out_bf16=None,
-         act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0, cg: int = 0, trace=None, dbg: int = 0) -> None:
+         act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0, cg: int = 0, trace=None, dbg: int = 0,
+         split_k: int = 0) -> None:
     """out = epilogue(sum_taps a[rows + shift] @ w[:, tap*Kc:(tap+1)*Kc].T).  a: (batches, M, Kc) or (M, Kc) bf16."""
     lib = _lib.load(strict=False)
     if a.dim() == 2:
@@ -46,6 +47,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence
     d.act, d.alpha, d.col_mod, d.bn, d.cg = act, _ptr(alpha), col_mod, bn, cg
     d.trace = _ptr(trace)
     d.dbg = dbg
+    d.split_k = split_k
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm")
 
 
@@ -87,7 +89,7 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoi
 
 
 def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch.Tensor] = None,
-              scale: Optional[float] = None) -> None:
+              scale: Optional[float] = None, trace: Optional[torch.Tensor] = None) -> None:
     """q: (b, S, H, D) bf16. segments: list of dicts with keys k, v ((b, L, H, D) bf16) and optional mask (b, L) bool,
     eff_len (b,) int32, pos_limit_mult, pos_limit, causal, window."""
     lib = _lib.load(strict=False)
@@ -98,6 +100,7 @@ def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch
     d.b, d.S, d.H, d.D = b, S, H, D
     d.scale = scale if scale is not None else D ** -0.5
     d.nseg = len(segments)
+    d.trace = _ptr(trace)
     keep = []
     for i, sg in enumerate(segments):
         k, v = sg["k"], sg["v"]
@@ -117,3 +120,24 @@ def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch
         s.causal, s.window = int(sg.get("causal", 0)), int(sg.get("window", 0))
         s.batch_mod = int(sg.get("batch_mod", 0))
     _lib.check(lib.echo_op_attention(C.byref(d), _stream()), "echo_op_attention")
+
+
+def rmsnorm_affine(x: torch.Tensor, a: torch.Tensor, c0: Optional[torch.Tensor] = None, rows_per_group: int = 0,
+                   eps: float = 1e-5) -> torch.Tensor:
+    """x (rows, W) fp32; a / c0 (groups, W) fp32 -> bf16 (rows, W)."""
+    lib = _lib.load(strict=False)
+    rows, W = x.shape
+    out = torch.empty(rows, W, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.echo_op_rmsnorm_affine(x.data_ptr(), out.data_ptr(), a.data_ptr(), _ptr(c0), rows, W, rows_per_group,
+                                          a.stride(0) if a.dim() == 2 else 0, eps, _stream()), "echo_op_rmsnorm_affine")
+    return out
+
+
+def cfg_euler_update(x: torch.Tensor, v: torch.Tensor, has_cfg: bool, s_text: float, s_spk: float, dt: float,
+                     rescale: Optional[tuple] = None) -> None:
+    """In place: x += dt * combine(v). v is (3, ...) when has_cfg else (1, ...); rescale = (one_minus_t, ratio)."""
+    lib = _lib.load(strict=False)
+    omt, ratio = rescale if rescale is not None else (0.0, 1.0)
+    _lib.check(lib.echo_op_cfg_euler_update(x.data_ptr(), v.data_ptr(), x.numel(), int(has_cfg), s_text, s_spk,
+                                            int(rescale is not None), omt, ratio, dt, _stream()),
+               "echo_op_cfg_euler_update")

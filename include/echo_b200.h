@@ -95,6 +95,9 @@ int echo_create(echo_handle** out, int device);
 int echo_destroy(echo_handle* h);
 const char* echo_last_error(void);
 int echo_num_launches(echo_handle* h, int64_t* out); /* kernels launched by this handle so far */
+/* Process-wide: 1 = bit-reproducible results (disables the atomic split-K of the residual-accumulate GEMMs, ~4 % slower
+ * at batch 1); 0 (default) = fastest. Both settings meet the same tolerances against the reference. */
+int echo_set_deterministic(int on);
 
 /* ---- weights: replaces load_state_dict (reference inference.py:14-47, 56-76) ---------------------------- */
 int echo_dit_configure(echo_handle* h, const echo_dit_config* cfg);
@@ -178,7 +181,8 @@ typedef struct echo_gemm_desc {
   int bn; /* 0 = auto */
   int cg; /* 0 = auto, 1 = one CTA per tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
   int dbg;          /* tuning switches for the epilogue (0 in production) */
-  long long* trace; /* optional device buffer, 8 clock64 stamps per CTA (kernel timeline for tuning); NULL normally */
+  long long* trace; /* optional device buffer, 16 clock64 stamps per CTA (kernel timeline for tuning); NULL normally */
+  int split_k;      /* 0 = auto, 1 = off, n > 1 = n K-splits per tile (only when out_f32 == resid: atomic accumulate) */
 } echo_gemm_desc;
 int echo_op_gemm(const echo_gemm_desc* d, void* stream);
 
@@ -202,8 +206,20 @@ typedef struct echo_attn_desc {
   int b, S, H, D;    /* D = 128 or 64 */
   float scale;       /* softmax scale, 1/sqrt(D) */
   int nseg; echo_attn_segment seg[4];
+  long long* trace;  /* optional device buffer, 64 clock64 stamps per CTA (tcgen05 kernel timeline); NULL normally */
 } echo_attn_desc;
 int echo_op_attention(const echo_attn_desc* d, void* stream);
+
+/* out[r,c] = bf16( x[r,c] * rsqrt(mean_c x[r,:]^2 + eps) * a[g(r),c] + c0[g(r),c] ),  g(r) = rows_per_group > 0 ?
+ * (r / rows_per_group) * group_ld : 0; c0 may be NULL. Covers RMSNorm (model.py:86-104: a = weight) and the
+ * LowRankAdaLN modulate (model.py:76-79: a = 1 + scale, c0 = shift). x fp32 (rows, W), a / c0 fp32. */
+int echo_op_rmsnorm_affine(const float* x, void* out_bf16, const float* a, const float* c0, int rows, int W,
+                           int rows_per_group, int64_t group_ld, float eps, void* stream);
+/* x += dt * v', v' = CFG combine of the 3 branches in v (inference.py:495) when has_cfg, else v; optional temporal
+ * score rescale (inference.py:416-424) with one_minus_t and ratio precomputed by the caller. x, v fp32. */
+int echo_op_cfg_euler_update(float* x, const float* v, int64_t n_per_branch, int has_cfg, float cfg_scale_text,
+                             float cfg_scale_speaker, int has_rescale, float one_minus_t, float ratio, float dt,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -243,6 +243,19 @@ def run_full(which: str):
     elif which == "cfg2":
         spk = torch.randn(1, 212, 80, generator=torch.Generator().manual_seed(1))
         smask = torch.ones(1, 212, dtype=torch.bool)
+    elif which == "cfg5":
+        # BASELINE configs[4]: blockwise 4 x 160, 5-minute speaker reference (6400 latents = 1600 patches),
+        # speaker_kv_scale 1.5 on all layers until t < 0.9 (gradio defaults), other knobs as the handler
+        spk = torch.randn(1, 6400, 80, generator=torch.Generator().manual_seed(1))
+        smask = torch.ones(1, 6400, dtype=torch.bool)
+        knobs = dict(HANDLER_KNOBS, speaker_kv_scale=1.5, speaker_kv_min_t=0.9, speaker_kv_max_layers=24)
+        t1 = time.time()
+        lat = refblk.sample_blockwise_euler_cfg_independent_guidances(m, spk, smask, ids, tmask, seed, [160] * 4, **knobs)
+        dt = time.time() - t1
+        print(f"cfg5: reference fp32 blockwise sampler {dt:.1f} s on {torch.get_num_threads()} threads")
+        torch.save(dict(latent=lat.clone(), seconds=torch.tensor(dt), threads=torch.tensor(torch.get_num_threads())),
+                   os.path.join(GOLD, "dit_full_cfg5.pt"))
+        return
     else:
         raise SystemExit(which)
     layers = []
@@ -279,7 +292,7 @@ def run_full(which: str):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiny", action="store_true")
-    ap.add_argument("--full", choices=["cfg1", "cfg2", "dac"])
+    ap.add_argument("--full", choices=["cfg1", "cfg2", "cfg5", "dac"])
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     if a.tiny:

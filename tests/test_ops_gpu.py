@@ -234,3 +234,53 @@ def test_attention_tc_matches_mma_sync_kernel(ops, monkeypatch):
     # the last query row of a causal attention sees every key: identical problem, different kernel
     assert rel_l2(out_causal[:, -1], ref[:, -1]) < 6e-3
     assert rel_l2(out_causal[:, -1], out_tc[:, -1].float()) < 8e-3
+
+
+@pytest.mark.parametrize("rows,W,groups", [(1920, 2048, 0), (640, 2048, 0), (768, 1280, 0), (53, 1280, 0), (640, 1024, 0),
+                                           (480, 2048, 3), (37, 256, 0), (20, 512, 0), (9, 384, 0)])
+def test_rmsnorm_affine(ops, rows, W, groups):
+    """LowRankAdaLN modulate / RMSNorm (reference model.py:76-79, 99-104): fp32 statistics, one bf16 rounding.
+    Covers the warp-per-row instances (W = 256..2048) and the block-per-row fallback (W = 384)."""
+    x = _rand((rows, W), 81, scale=1.7, dtype=torch.float32)
+    g = max(groups, 1)
+    a = 1.0 + _rand((g, W), 82, scale=0.3, dtype=torch.float32)
+    c0 = _rand((g, W), 83, scale=0.5, dtype=torch.float32)
+    rpg = rows // g if groups else 0
+    for shift in (c0, None):
+        out = ops.rmsnorm_affine(x, a, shift, rows_per_group=rpg)
+        xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5)
+        idx = (torch.arange(rows, device="cuda") // rpg) if groups else torch.zeros(rows, dtype=torch.long, device="cuda")
+        ref = xn * a[idx] + (shift[idx] if shift is not None else 0.0)
+        assert (out.float() - ref.to(torch.bfloat16).float()).abs().max() <= 2 * ref.abs().max() * 2 ** -8
+        assert rel_l2(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("has_cfg,rescale", [(True, None), (False, None), (True, (0.37, 1.18)), (False, (0.9, 0.8))])
+def test_cfg_euler_update(ops, has_cfg, rescale):
+    """v = v_c + s_t (v_c - v_ut) + s_s (v_c - v_us) (inference.py:495), temporal rescale (inference.py:416-424),
+    x += v (t_next - t) (inference.py:515); fp32 elementwise -> tight tolerance."""
+    n = 2 * 640 * 80
+    x = _rand((n,), 91, dtype=torch.float32)
+    v = _rand((3 if has_cfg else 1, n), 92, dtype=torch.float32)
+    x0 = x.clone()
+    ops.cfg_euler_update(x, v, has_cfg, 3.0, 8.0, -0.025, rescale)
+    vv = v[0] + 3.0 * (v[0] - v[1]) + 8.0 * (v[0] - v[2]) if has_cfg else v[0]
+    if rescale is not None:
+        omt, ratio = rescale
+        vv = 1.0 / omt * (ratio * (omt * vv + x0) - x0)
+    ref = x0 + vv * -0.025
+    assert torch.allclose(x, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,N,K,split", [(640, 2048, 2048, 0), (640, 2048, 5888, 3), (200, 512, 1280, 2), (640, 1024, 1024, 4),
+                                         (77, 256, 4096, 4), (1920, 2048, 2048, 2)])
+def test_gemm_split_k_residual_accumulate(ops, M, N, K, split):
+    """x += gate * (a @ w.T) with the K blocks split over several CTAs per tile (fp32 vector atomics into the residual
+    stream). split = 0 lets the library decide (M = 640 picks 3 splits)."""
+    a, w = _rand((M, K), 101), _rand((N, K), 102, scale=K ** -0.5)
+    gate = _rand((1, N), 103, dtype=torch.float32)
+    bias = _rand((N,), 104, dtype=torch.float32)
+    res = _rand((M, N), 105, dtype=torch.float32)
+    ref = res + (a.float() @ w.float().T + bias) * gate
+    ops.gemm(a, w, bias=bias, gate=gate, resid=res, out_f32=res, split_k=split)
+    assert rel_l2(res, ref) < 1e-5
