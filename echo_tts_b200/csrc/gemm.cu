@@ -121,11 +121,10 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
   cudaError_t err;
   {
     char tag[96];
+    tag[0] = 0;
     if (prof_enabled())
-      snprintf(tag, sizeof(tag), "gemm epi=%d M=%d x%d N=%d K=%d taps=%d bn=%d cg=%d", EPI, p.M, p.batches, p.N, p.Kc,
-               p.taps, BN, CG);
-    if (prof_enabled() && p.split_k > 1) snprintf(tag + strlen(tag), sizeof(tag) - strlen(tag), " sk=%d", p.split_k);
-    else tag[0] = 0;
+      snprintf(tag, sizeof(tag), "gemm epi=%d M=%d x%d N=%d K=%d taps=%d bn=%d cg=%d sk=%d", EPI, p.M, p.batches, p.N,
+               p.Kc, p.taps, BN, CG, p.split_k > 1 ? p.split_k : 1);
     ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s, tag);
     err = launch_k(kern, dim3(grid), dim3(GEMM_THREADS), SMEM, s, CG, ma, mb, p);
   }

@@ -142,7 +142,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above touched only shared memory / TMEM / the kernel parameters: it overlaps the predecessor's tail
+  // Everything above touched only shared memory / TMEM / the kernel parameters: it overlaps the predecessor's tail.
+  // So does the first pipeline fill of the B operand: B is always a weight matrix (written at load time, never by a
+  // kernel of the chain), so its TMA loads may start before the predecessor has finished; only A waits.
+  int b_prefetched = 0;  // k-blocks of this CTA's first work unit whose B tiles are already in flight
+  if (warp == 0 && lane == 0 && !p.no_b_prefetch && tile0 < num_tiles) {
+    const int sk = tile0 % splits, tile = tile0 / splits;
+    const int rest = tile / tiles_m;
+    const int bt = rest % p.batches;
+    const int nt = rest / p.batches;
+    const int n0 = nt * BN + (int)cta_rank * BNH;
+    const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
+    const int pre = (kb_hi - kb_lo) < STAGES ? (kb_hi - kb_lo) : STAGES;
+    for (int i = 0; i < pre; ++i) {
+      const int kb = kb_lo + i;
+      const int tap = kb / kb_per_tap;
+      const int kc0 = (kb - tap * kb_per_tap) * (BK * ATOMS);
+      if (leader) mbar_expect_tx(&full_bar[i], STAGE_BYTES * CG);  // A's bytes are counted too; they are issued after the wait
+      uint8_t* sb = smem + i * STAGE_BYTES + A_ATOM * ATOMS;
+#pragma unroll
+      for (int a = 0; a < ATOMS; ++a) {
+        if constexpr (CG == 2) tma_load_2d_pair(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+        else tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+      }
+    }
+    b_prefetched = pre;
+  }
   pdl_wait();
   pdl_trigger();
   if (trace && threadIdx.x == 0) { trace[0] = t_entry; trace[1] = clock64(); }
@@ -163,18 +188,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           const int tap = kb / kb_per_tap;
           const int kc0 = (kb - tap * kb_per_tap) * (BK * ATOMS);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);  // counts both CTAs' bytes
+          const bool b_done = unit == tile0 && (kb - kb_lo) < b_prefetched;  // B (and expect_tx) issued before pdl_wait
+          if (!b_done) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);  // counts both CTAs' bytes
+          }
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_ATOM * ATOMS;
 #pragma unroll
           for (int a = 0; a < ATOMS; ++a) {
             if constexpr (CG == 2) {
               tma_load_3d_pair(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
-              tma_load_2d_pair(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+              if (!b_done) tma_load_2d_pair(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
             } else {
               tma_load_3d(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
-              tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+              if (!b_done) tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
             }
           }
           if (trace && kb == kb_lo && unit == tile0) trace[2] = clock64();

@@ -90,3 +90,36 @@ def test_full_size_determinism_switch(base_model):
     print("fast mode: run-to-run rel-L2", rel_l2(c, d), "vs reference", rel_l2(c, g["latent"]), rel_l2(d, g["latent"]))
     assert rel_l2(c, g["latent"]) < 2e-2 and rel_l2(d, g["latent"]) < 2e-2
     assert rel_l2(c, d) < 2e-2
+
+
+def test_full_size_blockwise_long_speaker_cfg5():
+    """BASELINE configs[4]: sample_blockwise 4 x 160 with a 5-minute speaker reference (6400 latents -> 1600 speaker
+    KV patches), speaker_kv_scale 1.5 on all layers until t < 0.9, against the fp32 reference golden
+    (oracle/pin_reference.py --full cfg5). Needs the latent_* (blockwise) weights."""
+    path = os.path.join(GOLD, "dit_full_cfg5.pt")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    from echo_tts_b200.model import B200EchoDiT
+    from echo_tts_b200.sampler import sample_blockwise_euler_cfg_independent_guidances as sample_blockwise
+    cfg = DitConfig.base()
+    model = B200EchoDiT(cfg, "cuda:0").load_state_dict(iter_dit_weights(cfg, 1234, include_latent=True))
+    model.round_t_to_model_dtype = False
+    g = gold("dit_full_cfg5.pt")
+    ids, mask = byte_tokens([PROMPT], 768)
+    spk = torch.randn(1, 6400, 80, generator=torch.Generator().manual_seed(1))
+    smask = torch.ones(1, 6400, dtype=torch.bool)
+    rng = torch.Generator().manual_seed(0)  # the reference draws one block of noise per block from one CPU generator
+    noise_blocks = [torch.randn((1, 160, 80), generator=rng) for _ in range(4)]
+    knobs = dict(HANDLER_KNOBS, speaker_kv_scale=1.5, speaker_kv_min_t=0.9, speaker_kv_max_layers=24)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    out = sample_blockwise(model, spk, smask, ids, mask, 0, [160] * 4, noise_blocks=noise_blocks, **knobs)
+    ev1.record()
+    torch.cuda.synchronize()
+    e = rel_l2(out, g["latent"])
+    print(f"cfg5 blockwise final latent rel-L2 {e:.3e}; {ev0.elapsed_time(ev1):.1f} ms on B200 "
+          f"(reference fp32 CPU: {float(g['seconds']):.0f} s on {int(g['threads'])} threads)")
+    assert tuple(out.shape) == (1, 640, 80) and e < 2e-2, e
+    del model
+    torch.cuda.empty_cache()
