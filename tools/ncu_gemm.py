@@ -1,4 +1,5 @@
-"""Three launches each of the four DiT GEMM kinds at M=1920 (for `ncu --set full -k regex:gemm_tc`)."""
+"""Three rounds of the four DiT GEMM kinds + the joint attention at M = 3*640 (env M=640 for the non-CFG shapes),
+for `ncu --set full -k regex:"gemm_tc|attn_tc" -s 10 -c 5`."""
 import os
 import sys
 
@@ -22,10 +23,22 @@ nw = torch.ones(D, device=dev)
 pos = torch.arange(4096, device=dev)[:, None] * (1e4 ** (-torch.arange(64, device=dev) / 64.0))[None]
 cos, sin = torch.cos(pos).contiguous(), torch.sin(pos).contiguous()
 hh = torch.empty(M, I, device=dev, dtype=torch.bfloat16)
+b, S, H, Dh = M // 640, 640, 16, 128
+q = torch.randn(b, S, H, Dh, device=dev).bfloat16()
+k = torch.randn(b, S, H, Dh, device=dev).bfloat16()
+v = torch.randn(b, S, H, Dh, device=dev).bfloat16()
+kt = torch.randn(1, 768, H, Dh, device=dev).bfloat16()
+ks = torch.randn(1, 53, H, Dh, device=dev).bfloat16()
+g = torch.rand(b, S, H * Dh, device=dev).bfloat16()
+ao = torch.empty(b, S, H * Dh, device=dev, dtype=torch.bfloat16)
+eff = torch.tensor([36, 0, 36][:b], dtype=torch.int32, device=dev)
+effs = torch.tensor([53, 53, 0][:b], dtype=torch.int32, device=dev)
+segs = [dict(k=k, v=v), dict(k=kt, v=kt, eff_len=eff, batch_mod=1), dict(k=ks, v=ks, eff_len=effs, batch_mod=1)]
 for _ in range(3):
     ops.gemm_qkv(x, w_qkv, outs, [nw, nw, None, None], [8, 8, 0, 0], [0, 0, 0, 1], D, cos, sin, 128, pos_period=640)
     ops.gemm_swiglu(x, w_13, hh)
     ops.gemm(x, w_o, gate=gate, resid=res, out_f32=res)
     ops.gemm(h, w_2, gate=gate, resid=res, out_f32=res)
+    ops.attention(q, segs, ao, gate=g)
 torch.cuda.synchronize()
 print("ok")
