@@ -99,6 +99,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the main kernels from the committed `ncu --set full` capture (profiles/), or {}."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return json.load(open(p))["kernels"]
+    except Exception:
+        return {}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -126,19 +135,27 @@ def oracle_sample_seconds(sd, dsd, pca, threads):
             state["kt"] = O.kv_cache_text(sd, cfg, ids, mask)
             state["ks"] = O.kv_cache_speaker(sd, cfg, spk)
             state["kv_s"] = time.time() - t0
+            state["kt3"], state["ks3"] = O._batch3(state["kt"]), O._batch3(state["ks"])
+            state["mask3"] = torch.cat([mask, torch.zeros_like(mask), mask])       # inference.py:474
+            state["smask3"] = torch.cat([smask, smask, torch.zeros_like(smask)])   # inference.py:475
 
     def step(seed):
+        """One CFG forward (3 branches stacked, as inference.py:487-494) + one plain forward (inference.py:497-504)
+        + a 16-latent DAC decode; a request is 20 of each forward kind, the KV caches and 40 x 16 latents of decode."""
         with torch.inference_mode():
             x = torch.randn(1, 640, 80, generator=torch.Generator().manual_seed(seed))
             t0 = time.time()
-            O.dit_forward(sd, cfg, x, torch.full((1,), 0.5), mask, smask, state["kt"], state["ks"])
-            t_fwd = time.time() - t0
+            O.dit_forward(sd, cfg, x.repeat(3, 1, 1), torch.full((3,), 0.75), state["mask3"], state["smask3"], state["kt3"],
+                          state["ks3"])
+            t_cfg = time.time() - t0
+            t0 = time.time()
+            O.dit_forward(sd, cfg, x, torch.full((1,), 0.25), mask, smask, state["kt"], state["ks"])
+            t_plain = time.time() - t0
             z = torch.randn(1, 16, 80, generator=torch.Generator().manual_seed(seed))
             t0 = time.time()
             O.ae_decode(dsd, dcfg, pca[0], pca[1], pca[2], z)
             t_dac = time.time() - t0
-        # request = 20 CFG steps (3 branches) + 20 plain steps = 80 b=1 forwards, + KV caches, + 40 x (T=16) of decode
-        return 80 * t_fwd + state["kv_s"] + 40 * t_dac, t_fwd + t_dac
+        return 20 * t_cfg + 20 * t_plain + state["kv_s"] + 40 * t_dac, t_cfg + t_plain + t_dac
 
     return prepare, step
 
@@ -165,8 +182,8 @@ def run_reference(args):
         wall += w
     req_s = sum(est) / len(est)
     value = AUDIO_SECONDS / req_s
-    sample = ("per step: one fp32 b=1 DiT forward (S=640, Lt=768 padded, 53 speaker patches) + one DAC decode of 16 "
-              "latents, extrapolated to a request as 80 forwards + KV caches + 40 x decode(16)")
+    sample = ("per step: one fp32 CFG forward (3 x 640 rows) + one plain forward (640 rows) at Lt=768 padded / 53 speaker "
+              "patches + one DAC decode of 16 latents; a request = 20 x each forward + KV caches + 40 x decode(16)")
     line = {"impl": "reference", "metric": "audio-sec/sec (RTF^-1) per GPU at seq 640/40 steps", "value": value,
             "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -325,6 +342,15 @@ def run_b200(args):
     gemm_tf = rep.flops[0] / (rep.ms[0] * 1e-3) / 1e12 if rep.ms[0] > 0 else 0.0
     prof_total = sum(rep.ms)
     fl = request_flops(n_text_valid=len(PROMPT.encode()) + 1, n_spk_patches=53)
+    traffic = ncu_traffic()
+    w13 = traffic.get("gemm_w13_M1920")  # largest single share of a request: SwiGLU up-projection on CFG steps
+    traffic_note = None
+    if w13:
+        traffic_note = {"kernel": "gemm_tc_kernel<256,64,1,EPI_SWIGLU,pair> M=1920 N=11776 K=2048 (29 % of the GEMM time)",
+                        "dram_bytes_per_launch": w13["dram_bytes_read"] + w13["dram_bytes_write"],
+                        "algorithmic_bytes_per_launch": 2 * (1920 * 2048 + 11776 * 2048 + 1920 * 5888),
+                        "tensor_pipe_active_pct_ncu": w13["tensor_pipe_active_pct"],
+                        "source": "profiles/r01_ncu_traffic.json (ncu --set full, cold cache)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -337,8 +363,8 @@ def run_b200(args):
         prepare()
         est, _ = step(7)
         cpu = {"value": AUDIO_SECONDS / est, "unit": "audio-s/s", "cores": threads, "kind": "port",
-               "sample": "one fp32 b=1 DiT forward (S=640) + KV caches + DAC decode of 16 latents with the oracle, "
-                         "extrapolated to a request (80 forwards + 40 x decode(16))"}
+               "sample": "one fp32 CFG forward (3 x 640 rows) + one plain forward + KV caches + DAC decode of 16 latents "
+                         "with the oracle, extrapolated to a request (20 x each forward + 40 x decode(16))"}
 
     if rank == 0:
         line = {
@@ -354,7 +380,9 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": gemm_tf / peak_tf, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
+                         "frac": gemm_tf / peak_tf,
+                         "traffic": (traffic_note["dram_bytes_per_launch"] if traffic_note else None),
+                         "traffic_detail": traffic_note, "peak_source": f"{peak_kind} bf16_tflops_sustained",
                          "kernel": "gemm_tc_kernel (tcgen05 GEMM, all DiT/encoder/DAC contractions of one request)",
                          "gemm_launches": int(rep.launches[0]), "gemm_ms": rep.ms[0], "gemm_flops": rep.flops[0],
                          "attention_ms": rep.ms[1], "glue_ms": rep.ms[2],

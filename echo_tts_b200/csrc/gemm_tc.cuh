@@ -295,7 +295,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const size_t row0 = (size_t)bt * p.M + mbase;      // global row of this warp's slab
         const int rows_left = p.M - mbase;                 // rows of the slab inside the matrix (may be <= 0)
         // split-K: out_f32 already holds the residual; every split adds its gated partial sum atomically
-        const float* resid = splits > 1 ? nullptr : p.resid;
+        const bool atomic_out = splits > 1 || p.atomic_out != 0;
+        const float* resid = atomic_out ? nullptr : p.resid;
         float4 rcur[8], rnext[8];
         auto load_resid = [&](int ch, float4* r) {
           const int c0 = n0 + ch * 32;
@@ -367,7 +368,7 @@ ECHO_CHUNK_UNROLL
                   if (resid) { t.x += rcur[i].x; t.y += rcur[i].y; t.z += rcur[i].z; t.w += rcur[i].w; }
                   if (p.out_f32) {
                     float4* dst = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + c0 + 4 * c4);
-                    if (splits > 1) atomicAdd(dst, t);  // RED.ADD.F32x4
+                    if (atomic_out) atomicAdd(dst, t);  // RED.ADD.F32x4
                     else *dst = t;
                   }
                   if (p.out_bf16) {

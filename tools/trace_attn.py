@@ -29,7 +29,7 @@ for b in (1, 3):
     ops.attention(q, segs, out, gate=g, trace=trace)
     torch.cuda.synchronize()
     t = trace.view(ncta, 64).cpu()
-    rel = (t - t[:, :1]).float() / 1.9e3
+    rel = (t - t[:, :1]).float() / 1.9e3  # stamps are taken by thread 64 (first softmax warp)
     rel[t == 0] = float("nan")
     med = rel.nanmedian(0).values
     print(f"b={b}: {ncta} CTAs; us @1.9GHz: setup={med[1]:.2f} tiles={med[2]:.2f} q_landed={med[3]:.2f} O_done={med[30]:.2f} end={med[31]:.2f}")
