@@ -64,6 +64,15 @@ class DacConfig:
     convnext_mlp_ratio: int = 4
     decoder_dim: int = 1536
     rates: List[int] = field(default_factory=lambda: [8, 8, 4, 2])
+    # ---- encode path (reference build_ae, autoencoder.py:1144-1195): Encoder + downsample + pre_module + RVQ
+    enc_dim: int = 64
+    enc_rates: List[int] = field(default_factory=lambda: [2, 4, 8, 8])
+    enc_t_layers: int = 4          # transformer layers of the LAST encoder block (encoder_transformer_layers=[0,0,0,4])
+    enc_window: int = 512          # EncoderBlock's WindowLimitedTransformer window (autoencoder.py:855)
+    n_codebooks: int = 9
+    codebook_size: int = 1024
+    semantic_codebook_size: int = 4096
+    codebook_dim: int = 8
 
     @staticmethod
     def base() -> "DacConfig":
@@ -73,7 +82,8 @@ class DacConfig:
     def tiny() -> "DacConfig":
         """Same topology at 1/4 width, 2 transformer layers; last stage still hits the 96-channel GEMM path."""
         return DacConfig(latent_dim=256, post_layers=2, post_heads=4, post_intermediate=768, post_window=16,
-                         decoder_dim=1536, rates=[8, 8, 4, 2])
+                         decoder_dim=1536, rates=[8, 8, 4, 2], enc_dim=64, enc_rates=[2, 4], enc_t_layers=1,
+                         enc_window=512, n_codebooks=3, codebook_size=32, semantic_codebook_size=64)
 
     @property
     def hop(self) -> int:
@@ -81,6 +91,18 @@ class DacConfig:
         for r in self.rates:
             h *= r
         return h
+
+    @property
+    def enc_hop(self) -> int:
+        """Encoder stride product (DAC.hop_length); one z_q frame = enc_hop * 2**num_upsample samples (frame_length)."""
+        h = 1
+        for r in self.enc_rates:
+            h *= r
+        return h
+
+    @property
+    def frame_length(self) -> int:
+        return self.enc_hop * 2 ** self.num_upsample
 
     def as_dict(self):
         return asdict(self)

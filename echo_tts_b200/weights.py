@@ -186,10 +186,80 @@ def dac_param_specs(cfg: DacConfig) -> Iterator[Tuple[str, Tuple[int, ...], str]
     yield f"decoder.model.{n + 2}.conv.parametrizations.weight.original1", (1, clast, 7), f"normal:{0.2 / math.sqrt(7 * clast)}"
 
 
-def make_dac_weights(cfg: DacConfig, seed: int = 4321) -> Dict[str, torch.Tensor]:
-    """Decode-path parameters of build_ae() (post_module, upsample, decoder)."""
+def dac_encoder_param_specs(cfg: DacConfig) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
+    """Encode-path parameters of build_ae(): Encoder (autoencoder.py:903-929), quantizer.downsample / pre_module and
+    the semantic + residual vector quantizers (:117-157, 376-440)."""
+    def wn_conv(p, cout, cin, k, std):
+        yield f"{p}.conv.bias", (cout,), "normal:0.02"
+        yield f"{p}.conv.parametrizations.weight.original0", (cout, 1, 1), "wn_g"
+        yield f"{p}.conv.parametrizations.weight.original1", (cout, cin, k), f"normal:{std}"
+
+    def transformer(p, Cd, layers, inter):
+        for i in range(layers):
+            q = f"{p}.layers.{i}"
+            yield f"{q}.attention.wqkv.weight", (3 * Cd, Cd), "linear"
+            yield f"{q}.attention.wo.weight", (Cd, Cd), "linear"
+            yield f"{q}.feed_forward.w1.weight", (inter, Cd), "linear"
+            yield f"{q}.feed_forward.w3.weight", (inter, Cd), "linear"
+            yield f"{q}.feed_forward.w2.weight", (Cd, inter), "linear"
+            yield f"{q}.ffn_norm.weight", (Cd,), "norm"
+            yield f"{q}.attention_norm.weight", (Cd,), "norm"
+            yield f"{q}.attention_layer_scale.gamma", (Cd,), "scale:0.2"
+            yield f"{q}.ffn_layer_scale.gamma", (Cd,), "scale:0.2"
+        yield f"{p}.norm.weight", (Cd,), "norm"
+
+    d = cfg.enc_dim
+    yield from wn_conv("encoder.block.0", d, 1, 7, 1.0 / math.sqrt(7))
+    nb = len(cfg.enc_rates)
+    for bi, stride in enumerate(cfg.enc_rates):
+        cin, d = d, d * 2
+        p = f"encoder.block.{bi + 1}.block"
+        for ui in range(3):
+            q = f"{p}.{ui}.block"
+            yield f"{q}.0.alpha", (1, cin, 1), "alpha"
+            yield from wn_conv(f"{q}.1", cin, cin, 7, 1.0 / math.sqrt(7 * cin))
+            yield f"{q}.2.alpha", (1, cin, 1), "alpha"
+            yield from wn_conv(f"{q}.3", cin, cin, 1, 0.3 / math.sqrt(cin))
+        yield f"{p}.3.alpha", (1, cin, 1), "alpha"
+        yield from wn_conv(f"{p}.4", d, cin, 2 * stride, 1.0 / math.sqrt(2 * stride * cin))
+        if bi == nb - 1 and cfg.enc_t_layers > 0:
+            yield from transformer(f"{p}.5", d, cfg.enc_t_layers, 3 * d)
+    assert d == cfg.latent_dim, "latent_dim must equal enc_dim * 2 ** len(enc_rates)"
+    C = cfg.latent_dim
+    yield f"encoder.block.{nb + 1}.alpha", (1, C, 1), "alpha"
+    yield from wn_conv(f"encoder.block.{nb + 2}", C, C, 3, 1.0 / math.sqrt(3 * C))
+    M = cfg.convnext_mlp_ratio * C
+    for i in range(cfg.num_upsample):
+        p = f"quantizer.downsample.{i}"
+        yield f"{p}.0.conv.weight", (C, C, 2), f"normal:{1.0 / math.sqrt(2 * C)}"
+        yield f"{p}.0.conv.bias", (C,), "normal:0.02"
+        yield f"{p}.1.gamma", (C,), "scale:0.2"
+        yield f"{p}.1.dwconv.conv.weight", (C, 1, 7), f"normal:{1.0 / math.sqrt(7)}"
+        yield f"{p}.1.dwconv.conv.bias", (C,), "normal:0.02"
+        yield f"{p}.1.norm.weight", (C,), "norm"
+        yield f"{p}.1.norm.bias", (C,), "normal:0.1"
+        yield f"{p}.1.pwconv1.weight", (M, C), "linear"
+        yield f"{p}.1.pwconv1.bias", (M,), f"bias:{C}"
+        yield f"{p}.1.pwconv2.weight", (C, M), "linear"
+        yield f"{p}.1.pwconv2.bias", (C,), f"bias:{M}"
+    yield from transformer("quantizer.pre_module", C, cfg.post_layers, cfg.post_intermediate)
+    for name, n, size in (("semantic_quantizer", 1, cfg.semantic_codebook_size), ("quantizer", cfg.n_codebooks, cfg.codebook_size)):
+        for i in range(n):
+            p = f"quantizer.{name}.quantizers.{i}"
+            yield f"{p}.in_proj.bias", (cfg.codebook_dim,), "normal:0.02"
+            yield f"{p}.in_proj.parametrizations.weight.original0", (cfg.codebook_dim, 1, 1), "wn_g"
+            yield f"{p}.in_proj.parametrizations.weight.original1", (cfg.codebook_dim, C, 1), f"normal:{1.0 / math.sqrt(C)}"
+            yield f"{p}.out_proj.bias", (C,), "normal:0.02"
+            yield f"{p}.out_proj.parametrizations.weight.original0", (C, 1, 1), "wn_g"
+            yield f"{p}.out_proj.parametrizations.weight.original1", (C, cfg.codebook_dim, 1), f"normal:{1.0 / math.sqrt(cfg.codebook_dim)}"
+            yield f"{p}.codebook.weight", (size, cfg.codebook_dim), "embed"
+
+
+def make_dac_weights(cfg: DacConfig, seed: int = 4321, include_encoder: bool = False) -> Dict[str, torch.Tensor]:
+    """Decode-path parameters of build_ae() (post_module, upsample, decoder); with include_encoder also the encode
+    path (Encoder, quantizer.downsample / pre_module, the vector quantizers)."""
     out: Dict[str, torch.Tensor] = {}
-    specs = list(dac_param_specs(cfg))
+    specs = list(dac_param_specs(cfg)) + (list(dac_encoder_param_specs(cfg)) if include_encoder else [])
     for key, shape, kind in specs:
         if kind != "wn_g":
             out[key] = _make(key, shape, kind, seed)

@@ -370,31 +370,36 @@ def dac_rope_table(n_pos: int, head_dim: int, base: float = 10000.0):
     return torch.cos(ang).to(torch.bfloat16).float(), torch.sin(ang).to(torch.bfloat16).float()
 
 
-def dac_post_module(sd: SD, cfg, z: torch.Tensor) -> torch.Tensor:
-    """WindowLimitedTransformer.forward (autoencoder.py:786-802) over (B, C, T): causal window-`post_window` attention,
-    RoPE on all heads, LayerScale residuals (:621-626), final RMSNorm (:607)."""
+def dac_window_transformer(sd: SD, prefix: str, z: torch.Tensor, layers: int, heads: int, window: int,
+                           eps: float) -> torch.Tensor:
+    """WindowLimitedTransformer.forward (autoencoder.py:786-802) over (B, C, T): causal window attention
+    (:762-773), RoPE on all heads with the bf16 table (:805-826), LayerScale residuals (:621-626), final RMSNorm
+    (:607). Used for quantizer.post_module / pre_module (window 128) and the last EncoderBlock (window 512)."""
     x = z.transpose(1, 2)
     B, T, C = x.shape
-    H = cfg.post_heads
-    hd = C // H
+    hd = C // heads
     cos, sin = dac_rope_table(T, hd)
     i = torch.arange(T)
-    mask = ((i[None, :] <= i[:, None]) & (i[None, :] >= (i[:, None] - cfg.post_window + 1).clamp(min=0)))[None, None]
-    eps = cfg.post_norm_eps
-    for li in range(cfg.post_layers):
-        p = f"quantizer.post_module.layers.{li}"
+    mask = ((i[None, :] <= i[:, None]) & (i[None, :] >= (i[:, None] - window + 1).clamp(min=0)))[None, None]
+    for li in range(layers):
+        p = f"{prefix}.layers.{li}"
         h = rms_norm(x, None, eps) * sd[f"{p}.attention_norm.weight"]
         q, k, v = linear(h, sd[f"{p}.attention.wqkv.weight"]).split(C, dim=-1)
-        q = rope_rotate(q.reshape(B, T, H, hd), cos, sin)
-        k = rope_rotate(k.reshape(B, T, H, hd), cos, sin)
-        o = masked_attention(q, k, v.reshape(B, T, H, hd), mask).reshape(B, T, C)
+        q = rope_rotate(q.reshape(B, T, heads, hd), cos, sin)
+        k = rope_rotate(k.reshape(B, T, heads, hd), cos, sin)
+        o = masked_attention(q, k, v.reshape(B, T, heads, hd), mask).reshape(B, T, C)
         x = x + linear(o, sd[f"{p}.attention.wo.weight"]) * sd[f"{p}.attention_layer_scale.gamma"]
         h = rms_norm(x, None, eps) * sd[f"{p}.ffn_norm.weight"]
         f = p + ".feed_forward"
         y = linear(silu(linear(h, sd[f"{f}.w1.weight"])) * linear(h, sd[f"{f}.w3.weight"]), sd[f"{f}.w2.weight"])
         x = x + y * sd[f"{p}.ffn_layer_scale.gamma"]
-    x = rms_norm(x, None, eps) * sd["quantizer.post_module.norm.weight"]
+    x = rms_norm(x, None, eps) * sd[f"{prefix}.norm.weight"]
     return x.transpose(1, 2)
+
+
+def dac_post_module(sd: SD, cfg, z: torch.Tensor) -> torch.Tensor:
+    return dac_window_transformer(sd, "quantizer.post_module", z, cfg.post_layers, cfg.post_heads, cfg.post_window,
+                                  cfg.post_norm_eps)
 
 
 def dac_upsample(sd: SD, cfg, z: torch.Tensor) -> torch.Tensor:
@@ -447,3 +452,145 @@ def ae_decode(sd: SD, cfg, pca_components: torch.Tensor, pca_mean: torch.Tensor,
 
 def pca_unproject(pca_components, pca_mean, latent_scale, z):
     return (z / latent_scale) @ pca_components + pca_mean
+
+
+# ------------------------------------------------------------------------------------------------ Fish S1-DAC encode
+def causal_conv1d_strided(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, stride: int) -> torch.Tensor:
+    """CausalConvNet.forward with stride (autoencoder.py:269-289): left pad (k - stride) zeros, plus the right pad of
+    get_extra_padding_for_conv1d (:48-55) so that the last window is complete."""
+    import math
+    k = w.shape[-1]
+    pad = k - stride
+    length = x.shape[-1]
+    n_frames = (length - k + pad) / stride + 1
+    extra = (math.ceil(n_frames) - 1) * stride + (k - pad) - length
+    return torch.nn.functional.conv1d(torch.nn.functional.pad(x, (pad, extra)), w, b, stride=stride)
+
+
+def _convnext(sd: SD, p: str, z: torch.Tensor) -> torch.Tensor:
+    """ConvNeXtBlock.forward (autoencoder.py:360-373): causal depthwise conv7, LayerNorm(eps 1e-6), pw1, GELU, pw2,
+    gamma, residual."""
+    C = z.shape[1]
+    y = causal_conv1d(z, sd[f"{p}.dwconv.conv.weight"], sd[f"{p}.dwconv.conv.bias"], groups=C).transpose(1, 2)
+    y = torch.nn.functional.layer_norm(y, (C,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], eps=1e-6)
+    y = linear(torch.nn.functional.gelu(linear(y, sd[f"{p}.pwconv1.weight"], sd[f"{p}.pwconv1.bias"])),
+               sd[f"{p}.pwconv2.weight"], sd[f"{p}.pwconv2.bias"])
+    return z + (y * sd[f"{p}.gamma"]).transpose(1, 2)
+
+
+def dac_encoder(sd: SD, cfg, audio: torch.Tensor) -> torch.Tensor:
+    """Encoder.forward (autoencoder.py:903-929), causal: WN-conv7 1 -> enc_dim; per rate an EncoderBlock (:839-876) =
+    three ResidualUnits (dilations 1, 3, 9) at the input width, Snake, WN-conv(k = 2 stride, stride) doubling the
+    width, and -- last block only -- a window-512 transformer; then Snake and WN-conv3. (B, 1, L) -> (B, C, L/hop)."""
+    x = causal_conv1d(audio, _wn(sd, "encoder.block.0.conv"), sd["encoder.block.0.conv.bias"])
+    nb = len(cfg.enc_rates)
+    for bi, stride in enumerate(cfg.enc_rates):
+        p = f"encoder.block.{bi + 1}.block"
+        for ui, dil in enumerate((1, 3, 9)):
+            q = f"{p}.{ui}.block"
+            y = snake(x, sd[f"{q}.0.alpha"])
+            y = causal_conv1d(y, _wn(sd, f"{q}.1.conv"), sd[f"{q}.1.conv.bias"], dilation=dil)
+            y = snake(y, sd[f"{q}.2.alpha"])
+            y = causal_conv1d(y, _wn(sd, f"{q}.3.conv"), sd[f"{q}.3.conv.bias"])
+            x = x + y
+        x = snake(x, sd[f"{p}.3.alpha"])
+        x = causal_conv1d_strided(x, _wn(sd, f"{p}.4.conv"), sd[f"{p}.4.conv.bias"], stride)
+        if bi == nb - 1 and cfg.enc_t_layers > 0:
+            x = dac_window_transformer(sd, f"{p}.5", x, cfg.enc_t_layers, x.shape[1] // 64, cfg.enc_window, 1e-5)
+    x = snake(x, sd[f"encoder.block.{nb + 1}.alpha"])
+    return causal_conv1d(x, _wn(sd, f"encoder.block.{nb + 2}.conv"), sd[f"encoder.block.{nb + 2}.conv.bias"])
+
+
+def dac_quantizer_front(sd: SD, cfg, z: torch.Tensor) -> torch.Tensor:
+    """DownsampleResidualVectorQuantize.forward up to the quantizers (autoencoder.py:452-453): per factor a causal
+    conv(k = 2, stride 2) + ConvNeXtBlock (:418-424), then pre_module (window-128 transformer)."""
+    for i in range(cfg.num_upsample):
+        p = f"quantizer.downsample.{i}"
+        z = causal_conv1d_strided(z, sd[f"{p}.0.conv.weight"], sd[f"{p}.0.conv.bias"], 2)
+        z = _convnext(sd, f"{p}.1", z)
+    return dac_window_transformer(sd, "quantizer.pre_module", z, cfg.post_layers, cfg.post_heads, cfg.post_window,
+                                  cfg.post_norm_eps)
+
+
+def vq_nearest(sd: SD, p: str, residual: torch.Tensor):
+    """VectorQuantize.forward in eval mode (autoencoder.py:132-157): z_e = in_proj(residual); nearest code by
+    L2 distance between the L2-normalised z_e and the L2-normalised codebook; z_q = out_proj(codebook[idx])."""
+    z_e = torch.nn.functional.conv1d(residual, _wn(sd, f"{p}.in_proj"), sd[f"{p}.in_proj.bias"])
+    B, D, T = z_e.shape
+    enc = torch.nn.functional.normalize(z_e.transpose(1, 2).reshape(B * T, D))
+    cb = torch.nn.functional.normalize(sd[f"{p}.codebook.weight"])
+    dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cb.t() + cb.pow(2).sum(1, keepdim=True).t()
+    idx = (-dist).max(1)[1].reshape(B, T)
+    z_q = torch.nn.functional.conv1d(sd[f"{p}.codebook.weight"][idx].transpose(1, 2), _wn(sd, f"{p}.out_proj"),
+                                     sd[f"{p}.out_proj.bias"])
+    return z_q, idx
+
+
+def dac_encode_codes(sd: SD, cfg, z: torch.Tensor) -> torch.Tensor:
+    """The code path of DownsampleResidualVectorQuantize.forward (autoencoder.py:455-463): one semantic codebook on
+    z, then n_codebooks residual codebooks on z - z_semantic. Returns codes (B, 1 + n_codebooks, T)."""
+    z_sem, idx = vq_nearest(sd, "quantizer.semantic_quantizer.quantizers.0", z)
+    codes = [idx]
+    residual = z - z_sem
+    for i in range(cfg.n_codebooks):
+        z_q_i, idx = vq_nearest(sd, f"quantizer.quantizer.quantizers.{i}", residual)
+        residual = residual - z_q_i
+        codes.append(idx)
+    return torch.stack(codes, dim=1)
+
+
+def dac_zq_from_codes(sd: SD, cfg, codes: torch.Tensor) -> torch.Tensor:
+    """DAC.encode_zq after encode() (autoencoder.py:1116-1126): clamp, then from_codes of both quantizers (:215-225),
+    z_q = z_q_semantic + sum_i out_proj_i(codebook_i[code_i])."""
+    def from_codes(name, c, size):
+        z_q = 0.0
+        for i in range(c.shape[1]):
+            p = f"quantizer.{name}.quantizers.{i}"
+            e = sd[f"{p}.codebook.weight"][c[:, i].clamp(max=size - 1)].transpose(1, 2)
+            z_q = z_q + torch.nn.functional.conv1d(e, _wn(sd, f"{p}.out_proj"), sd[f"{p}.out_proj.bias"])
+        return z_q
+    return from_codes("semantic_quantizer", codes[:, :1], cfg.semantic_codebook_size) + \
+        from_codes("quantizer", codes[:, 1:], cfg.codebook_size)
+
+
+def dac_encode_zq(sd: SD, cfg, audio: torch.Tensor, return_parts: bool = False):
+    """DAC.encode_zq (autoencoder.py:1080-1126): right-pad to a multiple of frame_length, encoder, quantizer front,
+    codes, z_q. (B, 1, L) -> (B, C, ceil(L / frame_length)). The post_module / upsample that DAC.encode also runs
+    inside quantizer.forward (:464-465) do not influence the codes and are skipped."""
+    import math
+    if audio.dim() == 2:
+        audio = audio.unsqueeze(1)
+    L = audio.shape[-1]
+    audio = torch.nn.functional.pad(audio, (0, math.ceil(L / cfg.frame_length) * cfg.frame_length - L))
+    z_enc = dac_encoder(sd, cfg, audio)
+    z = dac_quantizer_front(sd, cfg, z_enc)
+    codes = dac_encode_codes(sd, cfg, z)
+    zq = dac_zq_from_codes(sd, cfg, codes)
+    return (zq, dict(z_enc=z_enc, z_pre=z, codes=codes)) if return_parts else zq
+
+
+def ae_encode(sd: SD, cfg, pca_components: torch.Tensor, pca_mean: torch.Tensor, latent_scale: float,
+              audio: torch.Tensor) -> torch.Tensor:
+    """inference.ae_encode (inference.py:219-224): z_q -> PCA projection -> * latent_scale. (B, 1, L) -> (B, T, 80)."""
+    zq = dac_encode_zq(sd, cfg, audio).float()
+    return ((zq.transpose(1, 2) - pca_mean) @ pca_components.T) * latent_scale
+
+
+def get_speaker_latent_and_mask(sd: SD, cfg, pca, audio: torch.Tensor, max_speaker_latent_length: int = 6400,
+                                audio_chunk_size: int = 640 * 2048, divis_by_patch_size: int = 4):
+    """inference.get_speaker_latent_and_mask (inference.py:240-283), pad_to_max=False: encode in 640-latent chunks
+    (last one zero padded), keep the latents of complete frames, trim to a multiple of the patch size."""
+    hop = cfg.frame_length
+    audio = audio[:, : max_speaker_latent_length * hop]
+    lat = []
+    for i in range(0, audio.shape[1], audio_chunk_size):
+        chunk = audio[:, i:i + audio_chunk_size]
+        if chunk.shape[1] < audio_chunk_size:
+            chunk = torch.nn.functional.pad(chunk, (0, audio_chunk_size - chunk.shape[1]))
+        lat.append(ae_encode(sd, cfg, pca[0], pca[1], pca[2], chunk.unsqueeze(0)))
+    lat = torch.cat(lat, dim=1)
+    n = audio.shape[1] // hop
+    mask = (torch.arange(lat.shape[1]) < n).unsqueeze(0)
+    lat, mask = lat[:, :n], mask[:, :n]
+    n4 = lat.shape[1] // divis_by_patch_size * divis_by_patch_size
+    return lat[:, :n4], mask[:, :n4]

@@ -86,6 +86,97 @@ def build_ref_dac(refae, cfg, sd):
     return ae.eval()
 
 
+def build_ref_dac_with_encoder(refae, cfg, sd):
+    """Reference DAC including the encode path (Encoder, downsample, pre_module, vector quantizers) for `cfg`."""
+    def tcfg(block_size, layers, heads, dim, inter):
+        return refae.ModelArgs(block_size=block_size, n_layer=layers, n_head=heads, dim=dim, intermediate_size=inter,
+                               head_dim=64, norm_eps=1e-5, dropout_rate=0.1, attn_dropout_rate=0.1, channels_first=True)
+
+    def general(**kw):  # build_ae's transformer_general_config (autoencoder.py:1169-1183)
+        return tcfg(kw.get("block_size", 16384), kw.get("n_layer", 8), kw.get("n_head", 8), kw.get("dim", 512),
+                    kw.get("intermediate_size", 1536))
+
+    C = cfg.latent_dim
+    nb = len(cfg.enc_rates)
+    with torch.device("meta"):
+        mk = lambda: refae.WindowLimitedTransformer(
+            causal=True, window_size=cfg.post_window, input_dim=C,
+            config=tcfg(cfg.post_block_size, cfg.post_layers, cfg.post_heads, C, cfg.post_intermediate))
+        quant = refae.DownsampleResidualVectorQuantize(
+            input_dim=C, n_codebooks=cfg.n_codebooks, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim,
+            downsample_factor=(2,) * cfg.num_upsample, semantic_codebook_size=cfg.semantic_codebook_size,
+            pre_module=mk(), post_module=mk())
+        ae = refae.DAC(encoder_dim=cfg.enc_dim, encoder_rates=list(cfg.enc_rates), latent_dim=C,
+                       decoder_dim=cfg.decoder_dim, decoder_rates=list(cfg.rates), quantizer=quant, causal=True,
+                       encoder_transformer_layers=[0] * (nb - 1) + [cfg.enc_t_layers],
+                       decoder_transformer_layers=[0] * len(cfg.rates), transformer_general_config=general)
+    missing, unexpected = ae.load_state_dict(sd, strict=False, assign=True)
+    assert not unexpected, unexpected
+    assert all(k.endswith(("freqs_cis", "causal_mask")) for k in missing), missing
+    mods = [ae.quantizer.post_module, ae.quantizer.pre_module]
+    if cfg.enc_t_layers > 0:
+        mods.append(ae.encoder.block[nb].block[5])
+    for pm in mods:  # non-persistent / derived buffers must be real tensors
+        pm.freqs_cis = refae.precompute_freqs_cis(pm.config.block_size, pm.config.head_dim, pm.config.rope_base)
+        pm.causal_mask = torch.tril(torch.ones(pm.config.block_size, pm.config.block_size, dtype=torch.bool))
+    return ae.eval()
+
+
+def run_encode(which: str):
+    """Pins the encode-path oracle (dac_encode_zq, ae_encode, get_speaker_latent_and_mask) against the reference's
+    DAC.encode_zq / inference.ae_encode / inference.get_speaker_latent_and_mask and stores goldens."""
+    from echo_tts_b200.config import DacConfig
+    from echo_tts_b200.weights import make_dac_weights, make_pca_state
+    from oracle import echo_oracle as O
+    _, refinf, _, refae = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    cfg = DacConfig.tiny() if which == "tiny" else DacConfig.base()
+    sd = make_dac_weights(cfg, seed=4321, include_encoder=True)
+    ae = build_ref_dac_with_encoder(refae, cfg, sd)
+    comps, mean, scale = make_pca_state(cfg)
+    pca = refinf.PCAState(pca_components=comps, pca_mean=mean, latent_scale=scale)
+    g = torch.Generator().manual_seed(17)
+    fl = cfg.frame_length
+    n_frames = 37 if which == "tiny" else 48
+    audio = 0.3 * torch.randn(2 if which == "tiny" else 1, 1, n_frames * fl - fl // 3, generator=g)  # ragged: not a frame multiple
+    t0 = time.time()
+    with torch.inference_mode():
+        zq_ref = ae.encode_zq(audio)
+        codes_ref, _ = ae.encode(audio)
+        lat_ref = refinf.ae_encode(ae, pca, audio)
+        z_enc_ref = ae.encoder(torch.nn.functional.pad(audio, (0, n_frames * fl - audio.shape[-1])))
+        zq_o, parts = O.dac_encode_zq(sd, cfg, audio, return_parts=True)
+        lat_o = O.ae_encode(sd, cfg, comps, mean, scale, audio)
+    print(f"{which}: reference encode {time.time() - t0:.1f} s; frames {zq_ref.shape[-1]}")
+    agree = (parts["codes"] == codes_ref).float().mean().item()
+    print("encoder out oracle vs reference", rel(parts["z_enc"], z_enc_ref), "| code agreement", agree,
+          "| z_q", rel(zq_o, zq_ref), "| latents", rel(lat_o, lat_ref))
+    assert rel(parts["z_enc"], z_enc_ref) < 2e-5 and agree == 1.0 and rel(zq_o, zq_ref) < 2e-5 and rel(lat_o, lat_ref) < 2e-5
+    out = dict(audio=audio, z_enc=z_enc_ref.clone(), z_pre=parts["z_pre"].clone(), codes=codes_ref.clone(),
+               zq=zq_ref.clone(), latent=lat_ref.clone())
+    if which == "tiny":
+        # get_speaker_latent_and_mask with a small chunk size (the chunking logic is size independent)
+        wav = 0.3 * torch.randn(1, 5 * 8 * fl + 3 * fl + 11, generator=g)
+        kw = dict(max_speaker_latent_length=48, audio_chunk_size=8 * fl)
+        orig = refinf.get_speaker_latent_and_mask.__wrapped__ if hasattr(refinf.get_speaker_latent_and_mask, "__wrapped__") else None
+        src = open(os.path.join(REF, "inference.py")).read()
+        assert "AE_DOWNSAMPLE_FACTOR = 2048" in src  # the reference hard-codes the base hop; tiny uses frame_length
+        ns = dict(vars(refinf))
+        import ast as _ast
+        node = [n for n in _ast.parse(src).body if isinstance(n, _ast.FunctionDef) and n.name == "get_speaker_latent_and_mask"][0]
+        node.decorator_list = []
+        code = _ast.unparse(node).replace("AE_DOWNSAMPLE_FACTOR = 2048", f"AE_DOWNSAMPLE_FACTOR = {fl}")
+        exec(code, ns)
+        with torch.inference_mode():
+            sl_ref, sm_ref = ns["get_speaker_latent_and_mask"](ae, pca, wav, **kw)
+            sl_o, sm_o = O.get_speaker_latent_and_mask(sd, cfg, (comps, mean, scale), wav, **kw)
+        assert sl_ref.shape == sl_o.shape and torch.equal(sm_ref, sm_o) and rel(sl_o, sl_ref) < 2e-5, (sl_ref.shape, sl_o.shape)
+        print("get_speaker_latent_and_mask: oracle == reference", tuple(sl_ref.shape), rel(sl_o, sl_ref))
+        out.update(spk_wav=wav, spk_latent=sl_ref.clone(), spk_mask=sm_ref.clone())
+    torch.save(out, os.path.join(GOLD, f"dac_encode_{which}.pt"))
+    print("wrote", os.path.join(GOLD, f"dac_encode_{which}.pt"))
+
+
 def text_ids_mask(refinf, prompts, max_length):
     return refinf.get_text_input_ids_and_mask(prompts, max_length=max_length, device=None)
 
@@ -293,9 +384,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--full", choices=["cfg1", "cfg2", "cfg5", "dac"])
+    ap.add_argument("--encode", choices=["tiny", "full"])
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     if a.tiny:
         run_tiny()
     if a.full:
         run_full(a.full)
+    if a.encode:
+        run_encode(a.encode)

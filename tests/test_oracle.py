@@ -105,3 +105,22 @@ def test_t_schedule_matches_torch():
             v = (torch.tensor(1.0) + step * i) if i < steps // 2 else (torch.tensor(0.0) - step * (steps - 1 - i))
             mine.append(v * torch.tensor(0.999))
         assert torch.allclose(torch.stack(mine).float(), ref, rtol=0, atol=1.2e-7), n
+
+
+@torch.inference_mode()
+def test_dac_encode_oracle_matches_reference_golden():
+    """Encode path: encoder, quantizer front, codes, z_q, PCA latents and get_speaker_latent_and_mask of
+    the oracle against outputs of the reference's DAC.encode_zq / ae_encode / get_speaker_latent_and_mask (tiny)."""
+    cfg = DacConfig.tiny()
+    sd = make_dac_weights(cfg, seed=4321, include_encoder=True)
+    comps, mean, scale = make_pca_state(cfg)
+    g = gold("dac_encode_tiny.pt")
+    zq, parts = O.dac_encode_zq(sd, cfg, g["audio"], return_parts=True)
+    assert rel_l2(parts["z_enc"], g["z_enc"]) < TOL
+    assert torch.equal(parts["codes"], g["codes"])
+    assert rel_l2(zq, g["zq"]) < TOL
+    assert rel_l2(O.ae_encode(sd, cfg, comps, mean, scale, g["audio"]), g["latent"]) < TOL
+    lat, mask = O.get_speaker_latent_and_mask(sd, cfg, (comps, mean, scale), g["spk_wav"], max_speaker_latent_length=48,
+                                              audio_chunk_size=8 * cfg.frame_length)
+    assert torch.equal(mask, g["spk_mask"]) and rel_l2(lat, g["spk_latent"]) < TOL
+    assert lat.shape[1] % 4 == 0 and lat.shape[1] == 40

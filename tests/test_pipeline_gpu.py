@@ -1,0 +1,76 @@
+"""GPU: the host pipeline (echo_tts_b200/pipeline.py) driving the CUDA sampler + DAC decoder end to end, tiny config.
+Mirrors what handler._synthesize does with the drop-in objects (reference handler.py:736-768, inference.py:309-347)."""
+import functools
+
+import pytest
+import torch
+
+import echo_tts_b200
+from echo_tts_b200 import pipeline as P
+from echo_tts_b200.config import DacConfig, DitConfig
+from echo_tts_b200.weights import make_dac_weights, make_dit_weights, make_pca_state
+from tests.util import PLAIN_KNOBS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def stack():
+    from echo_tts_b200.autoencoder import B200DAC, PCAState
+    from echo_tts_b200.model import B200EchoDiT
+    from echo_tts_b200.sampler import sample_euler_cfg_independent_guidances as sample
+    cfg, dcfg = DitConfig.tiny(), DacConfig.tiny()
+    model = B200EchoDiT.from_state_dict(make_dit_weights(cfg, 1234), cfg, "cuda:0")
+    dac = B200DAC.from_state_dict(make_dac_weights(dcfg, 4321), dcfg, "cuda:0")
+    comps, mean, scale = make_pca_state(dcfg)
+    pca = PCAState(comps.cuda(), mean.cuda(), scale)
+    # the sample_fn exactly as handler._build_sample_fn builds it: functools.partial over keyword knobs
+    sample_fn = functools.partial(sample, **dict(PLAIN_KNOBS, num_steps=4), sequence_length=24)
+    echo_tts_b200.set_deterministic(True)
+    yield model, dac, pca, sample_fn
+    echo_tts_b200.set_deterministic(False)
+
+
+def test_sample_pipeline_matches_manual_composition(stack):
+    from echo_tts_b200.autoencoder import ae_decode
+    model, dac, pca, sample_fn = stack
+    audio, norm = P.sample_pipeline(model, dac, pca, sample_fn, "Hello there: friend", rng_seed=7, pad_to_max_text_length=64)
+    assert norm == "[S1] Hello there, friend"
+    ids, mask = P.get_text_input_ids_and_mask(["Hello there: friend"], 64, device="cuda")
+    spk = torch.zeros(1, 4, 80, device="cuda", dtype=model.dtype)
+    smask = torch.zeros(1, 4, dtype=torch.bool, device="cuda")
+    lat = sample_fn(model, spk, smask, ids, mask, 7)
+    ref = P.crop_audio_to_flattening_point(ae_decode(dac, pca, lat), lat[0])
+    assert audio.dtype == torch.float32 and audio.dim() == 3 and audio.shape[:2] == (1, 1)
+    assert audio.shape[-1] % 2048 == 0 and audio.shape[-1] <= 24 * 2048
+    assert torch.equal(audio, ref)
+
+
+def test_sample_pipeline_with_speaker_latents(stack):
+    model, dac, pca, sample_fn = stack
+    spk = torch.randn(1, 16, 80, generator=torch.Generator().manual_seed(3)).cuda()
+    smask = torch.ones(1, 16, dtype=torch.bool, device="cuda")
+    a, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same text.", spk, smask, rng_seed=1, pad_to_max_text_length=64)
+    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same text.", None, None, rng_seed=1, pad_to_max_text_length=64)
+    assert torch.isfinite(a).all() and a.abs().max() <= 1.0
+    n = min(a.shape[-1], b.shape[-1])
+    assert n == 0 or not torch.equal(a[..., :n], b[..., :n])  # the speaker condition changes the result
+
+
+def test_synthesize_long_prompt_chunks_and_stitches(stack):
+    """Long prompt -> chunk_text_for_audio -> one sample_pipeline call per chunk with seed + 1000 * idx -> boundary
+    normalisation + crossfade on the host, as handler._synthesize (handler.py:736-768)."""
+    model, dac, pca, sample_fn = stack
+    text = ("This is the first sentence of a long prompt. " * 8).strip()
+
+    def synth_chunk(chunk, seed):
+        audio, _ = P.sample_pipeline(model, dac, pca, sample_fn, chunk, rng_seed=seed, pad_to_max_text_length=160)
+        return audio[0]  # (1, n) like handler's audio chunks
+
+    out = P.synthesize(text, synth_chunk, seed=11, max_chars_per_chunk=300, target_duration=10.0)
+    chunks = P.chunk_text_for_audio(text, 300, 10.0)
+    assert len(chunks) >= 3
+    manual = P.normalize_chunk_boundaries([synth_chunk(c, 11 + 1000 * i).cpu() for i, c in enumerate(chunks)])
+    assert out.dim() == 2 and torch.equal(out, manual)
+    plain = P.synthesize(text, synth_chunk, seed=11, normalize_boundaries=False, enable_crossfade=False)
+    assert plain.shape[-1] == sum(synth_chunk(c, 11 + 1000 * i).shape[-1] for i, c in enumerate(chunks))
