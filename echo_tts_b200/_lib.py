@@ -32,6 +32,9 @@ class DacConfig(C.Structure):
         ("latent_dim", C.c_int), ("pca_dim", C.c_int), ("post_layers", C.c_int), ("post_heads", C.c_int),
         ("post_intermediate", C.c_int), ("post_window", C.c_int), ("post_norm_eps", C.c_float),
         ("num_upsample", C.c_int), ("decoder_dim", C.c_int), ("num_rates", C.c_int), ("rates", C.c_int * 8),
+        ("enc_dim", C.c_int), ("num_enc_rates", C.c_int), ("enc_rates", C.c_int * 8), ("enc_t_layers", C.c_int),
+        ("enc_window", C.c_int), ("n_codebooks", C.c_int), ("codebook_size", C.c_int),
+        ("semantic_codebook_size", C.c_int), ("codebook_dim", C.c_int),
     ]
 
 
@@ -117,6 +120,8 @@ SYMBOLS = {
     "echo_sample_blockwise": (C.c_int, [_P, C.POINTER(SamplerArgs), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int, _P,
                                         _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
     "echo_dac_decode": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),
+    "echo_dac_encode_zq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "echo_dac_encode": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),
     "echo_dac_decode_zq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "echo_sample_euler_host": (C.c_int, [_P, C.POINTER(SamplerArgs), _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P]),
     "echo_profile_start": (C.c_int, [_P]),

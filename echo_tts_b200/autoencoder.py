@@ -1,8 +1,9 @@
-"""`B200DAC`: drop-in for the reference Fish S1-DAC object on the DECODE path, plus `PCAState` / `ae_decode`.
+"""`B200DAC`: drop-in for the reference Fish S1-DAC object, plus `PCAState` / `ae_decode` / `ae_encode`.
 
-Mirrors what the reference callers touch (reference inference.py:86-99, 226-229; autoencoder.py:1128-1138):
-`fish_ae.decode_zq(z (B, 1024, T)) -> (B, 1, 2048 T)`, `.dtype`, `.device`, and `ae_decode(fish_ae, pca_state, z_q)`.
-`encode_zq` (speaker-reference encoding) is out of scope for this round and raises.
+Mirrors what the reference callers touch (reference inference.py:86-99, 219-229; autoencoder.py:1080-1138):
+`fish_ae.decode_zq(z (B, 1024, T)) -> (B, 1, 2048 T)`, `fish_ae.encode_zq(audio (B, 1, L)) -> (B, 1024, ceil(L / 2048))`,
+`.dtype`, `.device`, `ae_decode(fish_ae, pca_state, z_q)` and `ae_encode(fish_ae, pca_state, audio)`.
+The encode path needs the encoder / quantizer tensors of the checkpoint; without them `encode_zq` raises.
 """
 from __future__ import annotations
 
@@ -35,15 +36,27 @@ class B200DAC:
         c.num_upsample, c.decoder_dim, c.num_rates = cfg.num_upsample, cfg.decoder_dim, len(cfg.rates)
         for i, r in enumerate(cfg.rates):
             c.rates[i] = r
+        c.enc_dim, c.num_enc_rates, c.enc_t_layers, c.enc_window = cfg.enc_dim, len(cfg.enc_rates), cfg.enc_t_layers, cfg.enc_window
+        for i, r in enumerate(cfg.enc_rates):
+            c.enc_rates[i] = r
+        c.n_codebooks, c.codebook_size = cfg.n_codebooks, cfg.codebook_size
+        c.semantic_codebook_size, c.codebook_dim = cfg.semantic_codebook_size, cfg.codebook_dim
+        self.has_encoder = False
         _lib.check(self.lib.echo_dac_configure(self.h.ptr, C.byref(c)), "echo_dac_configure")
 
     def load_state_dict(self, state: Iterable[Tuple[str, torch.Tensor]] | dict, strict: bool = False, assign: bool = False):
-        """Accepts a full reference DAC state dict; only decode-path tensors are consumed."""
+        """Accepts a full reference DAC state dict. The decode path is mandatory; the encode path (encoder.*,
+        quantizer.downsample / pre_module / *quantizer.quantizers) is used when present."""
         items = state.items() if isinstance(state, dict) else state
         for k, v in items:
-            if k.startswith("decoder.") or k.startswith("quantizer.upsample.") or (
-                    k.startswith("quantizer.post_module.") and not k.endswith(("freqs_cis", "causal_mask"))):
+            if k.endswith(("freqs_cis", "causal_mask")):
+                continue  # derived buffers
+            if k.startswith(("decoder.", "quantizer.upsample.", "quantizer.post_module.")):
                 self.h.set_weight("dac." + k, v)
+            elif k.startswith(("encoder.", "quantizer.downsample.", "quantizer.pre_module.",
+                               "quantizer.semantic_quantizer.", "quantizer.quantizer.")):
+                self.h.set_weight("dac." + k, v)
+                self.has_encoder = True
         with torch.cuda.device(self.device):
             _lib.check(self.lib.echo_dac_finalize(self.h.ptr, _stream(self.device)), "echo_dac_finalize")
         return self
@@ -76,9 +89,60 @@ class B200DAC:
                        "echo_dac_decode_zq")
         return audio
 
-    def encode_zq(self, audio_data: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("DAC encode / RVQ is outside this round's scope (SURVEY.md 8(f)); "
-                                  "run the reference encoder to obtain speaker latents")
+    def _padded_audio(self, audio_data: torch.Tensor) -> torch.Tensor:
+        """(B, L) or (B, 1, L) -> (B, 1, L') fp32 on the device, right-padded with zeros to a multiple of the frame
+        length exactly as DAC.encode does (autoencoder.py:1090-1095)."""
+        a = audio_data
+        if a.dim() == 2:
+            a = a.unsqueeze(1)
+        assert a.dim() == 3 and a.shape[1] == 1, "audio must be (B, 1, L)"
+        a = a.to(self.device, torch.float32)
+        fl = self.cfg.frame_length
+        pad = (-a.shape[-1]) % fl
+        if pad:
+            a = torch.nn.functional.pad(a, (0, pad))
+        return a.contiguous()
+
+    @torch.inference_mode()
+    def encode_zq(self, audio_data: torch.Tensor, return_codes: bool = False, return_z_pre: bool = False):
+        """reference DAC.encode_zq (autoencoder.py:1116-1126): (B, 1, L) -> z_q (B, latent_dim, ceil(L / 2048)) fp32.
+        With return_codes also the (B, 1 + n_codebooks, T) code indices of DAC.encode."""
+        if not self.has_encoder:
+            raise _lib.EchoError("B200DAC.encode_zq: the checkpoint had no encoder / quantizer tensors")
+        a = self._padded_audio(audio_data)
+        B, _, L = a.shape
+        T = L // self.cfg.frame_length
+        zq = torch.empty(B, self.cfg.latent_dim, T, device=self.device, dtype=torch.float32)
+        codes = torch.empty(B, 1 + self.cfg.n_codebooks, T, device=self.device, dtype=torch.int32) if return_codes else None
+        z_pre = torch.empty(B, T, self.cfg.latent_dim, device=self.device, dtype=torch.float32) if return_z_pre else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.echo_dac_encode_zq(self.h.ptr, a.data_ptr(), B, L, zq.data_ptr(),
+                                                   None if codes is None else codes.data_ptr(),
+                                                   None if z_pre is None else z_pre.data_ptr(), _stream(self.device)),
+                       "echo_dac_encode_zq")
+        if not (return_codes or return_z_pre):
+            return zq
+        return (zq,) + ((codes.long(),) if return_codes else ()) + ((z_pre,) if return_z_pre else ())
+
+    @torch.inference_mode()
+    def encode_latent(self, pca_state: PCAState, audio: torch.Tensor) -> torch.Tensor:
+        """Fused encode + PCA projection: audio (B, 1, L) -> (B, ceil(L / 2048), 80) fp32 (reference ae_encode)."""
+        if not self.has_encoder:
+            raise _lib.EchoError("B200DAC.encode_latent: the checkpoint had no encoder / quantizer tensors")
+        dev = self.device
+        a = self._padded_audio(audio)
+        B, _, L = a.shape
+        T = L // self.cfg.frame_length
+        comps = pca_state.pca_components.to(dev, torch.float32).contiguous()
+        mean = pca_state.pca_mean.to(dev, torch.float32).contiguous()
+        K = comps.shape[0]
+        assert comps.shape == (K, self.cfg.latent_dim) and K == self.cfg.pca_dim
+        out = torch.empty(B, T, K, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.echo_dac_encode(self.h.ptr, a.data_ptr(), comps.data_ptr(), mean.data_ptr(),
+                                                float(pca_state.latent_scale), B, L, out.data_ptr(), _stream(dev)),
+                       "echo_dac_encode")
+        return out
 
     @torch.inference_mode()
     def decode_latent(self, pca_state: PCAState, z: torch.Tensor) -> torch.Tensor:
@@ -104,3 +168,14 @@ def ae_decode(fish_ae, pca_state: PCAState, z_q: torch.Tensor) -> torch.Tensor:
         return fish_ae.decode_latent(pca_state, z_q)
     z = (z_q / pca_state.latent_scale) @ pca_state.pca_components + pca_state.pca_mean
     return fish_ae.decode_zq(z.transpose(1, 2).to(fish_ae.dtype)).float()
+
+
+@torch.inference_mode()
+def ae_encode(fish_ae, pca_state: PCAState, audio: torch.Tensor) -> torch.Tensor:
+    """reference inference.ae_encode (inference.py:219-224): (B, 1, L) -> (B, T, 80). Fused with a B200DAC."""
+    assert audio.ndim == 3 and audio.shape[1] == 1  # (b, 1, length)
+    if isinstance(fish_ae, B200DAC):
+        return fish_ae.encode_latent(pca_state, audio)
+    z_q = fish_ae.encode_zq(audio).float()
+    z_q = (z_q.transpose(1, 2) - pca_state.pca_mean) @ pca_state.pca_components.T
+    return z_q * pca_state.latent_scale

@@ -210,6 +210,228 @@ __global__ void __launch_bounds__(256) final_conv_tanh_kernel(const bf16* __rest
   audio[(size_t)b * T + t] = tanhf(acc);
 }
 
+// ---- encode path kernels -------------------------------------------------------------------------------------
+// First encoder conv (Cin = 1, k = 7, causal; autoencoder.py:915): x[b, t, c] = b[c] + sum_j w[j][c] a[b, t-6+j];
+// writes the fp32 residual stream and snake(x, alpha) in bf16 (the A operand of the first ResidualUnit's conv7).
+__global__ void __launch_bounds__(256) enc_conv0_kernel(const float* __restrict__ audio, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ alpha,
+                                                        float* __restrict__ xa, bf16* __restrict__ sx, int T, int C) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sw[];  // [7][C] weights, [C] bias, [C] alpha
+  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sw[7 * C + i] = bias[i]; sw[8 * C + i] = alpha[i]; }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float a[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) a[j] = (t - 6 + j >= 0) ? audio[(size_t)b * T + t - 6 + j] : 0.f;
+  float* xo = xa + ((size_t)b * T + t) * C;
+  bf16* so = sx + ((size_t)b * T + t) * C;
+  for (int c = 0; c < C; c += 2) {
+    float v0 = sw[7 * C + c], v1 = sw[7 * C + c + 1];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { v0 = fmaf(sw[j * C + c], a[j], v0); v1 = fmaf(sw[j * C + c + 1], a[j], v1); }
+    *reinterpret_cast<float2*>(xo + c) = make_float2(v0, v1);
+    const float al0 = sw[8 * C + c], al1 = sw[8 * C + c + 1];
+    const float s0 = sinf(al0 * v0), s1 = sinf(al1 * v1);
+    *reinterpret_cast<__nv_bfloat162*>(so + c) = __floats2bfloat162_rn(v0 + s0 * s0 / (al0 + 1e-9f), v1 + s1 * s1 / (al1 + 1e-9f));
+  }
+}
+
+// first conv weight (C, 1, 7) weight-normed -> [7][C] fp32
+__global__ void pack_enc_conv0_kernel(const float* __restrict__ v, const float* __restrict__ scale, float* __restrict__ out,
+                                      int C) {
+  for (int i = threadIdx.x; i < C * 7; i += blockDim.x) {
+    const int c = i % C, j = i / C;
+    out[i] = v[(size_t)c * 7 + j] * scale[c];
+  }
+}
+
+// RMSNorm with weight over fp32 rows (Transformer.norm, autoencoder.py:607), one warp per row, C = 128 * NV:
+//   out_f32 = x_hat * w (optional);  out_bf16 = bf16(alpha ? snake(x_hat * w, alpha) : x_hat * w) (optional)
+template <int NV>
+__global__ void __launch_bounds__(256) rmsnorm_out_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                          const float* __restrict__ alpha, float* __restrict__ out_f32,
+                                                          bf16* __restrict__ out_bf16, int rows, float eps) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int W = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(X + (size_t)r * W);
+  float4 v[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)W + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + c);
+    float4 o = make_float4(v[i].x * rstd * wv.x, v[i].y * rstd * wv.y, v[i].z * rstd * wv.z, v[i].w * rstd * wv.w);
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)r * W)[c] = o;
+    if (out_bf16) {
+      if (alpha) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(alpha) + c);
+        const float s0 = sinf(a.x * o.x), s1 = sinf(a.y * o.y), s2 = sinf(a.z * o.z), s3 = sinf(a.w * o.w);
+        o.x += s0 * s0 / (a.x + 1e-9f); o.y += s1 * s1 / (a.y + 1e-9f);
+        o.z += s2 * s2 / (a.z + 1e-9f); o.w += s3 * s3 / (a.w + 1e-9f);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+      reinterpret_cast<uint2*>(out_bf16 + (size_t)r * W)[c] =
+          make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+    }
+  }
+}
+
+// in_proj (C -> D, weight-normed 1x1 conv) as fp32 [D][C]; D <= 16
+__global__ void pack_vq_in_kernel(const float* __restrict__ v, const float* __restrict__ scale, float* __restrict__ out,
+                                  int D, int C) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * C; i += gridDim.x * blockDim.x) out[i] = v[i] * scale[i / C];
+}
+// normalised codebook + squared norms (F.normalize: x / max(||x||, 1e-12); autoencoder.py:149)
+__global__ void pack_vq_codebook_kernel(const float* __restrict__ cb, float* __restrict__ cbn, float* __restrict__ sq,
+                                        int size, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= size) return;
+  float ss = 0.f;
+  for (int d = 0; d < D; ++d) ss += cb[i * D + d] * cb[i * D + d];
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  float s2 = 0.f;
+  for (int d = 0; d < D; ++d) { const float t = cb[i * D + d] * inv; cbn[i * D + d] = t; s2 += t * t; }
+  sq[i] = s2;
+}
+// out_table[i][c] = bias[c] + sum_d (v[c][d] * scale[c]) * codebook[i][d]     (out_proj of every code, fp32)
+__global__ void pack_vq_out_kernel(const float* __restrict__ v, const float* __restrict__ scale, const float* __restrict__ bias,
+                                   const float* __restrict__ cb, float* __restrict__ table, int size, int D, int C) {
+  const int64_t total = (int64_t)size * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int code = (int)(i / C);
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) acc = fmaf(v[(size_t)c * D + d] * scale[c], cb[code * D + d], acc);
+    table[i] = acc + bias[c];
+  }
+}
+
+struct VqDev {  // device-side view of one DacVqW
+  const float *in_w, *in_b, *cb_norm, *cb_sq, *out_table;
+  int size;
+};
+struct VqAll { VqDev q[16]; int n; };
+
+// Semantic + residual vector quantisation of one row (autoencoder.py:132-157, 455-463, 1116-1126), all fp32:
+// per codebook z_e = in_proj(residual); nearest code between the L2-normalised z_e and codebook (first index on
+// ties, like torch.max); residual -= out_proj(code). One block per row keeps the row in registers across all
+// codebooks. z_q = semantic + (sum of the residual codebooks), summed in the reference's order.
+template <int NPT>  // C = 256 * NPT
+__global__ void __launch_bounds__(256) vq_encode_kernel(const float* __restrict__ Z, const __grid_constant__ VqAll vq,
+                                                        float* __restrict__ zq, int32_t* __restrict__ codes, int T,
+                                                        int D) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int C = 256 * NPT;
+  __shared__ float s_red[8][16];
+  __shared__ float s_e[16];
+  __shared__ float s_best[8];
+  __shared__ int s_idx[8];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float res[NPT], acc_sem[NPT], acc_res[NPT];
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) { res[i] = Z[(size_t)r * C + tid + 256 * i]; acc_sem[i] = 0.f; acc_res[i] = 0.f; }
+  for (int qi = 0; qi < vq.n; ++qi) {
+    const VqDev& q = vq.q[qi];
+    // ---- z_e = in_proj(residual): D dot products over C
+    for (int d = 0; d < D; ++d) {
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < NPT; ++i) p = fmaf(res[i], q.in_w[(size_t)d * C + tid + 256 * i], p);
+      for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (lane == 0) s_red[wid][d] = p;
+    }
+    __syncthreads();
+    if (tid < D) {
+      float t = q.in_b[tid];
+      for (int w = 0; w < 8; ++w) t += s_red[w][tid];
+      s_e[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {  // F.normalize(z_e)
+      float ss = 0.f;
+      for (int d = 0; d < D; ++d) ss += s_e[d] * s_e[d];
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      float s2 = 0.f;
+      for (int d = 0; d < D; ++d) { s_e[d] *= inv; s2 += s_e[d] * s_e[d]; }
+      s_e[15] = s2;  // |e_n|^2 (D <= 15)
+    }
+    __syncthreads();
+    // ---- nearest code: maximise -(|e|^2 - 2 e.c + |c|^2)
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int code = tid; code < q.size; code += 256) {
+      float dot = 0.f;
+      for (int d = 0; d < D; ++d) dot = fmaf(s_e[d], q.cb_norm[(size_t)code * D + d], dot);
+      const float score = -(s_e[15] - 2.f * dot + q.cb_sq[code]);
+      if (score > best) { best = score; bidx = code; }  // ascending codes per thread: first maximum is kept
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { s_best[wid] = best; s_idx[wid] = bidx; }
+    __syncthreads();
+    if (tid == 0) {
+      float bb = s_best[0];
+      int bi = s_idx[0];
+      for (int w = 1; w < 8; ++w)
+        if (s_best[w] > bb || (s_best[w] == bb && s_idx[w] < bi)) { bb = s_best[w]; bi = s_idx[w]; }
+      s_idx[0] = bi;
+      if (codes) codes[((size_t)(r / T) * vq.n + qi) * T + (r % T)] = bi;
+    }
+    __syncthreads();
+    const int idx = s_idx[0];
+    const float* row = q.out_table + (size_t)idx * C;
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const float t = row[tid + 256 * i];
+      res[i] -= t;
+      if (qi == 0) acc_sem[i] = t;
+      else acc_res[i] += t;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) zq[(size_t)r * C + tid + 256 * i] = acc_sem[i] + acc_res[i];
+}
+
+// latent[r, k] = scale * sum_c (zq[r, c] - mean[c]) * comps[k, c]        (inference.py:222-223), fp32; one block per row
+__global__ void __launch_bounds__(256) pca_project_kernel(const float* __restrict__ zq, const float* __restrict__ comps,
+                                                          const float* __restrict__ mean, float scale,
+                                                          float* __restrict__ out, int C, int K) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sz[];
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sz[c] = zq[(size_t)r * C + c] - mean[c];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = wid; k < K; k += 8) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(sz[c], comps[(size_t)k * C + c], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(size_t)r * K + k] = acc * scale;
+  }
+}
+
 inline int grid_for(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
@@ -252,6 +474,15 @@ extern "C" int echo_dac_configure(echo_handle* h, const echo_dac_config* c) {
   for (int i = 0; i < c->num_rates; ++i) {
     if (ch % 2 || (ch / 2) % 32) { set_error("decoder channels must stay multiples of 32"); return ECHO_ERR_ARG; }
     ch /= 2;
+  }
+  if (c->num_enc_rates > 0) {  // encode path described
+    int d = c->enc_dim;
+    if (d % 64 || c->num_enc_rates > 8 || c->codebook_dim < 1 || c->codebook_dim > 15 || c->n_codebooks < 0 || c->n_codebooks > 15) {
+      set_error("echo_dac_configure: unsupported encoder dims (enc_dim %% 64, codebook_dim <= 15, n_codebooks <= 15)");
+      return ECHO_ERR_ARG;
+    }
+    for (int i = 0; i < c->num_enc_rates; ++i) d *= 2;
+    if (d != C) { set_error("echo_dac_configure: enc_dim * 2^num_enc_rates must equal latent_dim"); return ECHO_ERR_ARG; }
   }
   h->dcfg = *c;
   h->dac_configured = true;
@@ -411,6 +642,124 @@ extern "C" int echo_dac_finalize(echo_handle* h, void* stream) {
       ECHO_CUDA(cudaMemcpyAsync(&h->final_b, b->p, 4, cudaMemcpyDeviceToHost, s));
     }
   }
+  // ---- encode path (optional: present iff the encoder weights were loaded)
+  h->dac_enc_ready = false;
+  const bool has_enc = h->dac_raw.count("encoder.block.0.conv.bias") > 0;
+  if (has_enc && pk.rc == ECHO_OK) {
+    const int D0 = c.enc_dim, nb = c.num_enc_rates, cd = c.codebook_dim;
+    {  // first conv, Cin = 1
+      const RawTensor* v = pk.get("encoder.block.0.conv.parametrizations.weight.original1");
+      const RawTensor* g = pk.get("encoder.block.0.conv.parametrizations.weight.original0");
+      if (v && g && v->numel == (int64_t)D0 * 7) {
+        float* scale = (float*)h->dalloc((size_t)D0 * 4);
+        slice_norm_kernel<<<D0, 256, 0, s>>>(v->p, scale, g->p, 7);
+        h->enc_conv0_w = (float*)h->dalloc((size_t)7 * D0 * 4);
+        pack_enc_conv0_kernel<<<1, 256, 0, s>>>(v->p, scale, h->enc_conv0_w, D0);
+      } else if (pk.rc == ECHO_OK) { set_error("dac.encoder.block.0: bad first conv"); pk.rc = ECHO_ERR_ARG; }
+      h->enc_conv0_b = pk.vecf("encoder.block.0.conv.bias", D0);
+    }
+    h->enc_blk.resize(nb);
+    int d = D0;
+    for (int b = 0; b < nb; ++b) {
+      const std::string p = "encoder.block." + std::to_string(b + 1) + ".block";
+      DacEncBlockW& eb = h->enc_blk[b];
+      eb.stride = c.enc_rates[b]; eb.cin = d; eb.cout = 2 * d;
+      for (int u = 0; u < 3; ++u) {
+        const std::string q = p + "." + std::to_string(u) + ".block";
+        eb.ru[u].alpha1 = pk.alpha(q + ".0.alpha", d);
+        eb.ru[u].conv7 = pk.conv(q + ".1", d, d, 7, true);
+        eb.ru[u].alpha2 = pk.alpha(q + ".2.alpha", d);
+        eb.ru[u].conv1 = pk.conv(q + ".3", d, d, 1, true);
+      }
+      eb.alpha_out = pk.alpha(p + ".3.alpha", d);
+      eb.down = pk.conv(p + ".4", 2 * d, d, 2 * eb.stride, true);  // [Cout][k][Cin] == 2 taps of (stride * Cin)
+      d *= 2;
+      if (b == nb - 1 && c.enc_t_layers > 0) {
+        const int It = 3 * d;
+        h->enc_tf.resize(c.enc_t_layers);
+        for (int i = 0; i < c.enc_t_layers; ++i) {
+          const std::string q = p + ".5.layers." + std::to_string(i);
+          DacPostLayerW& l = h->enc_tf[i];
+          l.wqkv = pk.matb(q + ".attention.wqkv.weight", 3 * d, d);
+          l.wo = pk.matb(q + ".attention.wo.weight", d, d);
+          l.w13 = (bf16*)h->dalloc((size_t)2 * It * d * 2);
+          pk.matb(q + ".feed_forward.w1.weight", It, d, l.w13, 128, 256, 0);
+          pk.matb(q + ".feed_forward.w3.weight", It, d, l.w13, 128, 256, 128);
+          l.w2 = pk.matb(q + ".feed_forward.w2.weight", d, It);
+          l.attn_norm = pk.vecf(q + ".attention_norm.weight", d);
+          l.ffn_norm = pk.vecf(q + ".ffn_norm.weight", d);
+          l.attn_gamma = pk.vecf(q + ".attention_layer_scale.gamma", d);
+          l.ffn_gamma = pk.vecf(q + ".ffn_layer_scale.gamma", d);
+        }
+        h->enc_tf_norm = pk.vecf(p + ".5.norm.weight", d);
+      }
+    }
+    if (d != C && pk.rc == ECHO_OK) { set_error("encoder width %d != latent_dim %d", d, C); pk.rc = ECHO_ERR_ARG; }
+    h->enc_alpha_out = pk.alpha("encoder.block." + std::to_string(nb + 1) + ".alpha", C);
+    h->enc_conv_out = pk.conv("encoder.block." + std::to_string(nb + 2), C, C, 3, true);
+    h->down.resize(c.num_upsample);
+    for (int i = 0; i < c.num_upsample; ++i) {
+      const std::string p = "quantizer.downsample." + std::to_string(i);
+      DacUpW& u = h->down[i];
+      u.convt = pk.conv(p + ".0", C, C, 2, false);  // k = s = 2: one tap over the (T / 2, 2 C) view
+      u.dw_w = pk.vecf(p + ".1.dwconv.conv.weight", (int64_t)C * 7);
+      u.dw_b = pk.vecf(p + ".1.dwconv.conv.bias", C);
+      u.ln_w = pk.vecf(p + ".1.norm.weight", C);
+      u.ln_b = pk.vecf(p + ".1.norm.bias", C);
+      u.w1 = pk.matb(p + ".1.pwconv1.weight", 4 * C, C);
+      u.b1 = pk.vecf(p + ".1.pwconv1.bias", 4 * C);
+      u.w2 = pk.matb(p + ".1.pwconv2.weight", C, 4 * C);
+      u.b2 = pk.vecf(p + ".1.pwconv2.bias", C);
+      u.gamma = pk.vecf(p + ".1.gamma", C);
+    }
+    h->pre.resize(c.post_layers);
+    for (int i = 0; i < c.post_layers; ++i) {
+      const std::string p = "quantizer.pre_module.layers." + std::to_string(i);
+      DacPostLayerW& l = h->pre[i];
+      l.wqkv = pk.matb(p + ".attention.wqkv.weight", 3 * C, C);
+      l.wo = pk.matb(p + ".attention.wo.weight", C, C);
+      l.w13 = (bf16*)h->dalloc((size_t)2 * I * C * 2);
+      pk.matb(p + ".feed_forward.w1.weight", I, C, l.w13, 128, 256, 0);
+      pk.matb(p + ".feed_forward.w3.weight", I, C, l.w13, 128, 256, 128);
+      l.w2 = pk.matb(p + ".feed_forward.w2.weight", C, I);
+      l.attn_norm = pk.vecf(p + ".attention_norm.weight", C);
+      l.ffn_norm = pk.vecf(p + ".ffn_norm.weight", C);
+      l.attn_gamma = pk.vecf(p + ".attention_layer_scale.gamma", C);
+      l.ffn_gamma = pk.vecf(p + ".ffn_layer_scale.gamma", C);
+    }
+    h->pre_final_norm = pk.vecf("quantizer.pre_module.norm.weight", C);
+    h->vq.resize(1 + c.n_codebooks);
+    for (int qi = 0; qi <= c.n_codebooks; ++qi) {
+      const std::string p = qi == 0 ? std::string("quantizer.semantic_quantizer.quantizers.0")
+                                    : "quantizer.quantizer.quantizers." + std::to_string(qi - 1);
+      DacVqW& q = h->vq[qi];
+      q.size = qi == 0 ? c.semantic_codebook_size : c.codebook_size;
+      const RawTensor* iv = pk.get(p + ".in_proj.parametrizations.weight.original1");
+      const RawTensor* ig = pk.get(p + ".in_proj.parametrizations.weight.original0");
+      const RawTensor* ov = pk.get(p + ".out_proj.parametrizations.weight.original1");
+      const RawTensor* og = pk.get(p + ".out_proj.parametrizations.weight.original0");
+      const RawTensor* ob = pk.get(p + ".out_proj.bias");
+      const RawTensor* cb = pk.get(p + ".codebook.weight");
+      q.in_b = pk.vecf(p + ".in_proj.bias", cd);
+      if (!iv || !ig || !ov || !og || !ob || !cb) break;
+      if (iv->numel != (int64_t)cd * C || ov->numel != (int64_t)C * cd || cb->numel != (int64_t)q.size * cd) {
+        if (pk.rc == ECHO_OK) { set_error("dac.%s: bad quantizer tensor sizes", p.c_str()); pk.rc = ECHO_ERR_ARG; }
+        break;
+      }
+      float* si = (float*)h->dalloc((size_t)cd * 4);
+      slice_norm_kernel<<<cd, 256, 0, s>>>(iv->p, si, ig->p, C);
+      q.in_w = (float*)h->dalloc((size_t)cd * C * 4);
+      pack_vq_in_kernel<<<grid_for((int64_t)cd * C), 256, 0, s>>>(iv->p, si, q.in_w, cd, C);
+      float* so = (float*)h->dalloc((size_t)C * 4);
+      slice_norm_kernel<<<C, 256, 0, s>>>(ov->p, so, og->p, cd);
+      q.cb_norm = (float*)h->dalloc((size_t)q.size * cd * 4);
+      q.cb_sq = (float*)h->dalloc((size_t)q.size * 4);
+      pack_vq_codebook_kernel<<<(q.size + 255) / 256, 256, 0, s>>>(cb->p, q.cb_norm, q.cb_sq, q.size, cd);
+      q.out_table = (float*)h->dalloc((size_t)q.size * C * 4);
+      pack_vq_out_kernel<<<grid_for((int64_t)q.size * C), 256, 0, s>>>(ov->p, so, ob->p, cb->p, q.out_table, q.size, cd, C);
+    }
+    h->dac_enc_ready = (pk.rc == ECHO_OK);
+  }
   if (pk.rc != ECHO_OK) return pk.rc;
   // RoPE cache of the post_module: stored in bfloat16 by the reference (autoencoder.py:805-813), used in fp32 math
   const int P = 4096, half = 32;
@@ -473,6 +822,61 @@ GemmCall convt_gemm(const DacConvW& w, const bf16* A, int B, int Tin, int cout) 
   return c;
 }
 
+struct TfBuffers { bf16 *XN, *Q, *K, *V, *AO, *Hh; };
+
+// The layers of a WindowLimitedTransformer (autoencoder.py:786-802, 621-626) over the fp32 stream X (B*T rows, in
+// place): pre-RMSNorm, fused QKV with RoPE on all heads, causal window attention, LayerScale residuals, SwiGLU.
+// Shared by quantizer.post_module / pre_module (window 128) and the last EncoderBlock (window 512). The final
+// RMSNorm (:607) is left to the caller (its output format differs per use).
+int run_window_transformer(echo_handle* h, const std::vector<DacPostLayerW>& layers, float* X, int B, int T, int C, int I,
+                           int H, int window, float eps, const TfBuffers& tb, cudaStream_t s) {
+  const int rows = B * T;
+  bf16 *XN = tb.XN, *Q = tb.Q, *K = tb.K, *V = tb.V, *AO = tb.AO, *Hh = tb.Hh;
+  for (size_t i = 0; i < layers.size(); ++i) {
+    const DacPostLayerW& w = layers[i];
+    rmsnorm_affine(X, XN, w.attn_norm, nullptr, rows, C, 0, 0, eps, s);
+    {
+      GemmCall g = base_gemm(XN, C, w.wqkv, C, 1, rows, 3 * C, C, 1);
+      g.p.epi = EPI_QKV;
+      g.p.sec[0] = {Q, nullptr, 1 << 20, 0};
+      g.p.sec[1] = {K, nullptr, 1 << 20, 0};
+      g.p.sec[2] = {V, nullptr, 0, 0};
+      g.p.sec_width = C; g.p.rope_cos = h->dac_rope_cos; g.p.rope_sin = h->dac_rope_sin; g.p.head_dim = 64;
+      g.p.pos_period = T; g.p.eps = eps;
+      DAC_GEMM(g);
+    }
+    {
+      echo_attn_desc a;
+      std::memset(&a, 0, sizeof(a));
+      a.Q = Q; a.q_batch_stride = (int64_t)T * C; a.q_row_stride = C; a.out = AO;
+      a.b = B; a.S = T; a.H = H; a.D = 64; a.scale = 0.125f; a.nseg = 1;
+      a.seg[0].K = K; a.seg[0].V = V; a.seg[0].batch_stride = (int64_t)T * C; a.seg[0].row_stride = C;
+      a.seg[0].len = T; a.seg[0].causal = 1; a.seg[0].window = window; a.seg[0].mask_stride = 1;
+      cudaError_t er = attention_launch(a, s);
+      if (er != cudaSuccess) { set_error("dac attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
+    }
+    {
+      GemmCall g = base_gemm(AO, C, w.wo, C, 1, rows, C, C, 1);
+      g.p.gate = w.attn_gamma; g.p.resid = X; g.p.out_f32 = X; g.p.ld_f32 = C;
+      g.split_k = 1;  // no atomic split-K here: < 0.1 ms to gain, and the decode stays bit-reproducible
+      DAC_GEMM(g);
+    }
+    rmsnorm_affine(X, XN, w.ffn_norm, nullptr, rows, C, 0, 0, eps, s);
+    {
+      GemmCall g = base_gemm(XN, C, w.w13, C, 1, rows, 2 * I, C, 1);
+      g.p.epi = EPI_SWIGLU; g.p.out_bf16 = Hh; g.p.ld_bf16 = I;
+      DAC_GEMM(g);
+    }
+    {
+      GemmCall g = base_gemm(Hh, I, w.w2, I, 1, rows, C, I, 1);
+      g.p.gate = w.ffn_gamma; g.p.resid = X; g.p.out_f32 = X; g.p.ld_f32 = C;
+      g.split_k = 1;
+      DAC_GEMM(g);
+    }
+  }
+  return ECHO_OK;
+}
+
 int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int B, int T, float* audio, cudaStream_t s) {
   const echo_dac_config& c = h->dcfg;
   const int C = c.latent_dim, I = c.post_intermediate, H = c.post_heads, rows = B * T;
@@ -500,48 +904,8 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
   const float eps = c.post_norm_eps;
 
   // ---- quantizer.post_module (autoencoder.py:786-802, 621-626)
-  for (int i = 0; i < c.post_layers; ++i) {
-    const DacPostLayerW& w = h->post[i];
-    rmsnorm_affine(X, XN, w.attn_norm, nullptr, rows, C, 0, 0, eps, s);
-    {
-      GemmCall g = base_gemm(XN, C, w.wqkv, C, 1, rows, 3 * C, C, 1);
-      g.p.epi = EPI_QKV;
-      g.p.sec[0] = {Q, nullptr, 1 << 20, 0};
-      g.p.sec[1] = {K, nullptr, 1 << 20, 0};
-      g.p.sec[2] = {V, nullptr, 0, 0};
-      g.p.sec_width = C; g.p.rope_cos = h->dac_rope_cos; g.p.rope_sin = h->dac_rope_sin; g.p.head_dim = 64;
-      g.p.pos_period = T; g.p.eps = eps;
-      DAC_GEMM(g);
-    }
-    {
-      echo_attn_desc a;
-      std::memset(&a, 0, sizeof(a));
-      a.Q = Q; a.q_batch_stride = (int64_t)T * C; a.q_row_stride = C; a.out = AO;
-      a.b = B; a.S = T; a.H = H; a.D = 64; a.scale = 0.125f; a.nseg = 1;
-      a.seg[0].K = K; a.seg[0].V = V; a.seg[0].batch_stride = (int64_t)T * C; a.seg[0].row_stride = C;
-      a.seg[0].len = T; a.seg[0].causal = 1; a.seg[0].window = c.post_window; a.seg[0].mask_stride = 1;
-      cudaError_t er = attention_launch(a, s);
-      if (er != cudaSuccess) { set_error("dac attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
-    }
-    {
-      GemmCall g = base_gemm(AO, C, w.wo, C, 1, rows, C, C, 1);
-      g.p.gate = w.attn_gamma; g.p.resid = X; g.p.out_f32 = X; g.p.ld_f32 = C;
-      g.split_k = 1;  // no atomic split-K here: < 0.1 ms to gain, and the decode stays bit-reproducible
-      DAC_GEMM(g);
-    }
-    rmsnorm_affine(X, XN, w.ffn_norm, nullptr, rows, C, 0, 0, eps, s);
-    {
-      GemmCall g = base_gemm(XN, C, w.w13, C, 1, rows, 2 * I, C, 1);
-      g.p.epi = EPI_SWIGLU; g.p.out_bf16 = Hh; g.p.ld_bf16 = I;
-      DAC_GEMM(g);
-    }
-    {
-      GemmCall g = base_gemm(Hh, I, w.w2, I, 1, rows, C, I, 1);
-      g.p.gate = w.ffn_gamma; g.p.resid = X; g.p.out_f32 = X; g.p.ld_f32 = C;
-      g.split_k = 1;
-      DAC_GEMM(g);
-    }
-  }
+  TfBuffers tb{XN, Q, K, V, AO, Hh};
+  ECHO_TRY(run_window_transformer(h, h->post, X, B, T, C, I, H, c.post_window, eps, tb, s));
   rmsnorm_affine(X, sa, h->post_final_norm, nullptr, rows, C, 0, 0, eps, s);  // sa = post_module output, bf16
 
   // ---- quantizer.upsample (autoencoder.py:427-435): [ConvTranspose k2 s2 ; ConvNeXt] per stage
@@ -649,4 +1013,217 @@ extern "C" int echo_dac_decode_zq(echo_handle* h, const float* zq, int B, int T,
   launch_k(transpose_ct_kernel, dim3(grid), dim3(block), 0, s, 1, zq, X, C, T);
   count_launch();
   return dac_run(h, X, B, T, audio, s);
+}
+
+// ------------------------------------------------------------------------------------------------ encode
+namespace {
+
+template <int NV>
+void launch_rmsnorm_out(const float* X, const float* w, const float* alpha, float* of, bf16* ob, int rows, float eps,
+                        cudaStream_t s) {
+  launch_k(rmsnorm_out_kernel<NV>, dim3((rows + 7) / 8), dim3(256), 0, s, 1, X, w, alpha, of, ob, rows, eps);
+  count_launch();
+}
+int rmsnorm_out(const float* X, const float* w, const float* alpha, float* of, bf16* ob, int rows, int C, float eps,
+                cudaStream_t s) {
+  switch (C) {
+    case 256: launch_rmsnorm_out<2>(X, w, alpha, of, ob, rows, eps, s); break;
+    case 512: launch_rmsnorm_out<4>(X, w, alpha, of, ob, rows, eps, s); break;
+    case 1024: launch_rmsnorm_out<8>(X, w, alpha, of, ob, rows, eps, s); break;
+    case 2048: launch_rmsnorm_out<16>(X, w, alpha, of, ob, rows, eps, s); break;
+    default: set_error("dac encode: unsupported transformer width %d", C); return ECHO_ERR_ARG;
+  }
+  return ECHO_OK;
+}
+
+// Encoder + quantizer front + RVQ (autoencoder.py:903-929, 452-463, 1116-1126). audio (B, 1, L) fp32; writes
+// zq_rows (B*T, C) fp32 time-major and optionally codes (B, 1 + n_codebooks, T).
+int dac_encode_run(echo_handle* h, const float* audio, int B, int L, float* zq_rows, int32_t* codes, float* z_pre_out,
+                   cudaStream_t s) {
+  const echo_dac_config& c = h->dcfg;
+  const int C = c.latent_dim, I = c.post_intermediate, H = c.post_heads, nb = c.num_enc_rates;
+  int hop = 1;
+  for (int i = 0; i < nb; ++i) hop *= c.enc_rates[i];
+  const int frame = hop << c.num_upsample;
+  if (L <= 0 || L % frame) { set_error("dac encode: L=%d must be a positive multiple of the frame length %d", L, frame); return ECHO_ERR_ARG; }
+  const int Tenc = L / hop, T = L / frame;
+  if (Tenc > 4096) { set_error("dac encode: %d encoder frames exceed the RoPE table (4096); encode in chunks", Tenc); return ECHO_ERR_ARG; }
+  // largest activation: stage 0 holds L x enc_dim, every later stage half of it or less; transformer buffers separately
+  int64_t max_elems = (int64_t)B * L * c.enc_dim;
+  max_elems = std::max<int64_t>(max_elems, (int64_t)B * Tenc * C * 4);  // ConvNeXt hidden / SwiGLU hidden
+  float* xa = (float*)h->wsget("dac.xa", (size_t)max_elems * 4, s);
+  bf16* sa = (bf16*)h->wsget("dac.sa", (size_t)max_elems * 2, s);
+  bf16* sb = (bf16*)h->wsget("dac.sb", (size_t)max_elems * 2, s);
+  bf16* hb = (bf16*)h->wsget("dac.hb", (size_t)max_elems * 2, s);
+  const int64_t trow = (int64_t)B * Tenc;
+  bf16* XN = (bf16*)h->wsget("dac.XN", (size_t)trow * C * 2, s);
+  bf16* Q = (bf16*)h->wsget("dac.Q", (size_t)trow * C * 2, s);
+  bf16* K = (bf16*)h->wsget("dac.K", (size_t)trow * C * 2, s);
+  bf16* V = (bf16*)h->wsget("dac.V", (size_t)trow * C * 2, s);
+  bf16* AO = (bf16*)h->wsget("dac.AO", (size_t)trow * C * 2, s);
+  bf16* Hh = (bf16*)h->wsget("dac.Hh", (size_t)trow * 3 * C * 2, s);
+  float* xq = (float*)h->wsget("dac.xq", (size_t)trow * C * 4, s);  // fp32 stream of the transformers / quantizer input
+  if (!xa || !sa || !sb || !hb || !XN || !Q || !K || !V || !AO || !Hh || !xq) { set_error("dac encode: workspace allocation failed"); return ECHO_ERR_CUDA; }
+  TfBuffers tb{XN, Q, K, V, AO, Hh};
+
+  // ---- Encoder: conv7 (Cin = 1) fused with the first Snake
+  int Tc = L, d = c.enc_dim;
+  bf16* cur = sa;
+  bf16* nxt = sb;
+  {
+    dim3 grid((Tc + 255) / 256, B);
+    launch_k(enc_conv0_kernel, grid, dim3(256), (size_t)9 * d * sizeof(float), s, 1, audio, h->enc_conv0_w, h->enc_conv0_b,
+             h->enc_blk[0].ru[0].alpha1, xa, cur, Tc, d);
+    count_launch();
+  }
+  static const int dil[3] = {1, 3, 9};
+  for (int b = 0; b < nb; ++b) {
+    const DacEncBlockW& eb = h->enc_blk[b];
+    for (int u = 0; u < 3; ++u) {  // ResidualUnit (autoencoder.py:879-900): cur = snake1(x) on entry
+      const DacResUnitW& ru = eb.ru[u];
+      {
+        GemmCall g = conv_gemm(ru.conv7, cur, B, Tc, dil[u]);
+        g.p.out_bf16 = hb; g.p.ld_bf16 = d; g.p.act = ACT_SNAKE; g.p.alpha = ru.alpha2; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
+        DAC_GEMM(g);
+      }
+      {
+        const float* next_alpha = (u < 2) ? eb.ru[u + 1].alpha1 : eb.alpha_out;
+        GemmCall g = conv_gemm(ru.conv1, hb, B, Tc, 1);
+        g.p.resid = xa; g.p.out_f32 = xa; g.p.ld_f32 = d;
+        g.p.out_bf16 = cur; g.p.ld_bf16 = d; g.p.act = ACT_SNAKE; g.p.alpha = next_alpha; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
+        DAC_GEMM(g);
+      }
+    }
+    // strided conv k = 2s (left pad s): out[t] = W[:, :, 0:s] x[s t - s ... s t - 1] + W[:, :, s:2s] x[s t ... s t + s - 1]
+    // == 2-tap GEMM over the (Tc / s, s * d) view of cur with row shifts {-1, 0}
+    const int st = eb.stride, To = Tc / st;
+    const bool last = (b == nb - 1);
+    {
+      DacConvW w2 = eb.down;
+      w2.cin = st * d; w2.taps = 2;
+      GemmCall g = base_gemm(cur, (int64_t)st * d, w2.w, (int64_t)2 * st * d, B, To, eb.cout, st * d, 2);
+      g.p.tap_shift[0] = -1; g.p.tap_shift[1] = 0;
+      g.p.bias = w2.bias; g.p.col_mod = eb.cout;
+      if (last && !h->enc_tf.empty()) {
+        g.p.out_f32 = xq; g.p.ld_f32 = eb.cout;  // fp32 stream of the block's transformer
+      } else {
+        const float* next_alpha = last ? h->enc_alpha_out : h->enc_blk[b + 1].ru[0].alpha1;
+        g.p.out_f32 = xa; g.p.ld_f32 = eb.cout;
+        g.p.out_bf16 = nxt; g.p.ld_bf16 = eb.cout; g.p.act = ACT_SNAKE; g.p.alpha = next_alpha; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
+      }
+      DAC_GEMM(g);
+    }
+    Tc = To; d = eb.cout;
+    std::swap(cur, nxt);
+  }
+  // ---- last block's window-512 transformer, final norm fused with the encoder's closing Snake
+  if (!h->enc_tf.empty()) {
+    ECHO_TRY(run_window_transformer(h, h->enc_tf, xq, B, Tc, C, 3 * C, C / 64, c.enc_window, 1e-5f, tb, s));
+    ECHO_TRY(rmsnorm_out(xq, h->enc_tf_norm, h->enc_alpha_out, nullptr, cur, B * Tc, C, 1e-5f, s));
+  }
+  {  // closing conv3 (causal) -> z_enc: bf16 for the downsample GEMM
+    GemmCall g = conv_gemm(h->enc_conv_out, cur, B, Tc, 1);
+    g.p.out_bf16 = nxt; g.p.ld_bf16 = C;
+    DAC_GEMM(g);
+  }
+  std::swap(cur, nxt);
+  // ---- quantizer.downsample: [conv k2 s2 ; ConvNeXt] per factor (autoencoder.py:418-424, 360-373)
+  for (int i = 0; i < c.num_upsample; ++i) {
+    const DacUpW& u = h->down[i];
+    const int To = Tc / 2, r2 = B * To;
+    {
+      GemmCall g = base_gemm(cur, (int64_t)2 * C, u.convt.w, (int64_t)2 * C, B, To, C, 2 * C, 1);
+      g.p.bias = u.convt.bias; g.p.col_mod = C;
+      g.p.out_f32 = xa; g.p.ld_f32 = C;
+      DAC_GEMM(g);
+    }
+    Tc = To;
+    launch_k(dwconv_ln_kernel, dim3(r2), dim3(256), 0, s, 1, xa, u.dw_w, u.dw_b, u.ln_w, u.ln_b, nxt, Tc, C);
+    count_launch();
+    {
+      GemmCall g = base_gemm(nxt, C, u.w1, C, 1, r2, 4 * C, C, 1);
+      g.p.bias = u.b1; g.p.out_bf16 = hb; g.p.ld_bf16 = 4 * C; g.p.act = ACT_GELU;
+      DAC_GEMM(g);
+    }
+    {
+      const bool lastd = (i == c.num_upsample - 1);
+      GemmCall g = base_gemm(hb, 4 * C, u.w2, 4 * C, 1, r2, C, 4 * C, 1);
+      g.p.bias = u.b2; g.p.gate = u.gamma; g.p.resid = xa; g.p.out_f32 = lastd ? xq : xa; g.p.ld_f32 = C;
+      if (!lastd) { g.p.out_bf16 = cur; g.p.ld_bf16 = C; }  // bf16 copy feeds the next strided conv
+      g.split_k = 1;
+      DAC_GEMM(g);
+    }
+  }
+  if (Tc != T) { set_error("dac encode: internal length mismatch %d vs %d", Tc, T); return ECHO_ERR_ARG; }
+  // ---- quantizer.pre_module + final norm in fp32 (the quantizers work on the un-rounded stream)
+  ECHO_TRY(run_window_transformer(h, h->pre, xq, B, T, C, I, H, c.post_window, c.post_norm_eps, tb, s));
+  ECHO_TRY(rmsnorm_out(xq, h->pre_final_norm, nullptr, xa, nullptr, B * T, C, c.post_norm_eps, s));
+  if (z_pre_out) ECHO_CUDA(cudaMemcpyAsync(z_pre_out, xa, (size_t)B * T * C * 4, cudaMemcpyDeviceToDevice, s));
+  // ---- semantic + residual VQ
+  VqAll va;
+  va.n = (int)h->vq.size();
+  for (int i = 0; i < va.n; ++i) {
+    const DacVqW& q = h->vq[i];
+    va.q[i] = VqDev{q.in_w, q.in_b, q.cb_norm, q.cb_sq, q.out_table, q.size};
+  }
+  switch (C) {
+    case 256: launch_k(vq_encode_kernel<1>, dim3(B * T), dim3(256), 0, s, 1, xa, va, zq_rows, codes, T, c.codebook_dim); break;
+    case 512: launch_k(vq_encode_kernel<2>, dim3(B * T), dim3(256), 0, s, 1, xa, va, zq_rows, codes, T, c.codebook_dim); break;
+    case 1024: launch_k(vq_encode_kernel<4>, dim3(B * T), dim3(256), 0, s, 1, xa, va, zq_rows, codes, T, c.codebook_dim); break;
+    default: set_error("dac encode: unsupported latent_dim %d", C); return ECHO_ERR_ARG;
+  }
+  count_launch();
+  ECHO_CUDA(cudaGetLastError());
+  return ECHO_OK;
+}
+
+int dac_enc_check(echo_handle* h, const char* who) {
+  ECHO_TRY(dac_check(h, who));
+  if (!h->dac_enc_ready) { set_error("%s: the DAC encoder / quantizer weights were not loaded", who); return ECHO_ERR_STATE; }
+  return ECHO_OK;
+}
+
+}  // namespace
+
+extern "C" int echo_dac_encode_zq(echo_handle* h, const float* audio, int B, int L, float* zq, int32_t* codes, float* z_pre,
+                                  void* stream) {
+  ECHO_TRY(dac_enc_check(h, "echo_dac_encode_zq"));
+  if (!audio || !zq || B <= 0) { set_error("echo_dac_encode_zq: bad argument"); return ECHO_ERR_ARG; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C = h->dcfg.latent_dim;
+  int hop = 1;
+  for (int i = 0; i < h->dcfg.num_enc_rates; ++i) hop *= h->dcfg.enc_rates[i];
+  const int frame = hop << h->dcfg.num_upsample;
+  if (L <= 0 || L % frame) { set_error("echo_dac_encode_zq: L=%d is not a positive multiple of %d", L, frame); return ECHO_ERR_ARG; }
+  const int T = L / frame;
+  float* rows = (float*)h->wsget("dac.zq_rows", (size_t)B * T * C * 4, s);
+  if (!rows) { set_error("out of memory"); return ECHO_ERR_CUDA; }
+  ECHO_TRY(dac_encode_run(h, audio, B, L, rows, codes, z_pre, s));
+  // (B, T, C) -> (B, C, T): the same tiled transpose with the roles of the two inner dims swapped
+  dim3 block(32, 8), grid((C + 31) / 32, (T + 31) / 32, B);
+  launch_k(transpose_ct_kernel, grid, block, 0, s, 1, (const float*)rows, zq, T, C);
+  count_launch();
+  ECHO_CUDA(cudaGetLastError());
+  return ECHO_OK;
+}
+
+extern "C" int echo_dac_encode(echo_handle* h, const float* audio, const float* pca_components, const float* pca_mean,
+                               float latent_scale, int B, int L, float* latent, void* stream) {
+  ECHO_TRY(dac_enc_check(h, "echo_dac_encode"));
+  if (!audio || !pca_components || !pca_mean || !latent || B <= 0) { set_error("echo_dac_encode: bad argument"); return ECHO_ERR_ARG; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C = h->dcfg.latent_dim, Kp = h->dcfg.pca_dim;
+  int hop = 1;
+  for (int i = 0; i < h->dcfg.num_enc_rates; ++i) hop *= h->dcfg.enc_rates[i];
+  const int frame = hop << h->dcfg.num_upsample;
+  if (L <= 0 || L % frame) { set_error("echo_dac_encode: L=%d is not a positive multiple of %d", L, frame); return ECHO_ERR_ARG; }
+  const int T = L / frame;
+  float* rows = (float*)h->wsget("dac.zq_rows", (size_t)B * T * C * 4, s);
+  if (!rows) { set_error("out of memory"); return ECHO_ERR_CUDA; }
+  ECHO_TRY(dac_encode_run(h, audio, B, L, rows, nullptr, nullptr, s));
+  launch_k(pca_project_kernel, dim3(B * T), dim3(256), (size_t)C * sizeof(float), s, 1, (const float*)rows, pca_components,
+           pca_mean, latent_scale, latent, C, Kp);
+  count_launch();
+  ECHO_CUDA(cudaGetLastError());
+  return ECHO_OK;
 }

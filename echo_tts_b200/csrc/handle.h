@@ -78,6 +78,21 @@ struct DacStageW {
   DacResUnitW ru[3];
 };
 
+struct DacEncBlockW {  // EncoderBlock (autoencoder.py:839-876): 3 ResidualUnits at cin, Snake, strided conv cin -> cout
+  DacResUnitW ru[3];
+  float* alpha_out = nullptr;
+  DacConvW down;  // k = 2 * stride, lowered to a 2-tap GEMM over the (T / stride, stride * cin) view
+  int stride = 0, cin = 0, cout = 0;
+};
+struct DacVqW {  // VectorQuantize (autoencoder.py:117-157), everything fp32
+  float* in_w = nullptr;     // [codebook_dim][C]   weight-norm folded in_proj
+  float* in_b = nullptr;     // [codebook_dim]
+  float* cb_norm = nullptr;  // [size][codebook_dim] L2-normalised codebook
+  float* cb_sq = nullptr;    // [size]               |normalised code|^2 (the reference keeps this term)
+  float* out_table = nullptr;  // [size][C]          out_proj(codebook[i]) + bias
+  int size = 0;
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -119,6 +134,18 @@ struct echo_handle {
   float* final_w = nullptr;  // [7][C] fp32
   float final_b = 0.f;
   std::map<const float*, float*> dac_alpha_inv;  // snake alpha -> 1 / (alpha + 1e-9)
+  // ---- DAC encode path (optional)
+  bool dac_enc_ready = false;
+  float *enc_conv0_w = nullptr, *enc_conv0_b = nullptr;  // first conv, Cin = 1: [7][enc_dim] fp32
+  std::vector<echo::DacEncBlockW> enc_blk;
+  std::vector<echo::DacPostLayerW> enc_tf;
+  float* enc_tf_norm = nullptr;
+  float* enc_alpha_out = nullptr;
+  echo::DacConvW enc_conv_out;  // k = 3
+  std::vector<echo::DacUpW> down;  // quantizer.downsample: `convt` holds the k2 s2 conv as a 1-tap GEMM
+  std::vector<echo::DacPostLayerW> pre;
+  float* pre_final_norm = nullptr;
+  std::vector<echo::DacVqW> vq;  // [0] semantic, [1 ..] residual
 
   void* wsget(const char* name, size_t bytes, cudaStream_t s);
   void* dalloc(size_t bytes);

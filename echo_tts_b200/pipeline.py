@@ -6,8 +6,8 @@ Mirrors the callers either side of the CUDA hot path, with the reference's names
   chunk_text / chunk_text_for_audio                 reference inference.py:140-190, handler.py:102-123
   find_flattening_point / crop_audio_to_...         reference inference.py:288-301   (vectorised: one pass, no
                                                     per-window device sync)
-  sample_pipeline                                   reference inference.py:309-347   (speaker given as latents:
-                                                    the DAC *encoder* is outside this round's scope)
+  get_speaker_latent_and_mask                       reference inference.py:240-283   (chunks batched into one call)
+  sample_pipeline                                   reference inference.py:309-347
   crossfade_chunks / normalize_chunk_boundaries     reference handler.py:126-240     (the per-sample Python loop of
                                                     handler.py:214-218 becomes one reduction)
   synthesize                                        reference handler.py:736-768     (chunk loop + stitching)
@@ -113,6 +113,41 @@ def chunk_text_for_audio(text: str, max_chars: int = 300, target_duration_second
     return chunks
 
 
+# ------------------------------------------------------------------------------------------------ audio -> latents
+@torch.inference_mode()
+def get_speaker_latent_and_mask(fish_ae, pca_state, audio: torch.Tensor,
+                                max_speaker_latent_length: int = MAX_SPEAKER_LATENT_LENGTH,
+                                audio_chunk_size: Optional[int] = None, pad_to_max: bool = False,
+                                divis_by_patch_size: Optional[int] = 4) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reference inference.get_speaker_latent_and_mask (inference.py:240-283): the speaker reference (1, L) is encoded
+    in chunks of 640 latents (the last one zero padded), latents of incomplete frames are dropped, and the length is
+    cut to a multiple of the speaker patch size. All chunks go through ONE batched encoder call here (the reference
+    loops); results are identical because chunks are independent."""
+    from .autoencoder import ae_encode
+    hop = getattr(getattr(fish_ae, "cfg", None), "frame_length", AE_DOWNSAMPLE_FACTOR)
+    if audio_chunk_size is None:
+        audio_chunk_size = 640 * hop
+    assert audio.ndim == 2 and audio.shape[0] == 1  # (1, length)
+    audio = audio[:, : max_speaker_latent_length * hop]
+    n_chunks = max(1, -(-audio.shape[1] // audio_chunk_size))
+    padded = torch.nn.functional.pad(audio, (0, n_chunks * audio_chunk_size - audio.shape[1]))
+    chunks = padded.reshape(n_chunks, 1, audio_chunk_size)
+    latent = ae_encode(fish_ae, pca_state, chunks)                      # (n_chunks, frames, 80)
+    speaker_latent = latent.reshape(1, -1, latent.shape[-1])
+    actual = audio.shape[1] // hop
+    speaker_mask = (torch.arange(speaker_latent.shape[1], device=speaker_latent.device) < actual).unsqueeze(0)
+    if pad_to_max and speaker_latent.shape[1] < max_speaker_latent_length:
+        extra = max_speaker_latent_length - speaker_latent.shape[1]
+        speaker_latent = torch.nn.functional.pad(speaker_latent, (0, 0, 0, extra))
+        speaker_mask = torch.nn.functional.pad(speaker_mask, (0, extra))
+    elif not pad_to_max:
+        speaker_latent, speaker_mask = speaker_latent[:, :actual], speaker_mask[:, :actual]
+    if divis_by_patch_size is not None:
+        n = speaker_latent.shape[1] // divis_by_patch_size * divis_by_patch_size
+        speaker_latent, speaker_mask = speaker_latent[:, :n], speaker_mask[:, :n]
+    return speaker_latent, speaker_mask
+
+
 # ------------------------------------------------------------------------------------------------ latents -> audio
 def find_flattening_point(data: torch.Tensor, target_value: float = 0.0, window_size: int = 20,
                           std_threshold: float = 0.05) -> int:
@@ -138,14 +173,21 @@ def crop_audio_to_flattening_point(audio: torch.Tensor, latent: torch.Tensor) ->
 def sample_pipeline(model, fish_ae, pca_state, sample_fn: Callable, text_prompt: str,
                     speaker_latent: Optional[torch.Tensor] = None, speaker_mask: Optional[torch.Tensor] = None,
                     rng_seed: int = 0, pad_to_max_speaker_latent_length: Optional[int] = None,
-                    pad_to_max_text_length: Optional[int] = None, normalize_text: bool = True) -> Tuple[torch.Tensor, str]:
-    """One chunk: reference inference.py:309-347 with the speaker reference passed as PCA latents
-    (`get_speaker_latent_and_mask` output) instead of raw audio. Returns (audio (1, 1, n) fp32, normalised text)."""
+                    pad_to_max_text_length: Optional[int] = None, normalize_text: bool = True,
+                    speaker_audio: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, str]:
+    """One chunk: reference inference.py:309-347. The speaker reference is either raw audio (1, L) @ 44.1 kHz
+    (`speaker_audio`, encoded here like the reference does) or already-encoded PCA latents + mask (lets a server cache
+    them per voice). Returns (audio (1, 1, n) fp32, normalised text)."""
     from .autoencoder import ae_decode
     device = model.device
     ids, mask, norm = get_text_input_ids_and_mask(
         [text_prompt], max_length=min(pad_to_max_text_length or MAX_TEXT_LENGTH, MAX_TEXT_LENGTH), device=device,
         normalize=normalize_text, return_normalized_text=True, pad_to_max=(pad_to_max_text_length is not None))
+    if speaker_audio is not None and speaker_latent is None:  # inference.py:332-339
+        speaker_latent, speaker_mask = get_speaker_latent_and_mask(
+            fish_ae, pca_state, speaker_audio.to(device),
+            max_speaker_latent_length=pad_to_max_speaker_latent_length or MAX_SPEAKER_LATENT_LENGTH,
+            pad_to_max=(pad_to_max_speaker_latent_length is not None))
     if speaker_latent is None:  # inference.py:329-331
         n = pad_to_max_speaker_latent_length or 4
         speaker_latent = torch.zeros((1, n, 80), device=device, dtype=model.dtype)

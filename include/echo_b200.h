@@ -71,6 +71,16 @@ typedef struct echo_dac_config {
   int decoder_dim;     /* 1536 */
   int num_rates;       /* 4    */
   int rates[8];        /* 8, 8, 4, 2 */
+  /* encode path (Encoder + quantizer.downsample / pre_module + RVQ); only used when the encoder weights are loaded */
+  int enc_dim;         /* 64   */
+  int num_enc_rates;   /* 4    */
+  int enc_rates[8];    /* 2, 4, 8, 8 */
+  int enc_t_layers;    /* 4    transformer layers of the last EncoderBlock (window enc_window, head_dim 64) */
+  int enc_window;      /* 512  */
+  int n_codebooks;     /* 9    residual codebooks (plus one semantic codebook) */
+  int codebook_size;   /* 1024 */
+  int semantic_codebook_size; /* 4096 */
+  int codebook_dim;    /* 8    */
 } echo_dac_config;
 
 /* Knobs of sample_euler_cfg_independent_guidances (reference inference.py:427-447). */
@@ -145,6 +155,18 @@ int echo_dac_decode(echo_handle* h, const float* z, const float* pca_components,
                     float latent_scale, int B, int T, float* audio, void* stream);
 /* == DAC.decode_zq: zq (B,1024,T) fp32 channels-first. */
 int echo_dac_decode_zq(echo_handle* h, const float* zq, int B, int T, float* audio, void* stream);
+
+/* ---- Fish S1-DAC encode: replaces inference.ae_encode (inference.py:219-224) / DAC.encode_zq (autoencoder.py:1080-1126)
+ * audio: (B, 1, L) fp32 on the device, L a multiple of the frame length (enc hop * 2^num_upsample = 2048; the caller
+ * right-pads with zeros as DAC.encode does). T = L / frame length.
+ *   echo_dac_encode_zq : z_q (B, latent_dim, T) fp32; codes (B, 1 + n_codebooks, T) int32 (optional, may be NULL);
+ *                        z_pre (B, T, latent_dim) fp32 = the quantizers' input, for parity tests (optional, may be NULL)
+ *   echo_dac_encode    : PCA-projected, scaled latents (B, T, pca_dim) fp32 = ((z_q^T - mean) @ components^T) * scale
+ * Needs the encoder / quantizer weights ("dac.encoder.*", "dac.quantizer.downsample|pre_module|*quantizer.*"). */
+int echo_dac_encode_zq(echo_handle* h, const float* audio, int B, int L, float* zq, int32_t* codes, float* z_pre,
+                       void* stream);
+int echo_dac_encode(echo_handle* h, const float* audio, const float* pca_components, const float* pca_mean,
+                    float latent_scale, int B, int L, float* latent, void* stream);
 
 /* ---- host-buffer convenience (what a non-PyTorch host binds): copies in, runs, copies out, synchronises. -- */
 int echo_sample_euler_host(echo_handle* h, const echo_sampler_args* a, const float* speaker_latent_f32_host,
