@@ -74,3 +74,19 @@ def test_synthesize_long_prompt_chunks_and_stitches(stack):
     assert out.dim() == 2 and torch.equal(out, manual)
     plain = P.synthesize(text, synth_chunk, seed=11, normalize_boundaries=False, enable_crossfade=False)
     assert plain.shape[-1] == sum(synth_chunk(c, 11 + 1000 * i).shape[-1] for i, c in enumerate(chunks))
+
+
+def test_sample_pipeline_with_speaker_audio(stack):
+    """Raw speaker audio -> get_speaker_latent_and_mask (DAC encoder on the GPU) -> sampler -> decode, the complete
+    reference sample_pipeline (inference.py:309-347). Equals the two-step call with pre-encoded latents."""
+    from echo_tts_b200.autoencoder import B200DAC
+    model, _, pca, sample_fn = stack
+    dcfg = DacConfig.tiny()
+    dac = B200DAC.from_state_dict(make_dac_weights(dcfg, 4321, include_encoder=True), dcfg, "cuda:0")
+    wav = 0.3 * torch.randn(1, 70 * dcfg.frame_length + 5, generator=torch.Generator().manual_seed(2))
+    spk, smask = P.get_speaker_latent_and_mask(dac, pca, wav.cuda())
+    assert spk.shape[1] == 68 and bool(smask.all())  # 70 complete frames -> trimmed to a multiple of 4
+    a, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] With a voice.", rng_seed=3, pad_to_max_text_length=64,
+                             speaker_audio=wav)
+    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] With a voice.", spk, smask, rng_seed=3, pad_to_max_text_length=64)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
