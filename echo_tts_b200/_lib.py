@@ -101,6 +101,7 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 
 # every symbol include/echo_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
+BLOCK_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int)  # echo_block_cb(user, index, start, len)
 SYMBOLS = {
     "echo_create": (C.c_int, [C.POINTER(_P), C.c_int]),
     "echo_destroy": (C.c_int, [_P]),
@@ -119,6 +120,8 @@ SYMBOLS = {
     "echo_sample_euler": (C.c_int, [_P, C.POINTER(SamplerArgs), _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "echo_sample_blockwise": (C.c_int, [_P, C.POINTER(SamplerArgs), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int, _P,
                                         _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "echo_sample_blockwise_stream": (C.c_int, [_P, C.POINTER(SamplerArgs), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int,
+                                               _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, BLOCK_CB, _P, _P]),
     "echo_dac_decode": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),
     "echo_dac_encode_zq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "echo_dac_encode": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),

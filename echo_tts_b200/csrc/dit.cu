@@ -905,6 +905,15 @@ extern "C" int echo_sample_blockwise(echo_handle* h, const echo_sampler_args* a,
                                      const int32_t* text_ids, const uint8_t* text_mask, int Lt, int B,
                                      const float* continuation, int Lc, const float* noise, float* prefix_out,
                                      void* stream) {
+  return echo_sample_blockwise_stream(h, a, block_sizes, nblocks, speaker_latent, speaker_mask, Ls, text_ids, text_mask, Lt,
+                                      B, continuation, Lc, noise, prefix_out, nullptr, nullptr, stream);
+}
+
+extern "C" int echo_sample_blockwise_stream(echo_handle* h, const echo_sampler_args* a, const int* block_sizes, int nblocks,
+                                            const void* speaker_latent, const uint8_t* speaker_mask, int Ls,
+                                            const int32_t* text_ids, const uint8_t* text_mask, int Lt, int B,
+                                            const float* continuation, int Lc, const float* noise, float* prefix_out,
+                                            echo_block_cb cb, void* user, void* stream) {
   ECHO_TRY(check_ready(h, "echo_sample_blockwise"));
   if (!h->has_latent) { set_error("echo_sample_blockwise: latent_* weights were not loaded"); return ECHO_ERR_STATE; }
   if (!a || !block_sizes || nblocks <= 0 || !speaker_latent || !speaker_mask || !text_ids || !text_mask || !noise || !prefix_out) {
@@ -948,6 +957,7 @@ extern "C" int echo_sample_blockwise(echo_handle* h, const echo_sampler_args* a,
     ECHO_CUDA(cudaMemcpy2DAsync(prefix_out + (size_t)start * C, (size_t)total * C * 4, xb, (size_t)bs * C * 4,
                                 (size_t)bs * C * 4, B, cudaMemcpyDeviceToDevice, s));
     nz += (size_t)B * bs * C;
+    if (cb) cb(user, bi, start, bs);  // block bi is final in stream order from here on
     start += bs;
   }
   return ECHO_OK;

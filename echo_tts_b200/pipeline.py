@@ -197,6 +197,42 @@ def sample_pipeline(model, fish_ae, pca_state, sample_fn: Callable, text_prompt:
     return crop_audio_to_flattening_point(audio, latent[0]), norm[0]
 
 
+@torch.inference_mode()
+def stream_blockwise_audio(model, fish_ae, pca_state, sample_blockwise_fn: Callable, speaker_latent, speaker_mask,
+                           text_input_ids, text_mask, rng_seed: int, block_sizes: Sequence[int], on_audio=None,
+                           **sampler_kwargs):
+    """Streaming synthesis: audio of block i is decoded while block i + 1 is being sampled.
+    `sample_blockwise_fn` is the blockwise sampler (or a functools.partial of it, as handler._build_sample_fn would
+    build). The DAC is exactly causal, so decoding the finished prefix and keeping the new samples equals decoding
+    everything at the end. Returns (final_latents, [(audio_block (1, 1, n) fp32 on the device, ready_event), ...]);
+    `ready_event` completes when that block's audio is final -- for the first block long before the sampler has
+    finished. The call itself returns once everything is enqueued (the CUDA launch queue back-pressures the host), so
+    a consumer that wants the early blocks polls the events from another thread or from `on_audio`.
+    `on_audio(index, audio_block, ready_event)` (optional) is invoked on the host right after block `index`'s decode
+    has been enqueued."""
+    from .autoencoder import ae_decode
+    hop = getattr(getattr(fish_ae, "cfg", None), "hop", AE_DOWNSAMPLE_FACTOR)
+    blocks = []
+    # size the decoder workspace for the longest prefix up front: growing it mid-stream would synchronise the stream
+    total = sum(block_sizes) + (sampler_kwargs["continuation_latent"].shape[1]
+                                if sampler_kwargs.get("continuation_latent") is not None else 0)
+    if getattr(fish_ae, "_reserved_latents", 0) < total * text_input_ids.shape[0]:
+        ae_decode(fish_ae, pca_state, torch.zeros(text_input_ids.shape[0], total, 80, device=model.device))
+        fish_ae._reserved_latents = total * text_input_ids.shape[0]
+
+    def on_block(index, start, length, prefix):
+        audio = ae_decode(fish_ae, pca_state, prefix[:, : start + length])  # enqueued behind the block's kernels
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        blocks.append((audio[..., start * hop:], ev))
+        if on_audio is not None:
+            on_audio(index, blocks[-1][0], ev)
+
+    latents = sample_blockwise_fn(model, speaker_latent, speaker_mask, text_input_ids, text_mask, rng_seed,
+                                  list(block_sizes), on_block=on_block, **sampler_kwargs)
+    return latents, blocks
+
+
 # ------------------------------------------------------------------------------------------------ stitching (host)
 def crossfade_chunks(audio_chunks: Sequence[torch.Tensor], overlap_samples: int = 4410) -> torch.Tensor:
     """Linear 100 ms cross-fades; the overlap shrinks to a quarter of the shorter side."""

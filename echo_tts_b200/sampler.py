@@ -123,7 +123,11 @@ def sample_blockwise_euler_cfg_independent_guidances(
     continuation_latent: Optional[torch.Tensor] = None,
     *,
     noise_blocks: Optional[List[torch.Tensor]] = None,
+    on_block=None,
 ) -> torch.Tensor:
+    """`on_block(index, start, length, prefix)` (optional, keyword-only extension): called on the host as soon as the
+    kernels of a block have been enqueued; `prefix[:, :start + length]` is final in stream order, so the callback can
+    enqueue the DAC decode of that prefix while the next block samples (streaming)."""
     dev = model.device
     B = text_input_ids.shape[0]
     C_lat = model.cfg.latent_size
@@ -142,9 +146,20 @@ def sample_blockwise_euler_cfg_independent_guidances(
     spk, sm, ids, tm = _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask)
     out = torch.empty(B, total, C_lat, device=dev, dtype=torch.float32)
     blocks = (C.c_int * len(block_sizes))(*[int(b) for b in block_sizes])
+    errors = []
+
+    def _cb(_user, index, start, length):
+        try:
+            on_block(index, start, length, out)
+        except BaseException as e:  # never unwind through the C frame
+            errors.append(e)
+
+    cb = _lib.BLOCK_CB(_cb) if on_block is not None else C.cast(None, _lib.BLOCK_CB)
     with torch.cuda.device(dev):
-        _lib.check(model.lib.echo_sample_blockwise(
+        _lib.check(model.lib.echo_sample_blockwise_stream(
             model.h.ptr, C.byref(a), blocks, len(block_sizes), spk.data_ptr(), sm.data_ptr(), sm.shape[1],
             ids.data_ptr(), tm.data_ptr(), tm.shape[1], B, None if cont is None else cont.data_ptr(), Lc,
-            noise.data_ptr(), out.data_ptr(), _stream(dev)), "echo_sample_blockwise")
+            noise.data_ptr(), out.data_ptr(), cb, None, _stream(dev)), "echo_sample_blockwise")
+    if errors:
+        raise errors[0]
     return out

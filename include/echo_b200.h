@@ -148,6 +148,16 @@ int echo_sample_blockwise(echo_handle* h, const echo_sampler_args* a, const int*
                           const void* speaker_latent_bf16, const uint8_t* speaker_mask, int Ls,
                           const int32_t* text_ids, const uint8_t* text_mask, int Lt, int B,
                           const float* continuation, int Lc, const float* noise, float* prefix_out, void* stream);
+/* Streaming form: identical arithmetic; after the kernels of block `index` have been ENQUEUED, `cb` is
+ * called on the host with the position of the block inside prefix_out (rows [start, start + len) of every batch
+ * item are final in stream order). The callback may enqueue work on the same stream -- e.g. echo_dac_decode of
+ * prefix_out[:, :start + len] -- so audio of block i is produced while block i + 1 samples. cb may be NULL. */
+typedef void (*echo_block_cb)(void* user, int index, int start, int len);
+int echo_sample_blockwise_stream(echo_handle* h, const echo_sampler_args* a, const int* block_sizes, int nblocks,
+                                 const void* speaker_latent_bf16, const uint8_t* speaker_mask, int Ls,
+                                 const int32_t* text_ids, const uint8_t* text_mask, int Lt, int B,
+                                 const float* continuation, int Lc, const float* noise, float* prefix_out,
+                                 echo_block_cb cb, void* user, void* stream);
 
 /* ---- DAC decode: replaces ae_decode (inference.py:226-229) + DAC.decode_zq (autoencoder.py:1128-1132) ---- */
 /* z (B,T,80) fp32 PCA latents; pca_components (80,1024) fp32; pca_mean (1024) fp32; audio (B,1,2048*T) fp32. */

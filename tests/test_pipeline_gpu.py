@@ -90,3 +90,28 @@ def test_sample_pipeline_with_speaker_audio(stack):
                              speaker_audio=wav)
     b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] With a voice.", spk, smask, rng_seed=3, pad_to_max_text_length=64)
     assert torch.equal(a, b) and torch.isfinite(a).all()
+
+
+def test_streaming_blockwise_equals_offline(stack):
+    """audio decoded block by block while the next block samples == decoding the final latents once
+    (the DAC is causal), and the latents equal the non-streaming sampler's."""
+    from echo_tts_b200.autoencoder import ae_decode
+    from echo_tts_b200.sampler import sample_blockwise_euler_cfg_independent_guidances as blockwise
+    model, dac, pca, _ = stack
+    ids, mask = P.get_text_input_ids_and_mask(["[S1] Streaming test."], 64, device="cuda")
+    spk = torch.randn(1, 16, 80, generator=torch.Generator().manual_seed(5)).cuda()
+    smask = torch.ones(1, 16, dtype=torch.bool, device="cuda")
+    knobs = dict(PLAIN_KNOBS, num_steps=4)
+    blocks = [8, 8, 4]
+    rng = torch.Generator().manual_seed(9)
+    nb = [torch.randn((1, b, 80), generator=rng) for b in blocks]
+    offline = blockwise(model, spk, smask, ids, mask, 0, blocks, noise_blocks=nb, **knobs)
+    lat, parts = P.stream_blockwise_audio(model, dac, pca, blockwise, spk, smask, ids, mask, 0, blocks, noise_blocks=nb, **knobs)
+    assert torch.equal(lat, offline) and len(parts) == 3
+    for _, ev in parts:
+        ev.synchronize()
+    streamed = torch.cat([a for a, _ in parts], dim=-1)
+    full = ae_decode(dac, pca, lat)
+    assert streamed.shape == full.shape == (1, 1, 20 * 2048)
+    assert [a.shape[-1] for a, _ in parts] == [8 * 2048, 8 * 2048, 4 * 2048]
+    assert torch.equal(streamed, full)  # exact: causal decoder, deterministic kernels
