@@ -389,7 +389,7 @@ def run_b200(args):
                          "gemm_share_of_step": rep.ms[0] / prof_total if prof_total else None,
                          # the per-launch events serialise the chain (no PDL overlap) and add ~2 us per launch; the
                          # same FLOPs over the kernel's SHARE of the un-instrumented step time:
-                         "achieved_in_uninstrumented_step": (rep.flops[0] / (ms / args.steps / Bq * 1e-3 * rep.ms[0] / prof_total) / 1e12
+                         "achieved_in_uninstrumented_step": (rep.flops[0] / (ms / args.steps * 1e-3 * rep.ms[0] / prof_total) / 1e12
                                                              if prof_total and rep.ms[0] > 0 else None),
                          "request_algorithmic_tflop": Bq * fl["total"] / 1e12,
                          "request_frac_of_peak": Bq * fl["total"] / (ms / args.steps * 1e-3) / 1e12 / peak_tf},
