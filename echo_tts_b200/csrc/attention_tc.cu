@@ -136,8 +136,8 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     if (lane == 0) ctl->ntiles = total < AT_MAX_TILES ? total : AT_MAX_TILES;
   }
   __syncthreads();
-  const int ntiles = ctl->ntiles;
-  const uint32_t tmem_base = ctl->tmem_slot;
+  const int ntiles = lds_i32(&ctl->ntiles);
+  const uint32_t tmem_base = (uint32_t)lds_i32(&ctl->tmem_slot);
   if (trace && threadIdx.x == 64) trace[2] = clock64();
 
   if (warp == 0) {
@@ -145,7 +145,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     if (lane == 0) {
       auto load_kv = [&](int j, bool is_v) {
         const int st = j & 1, u = j >> 1;
-        const int e = ctl->tiles[j];
+        const int e = lds_i32(&ctl->tiles[j]);
         const int si = e >> 24, n0 = e & 0xFFFFFF;
         const int bm = d.seg[si].batch_mod;
         const int cb = d.seg[si].batch_stride == 0 ? 0 : (bm > 0 ? b % bm : b);  // stride 0: one cache for all rows
@@ -231,10 +231,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     for (int j = 0; j < ntiles; ++j) {
       const int st = j & 1, u = j >> 1;
       // ---- key validity of this tile as a 64-bit mask (before the scores are ready)
-      const int e = ctl->tiles[j];
+      const int e = lds_i32(&ctl->tiles[j]);
       const int si = e >> 24, n0 = e & 0xFFFFFF;
       const echo_attn_segment& sg = d.seg[si];
-      const int hi = ctl->seg_hi[si];
+      const int hi = lds_i32(&ctl->seg_hi[si]);
       uint32_t vm_lo, vm_hi;
       {
         bool ok0 = (n0 + lane) < hi, ok1 = (n0 + 32 + lane) < hi;
@@ -334,8 +334,8 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     }
     if (trace && threadIdx.x == 64) trace[30] = clock64();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    uint8_t* stg = smem + Q_BYTES + (warp - 2) * 8192;  // 32 rows x 256 B, private to this warp; all tiles are dead
-    uint8_t* srow = stg + lane * 256;
+    const uint32_t stg = smem_u32(smem + Q_BYTES + (warp - 2) * 8192);  // 32 rows x 256 B, private to this warp; all tiles are dead
+    const uint32_t srow = stg + lane * 256;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       float o[32];
@@ -349,9 +349,9 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int chk = c * 4 + cc;  // 16-byte chunk of the row
-        *reinterpret_cast<uint4*>(srow + ((chk ^ (lane & 7)) << 4)) =
-            make_uint4(pack_bf16(o[8 * cc] * inv, o[8 * cc + 1] * inv), pack_bf16(o[8 * cc + 2] * inv, o[8 * cc + 3] * inv),
-                       pack_bf16(o[8 * cc + 4] * inv, o[8 * cc + 5] * inv), pack_bf16(o[8 * cc + 6] * inv, o[8 * cc + 7] * inv));
+        sts_u4(srow + ((chk ^ (lane & 7)) << 4),
+               make_uint4(pack_bf16(o[8 * cc] * inv, o[8 * cc + 1] * inv), pack_bf16(o[8 * cc + 2] * inv, o[8 * cc + 3] * inv),
+                          pack_bf16(o[8 * cc + 4] * inv, o[8 * cc + 5] * inv), pack_bf16(o[8 * cc + 6] * inv, o[8 * cc + 7] * inv)));
       }
     }
     __syncwarp();
@@ -359,7 +359,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     for (int i = 0; i < 16; ++i) {
       const int r = 2 * i + rsel;
       if (r < rows_ok) {
-        uint4 val = *reinterpret_cast<const uint4*>(stg + r * 256 + ((ch ^ (r & 7)) << 4));
+        uint4 val = lds_u4(stg + r * 256 + ((ch ^ (r & 7)) << 4));
         if (d.gate) {
           const uint32_t* vi = reinterpret_cast<const uint32_t*>(&val);
           const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gv[i]);

@@ -236,6 +236,31 @@ ECHO_DEVICE uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint3
 constexpr uint32_t kIdescBMajorMN = 1u << 16;  // instruction-descriptor bit: B operand is MN-major
 
 // ---------------------------------------------------------------- small math helpers
+// Explicit shared-space 128-bit accesses with a 32-bit address. Through a generic pointer derived from the aligned
+// dynamic-smem base the compiler emits generic LD.E / ST.E (64-bit address arithmetic, long-scoreboard latency).
+ECHO_DEVICE void sts_v4(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+ECHO_DEVICE float4 lds_v4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
+ECHO_DEVICE int lds_i32(const void* p) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+ECHO_DEVICE void sts_u4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+ECHO_DEVICE uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 ECHO_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

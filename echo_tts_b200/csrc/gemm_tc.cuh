@@ -288,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Software-pipelined: the residual of chunk c+1 is requested while chunk c is processed, and the first
         // chunk's residual before the accumulator barrier.
         constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (this warp takes ch = half, half + 2, ...)
-        float* stg = epi_stage + ew * 1024;
+        const uint32_t stg = smem_u32(epi_stage + ew * 1024);  // shared-space byte address of this warp's patch
         const int sub = lane >> 3;  // row inside a group of 4
         const int c4 = lane & 7;    // float4 column of the chunk owned after the transpose
         const int cmod = p.col_mod > 0 ? p.col_mod : p.N;  // multiple of 32, so a 32-column chunk never wraps
@@ -347,14 +347,13 @@ ECHO_CHUNK_UNROLL
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             __syncwarp();
             if (col_ok) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int rr = sub + 4 * i;
-                float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+                float4 t = lds_v4(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
                 if (rr < rows_left && c0 + 4 * c4 < nstore) {
                   const size_t grow = row0 + rr;
                   t.x = (t.x + b4.x) * p.scale; t.y = (t.y + b4.y) * p.scale;
@@ -399,7 +398,7 @@ ECHO_CHUNK_UNROLL
         // the bf16 rows leave as 64-byte runs (a lane owns 4 consecutive columns of 8 rows) instead of 32 scattered
         // 16-byte pieces per store instruction.
         constexpr int HALF_CH = BN / 64;  // chunks in the w1 half
-        float* stg = epi_stage + ew * 1024;
+        const uint32_t stg = smem_u32(epi_stage + ew * 1024);
         const int sub = lane >> 3, c4 = lane & 7;
         const size_t row0 = (size_t)bt * p.M + mbase;
         const int rows_left = p.M - mbase;
@@ -411,15 +410,14 @@ ECHO_CHUNK_UNROLL
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                make_float4(silu_f(a[4 * j]) * b[4 * j], silu_f(a[4 * j + 1]) * b[4 * j + 1],
-                            silu_f(a[4 * j + 2]) * b[4 * j + 2], silu_f(a[4 * j + 3]) * b[4 * j + 3]);
+            sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), silu_f(a[4 * j]) * b[4 * j], silu_f(a[4 * j + 1]) * b[4 * j + 1],
+                   silu_f(a[4 * j + 2]) * b[4 * j + 2], silu_f(a[4 * j + 3]) * b[4 * j + 3]);
           __syncwarp();
           bf16* op = p.out_bf16 + row0 * p.ld_bf16 + n0 / 2 + ch * 32 + 4 * c4;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = sub + 4 * i;
-            const float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+            const float4 t = lds_v4(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
             if (rr < rows_left)
               *reinterpret_cast<uint2*>(op + (size_t)rr * p.ld_bf16) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
           }
@@ -433,7 +431,7 @@ ECHO_CHUNK_UNROLL
           const int cs = g0 - si * p.sec_width;  // column inside the section
           const QkvSection sec = p.sec[si];
           const int grp = cs >> 7;
-          float* stg = epi_stage + ew * 1024;
+          const uint32_t stg = smem_u32(epi_stage + ew * 1024);
           const int sub = lane >> 3, c4 = lane & 7;
           const size_t row0 = (size_t)bt * p.M + mbase;
           const int rows_left = p.M - mbase;
@@ -481,14 +479,14 @@ ECHO_CHUNK_UNROLL
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                  make_float4(v[4 * j] * rstd, v[4 * j + 1] * rstd, v[4 * j + 2] * rstd, v[4 * j + 3] * rstd);
+              sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j] * rstd, v[4 * j + 1] * rstd, v[4 * j + 2] * rstd,
+                     v[4 * j + 3] * rstd);
             __syncwarp();
             bf16* op = sec.out + row0 * p.sec_width + cc + 4 * c4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = sub + 4 * i;
-              float4 t = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+              float4 t = lds_v4(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
               t.x *= w4.x; t.y *= w4.y; t.z *= w4.z; t.w *= w4.w;
               if (do_rope) {
                 const float x0 = t.x, y0 = t.y, x1 = t.z, y1 = t.w;

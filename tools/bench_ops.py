@@ -12,12 +12,12 @@ from echo_tts_b200 import ops  # noqa: E402
 
 def time_ms(fn, iters):
     """Launches are captured in a CUDA graph so the measurement is GPU-bound (Python launch overhead excluded)."""
-    for _ in range(3):
-        fn(0)
-    torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
+        for _ in range(3):  # warm up on the capture stream: per-stream workspaces are allocated on first use
+            fn(0)
+        torch.cuda.synchronize()
         with torch.cuda.graph(g, stream=st):
             for i in range(iters):
                 fn(i)
@@ -68,6 +68,24 @@ def main():
                 fn = lambda i: ops.gemm(h, ws[i % L], gate=gate, resid=res, out_f32=res)
             ms = time_ms(fn, a.iters)
             print(f"M={M:5d} {name:5s} N={N:6d} K={K:5d}: {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:8.1f} TFLOP/s", flush=True)
+    # LowRankAdaLN modulate + RMSNorm: alone (X hot in L2 from the previous iteration) and right behind the wo GEMM
+    for M in (1920, 640):
+        if a.only and a.only != "rmsnorm":
+            continue
+        res = torch.randn(M, D, device=dev)
+        sc, sh = 1 + 0.1 * torch.randn(1, D, device=dev), 0.1 * torch.randn(1, D, device=dev)
+        x = torch.randn(M, D, device=dev).bfloat16()
+        wo = torch.randn(D, D, device=dev).bfloat16() * D ** -0.5
+        gate = torch.randn(1, D, device=dev)
+        ms = time_ms(lambda i: ops.rmsnorm_affine(res, sc, sh), a.iters)
+        print(f"M={M:5d} rmsnorm_affine alone: {ms*1e3:8.1f} us  {M*D*6/ms/1e6:8.1f} GB/s (algorithmic 6 B/elem)", flush=True)
+
+        def pair(i):
+            ops.gemm(x, wo, gate=gate, resid=res, out_f32=res)
+            ops.rmsnorm_affine(res, sc, sh)
+        ms2 = time_ms(pair, a.iters)
+        ms1 = time_ms(lambda i: ops.gemm(x, wo, gate=gate, resid=res, out_f32=res), a.iters)
+        print(f"M={M:5d} wo GEMM {ms1*1e3:6.1f} us; wo GEMM + rmsnorm_affine {ms2*1e3:6.1f} us -> rmsnorm in the chain {1e3*(ms2-ms1):6.1f} us", flush=True)
     # attention at the CFG-step shape
     for b, S in ((3, 640), (1, 640)):
         H, Dh = 16, 128
