@@ -154,7 +154,7 @@ static TileCfg pick_cfg(const GemmCall& c) {
     const double per = std::max(bn / 2.0, (128.0 + bn / (double)cg) / 2.0);
     return waves * per + 12.0;  // small constant: prefer fewer, larger tiles on ties
   };
-  if (p.epi != EPI_GENERIC) {
+  if (p.epi != EPI_GENERIC && p.epi != EPI_ACCUM) {
     static const int env_cg = [] { const char* e = std::getenv("ECHO_GEMM_CG"); return e ? atoi(e) : 0; }();  // tuning only
     if (c.cg == 1 || env_cg == 1 || p.N % 256 != 0 || p.M <= 128) return {256, 1};
     return {256, 2};
@@ -170,6 +170,7 @@ static TileCfg pick_cfg(const GemmCall& c) {
   const int cand[3] = {256, 128, 64};
   for (int i = 0; i < 3; ++i) {
     if (p.N % cand[i] != 0) continue;
+    if (p.epi == EPI_ACCUM && cand[i] == 64) continue;  // the accumulate kernel is instantiated for 256 / 128 only
     for (int cg = 1; cg <= 2; ++cg) {
       if (cg == 2 && (!allow_pair || cand[i] == 64)) continue;
       const double cs = cost(cand[i], cg);
@@ -187,6 +188,7 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   if (p.scale == 0.f) p.scale = 1.f;
   if (p.pos_period < 1) p.pos_period = 1;
   if (p.M <= 0 || p.N <= 0 || p.Kc <= 0 || p.taps > 8) return cudaErrorInvalidValue;
+  if (p.epi == EPI_ACCUM) return cudaErrorInvalidValue;  // internal mode, chosen below
   if (p.N % 32 != 0 || (c.lda % 8) != 0 || (c.ldb % 8) != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15)) return cudaErrorInvalidValue;
 
@@ -223,6 +225,11 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
     // M = 1920). One contribution per element, so this stays bit-reproducible. ECHO_RED_EPILOGUE=0 restores the RMW.
     static const int env_red = [] { const char* e = std::getenv("ECHO_RED_EPILOGUE"); return e ? atoi(e) : 1; }();
     p.atomic_out = (eligible && env_red != 0) ? 1 : 0;
+    // ... and runs in the lean EPI_ACCUM instantiation when nothing but gate / bias / scale is asked for
+    static const int env_accum = [] { const char* e = std::getenv("ECHO_ACCUM_EPILOGUE"); return e ? atoi(e) : 1; }();
+    if (p.atomic_out && env_accum != 0 && p.act == ACT_NONE && p.n_valid == 0 && (p.col_mod == 0 || p.col_mod == p.N) &&
+        (p.rows_per_gate <= 0 || p.rows_per_gate % 32 == 0) && (c.bn == 0 || c.bn == 256 || c.bn == 128))
+      p.epi = EPI_ACCUM;
   }
   cc.p = p;
   const TileCfg tc = pick_cfg(cc);
@@ -242,6 +249,10 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
     return cudaErrorInvalidValue;
 
   switch (p.epi) {
+    case EPI_ACCUM:
+      if (bn == 256) return cg == 2 ? launch_inst<256, 64, 1, EPI_ACCUM, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_ACCUM, 1>(ma, mb, p, s);
+      if (bn == 128) return cg == 2 ? launch_inst<128, 64, 1, EPI_ACCUM, 2>(ma, mb, p, s) : launch_inst<128, 64, 1, EPI_ACCUM, 1>(ma, mb, p, s);
+      return cudaErrorInvalidValue;
     case EPI_SWIGLU:
       if (p.N % 256 != 0) return cudaErrorInvalidValue;
       return cg == 2 ? launch_inst<256, 64, 1, EPI_SWIGLU, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_SWIGLU, 1>(ma, mb, p, s);

@@ -8,7 +8,8 @@ namespace echo {
 
 typedef __nv_bfloat16 bf16;
 
-enum EpiMode : int { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV = 2 };
+enum EpiMode : int { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV = 2,
+                     EPI_ACCUM = 3 /* internal: lean instantiation of the pure residual accumulate, chosen by gemm_launch */ };
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SNAKE = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SILU = 5 };
 
 struct QkvSection {

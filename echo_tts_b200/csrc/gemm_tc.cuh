@@ -268,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nt * BN;
       const int as = it & 1;
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-      if constexpr (EPI != EPI_GENERIC) {
+      if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM) {
         mbar_wait(&tfull_bar[as], (it >> 1) & 1);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
@@ -422,6 +422,65 @@ ECHO_CHUNK_UNROLL
               *reinterpret_cast<uint2*>(op + (size_t)rr * p.ld_bf16) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
           }
           __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_ACCUM) {
+        // out_f32[r, c] += gate[c] * scale * (acc[r, c] + bias[c]) with fire-and-forget fp32 vector reductions: the
+        // residual-stream update of wo / w2 (model.py:388-389) and of every encoder / DAC transformer block. The
+        // generic epilogue executed ~2 800 instructions per warp and tile for this (ncu: epilogue 58 % of the wo
+        // kernel at M = 1920, stalls spread thin over `wait` / `selected` -- plain instruction count with only two
+        // epilogue warps per scheduler); this instantiation keeps only what the accumulate needs (~350).
+        constexpr int NCH = (BN / 32 + 1) / 2;
+        const uint32_t stg = smem_u32(epi_stage + ew * 1024);
+        const int sub = lane >> 3, c4 = lane & 7;
+        const size_t row0 = (size_t)bt * p.M + mbase;
+        const int rows_left = p.M - mbase;
+        const float* gate = p.gate;
+        // gemm_launch guarantees rows_per_gate % 32 == 0, so a warp's 32-row slab never straddles two gate rows
+        if (gate != nullptr && p.rows_per_gate > 0 && rows_left > 0) gate += (row0 / p.rows_per_gate) * (size_t)p.gate_ld;
+        const bool add_bias = p.bias != nullptr && sk == 0;
+        // rows sub + 4i of the transposed patch: (sub + 4i) & 7 is sub for even i and sub + 4 for odd i
+        const uint32_t rd_even = stg + sub * 128 + ((c4 ^ sub) << 4);
+        const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);
+        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        tc_fence_after();
+        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
+          trace[5] = clock64();
+          if (it < 4) trace[8 + 2 * it] = trace[5];
+        }
+ECHO_CHUNK_UNROLL
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int ch = half + 2 * ci;
+          const int c0 = n0 + ch * 32;
+          if (ch < BN / 32 && c0 < p.N) {
+            float v[32];
+            tc_ld_32x32(tbase + ch * 32, v);
+            float4 g4 = make_float4(p.scale, p.scale, p.scale, p.scale), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gate != nullptr) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(gate + c0 + 4 * c4));
+              g4.x *= g.x; g4.y *= g.y; g4.z *= g.z; g4.w *= g.w;
+            }
+            if (add_bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c4));
+              b4 = make_float4(b.x * g4.x, b.y * g4.y, b.z * g4.z, b.w * g4.w);
+            }
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            float* dst = p.out_f32 + (row0 + sub) * (size_t)p.ld_f32 + c0 + 4 * c4;
+            const size_t step = (size_t)4 * p.ld_f32;
+            const bool all_rows = rows_left >= 32;  // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = lds_v4(((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024);
+              t.x = fmaf(t.x, g4.x, b4.x); t.y = fmaf(t.y, g4.y, b4.y);
+              t.z = fmaf(t.z, g4.z, b4.z); t.w = fmaf(t.w, g4.w, b4.w);
+              if (all_rows || sub + 4 * i < rows_left) atomicAdd(reinterpret_cast<float4*>(dst), t);  // RED.ADD.F32x4
+              dst += step;
+            }
+            __syncwarp();  // the patch is rewritten by the next chunk
+          }
         }
       } else {  // EPI_QKV: this warp owns 32 rows x one 128-column group (group `half` of the 256-wide tile)
         static_assert(EPI != EPI_QKV || BN == 256, "QKV epilogue needs BN == 256");

@@ -284,3 +284,17 @@ def test_gemm_split_k_residual_accumulate(ops, M, N, K, split):
     ref = res + (a.float() @ w.float().T + bias) * gate
     ops.gemm(a, w, bias=bias, gate=gate, resid=res, out_f32=res, split_k=split)
     assert rel_l2(res, ref) < 1e-5
+
+
+@pytest.mark.parametrize("b,S,N,K", [(3, 160, 512, 256), (3, 640, 2048, 2048), (2, 96, 256, 128), (1, 77, 256, 192)])
+def test_gemm_residual_accumulate_gate_groups(ops, b, S, N, K):
+    """x += tanh-gate[batch row] * scale * (a @ w.T + bias): the lean accumulate instantiation (EPI_ACCUM) with one gate
+    row per S rows, as echo_dit_forward uses it (model.py:388-389 with per-sample timesteps)."""
+    M = b * S
+    a, w = _rand((M, K), 201), _rand((N, K), 202, scale=K ** -0.5)
+    gate = _rand((b, N), 203, dtype=torch.float32)
+    bias = _rand((N,), 204, dtype=torch.float32)
+    res = _rand((M, N), 205, dtype=torch.float32)
+    ref = res + (a.float() @ w.float().T + bias) * 0.75 * gate.repeat_interleave(S, 0)
+    ops.gemm(a, w, bias=bias, scale=0.75, gate=gate, rows_per_gate=S, resid=res, out_f32=res)
+    assert rel_l2(res, ref) < 1e-5
