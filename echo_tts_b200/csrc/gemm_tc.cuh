@@ -511,11 +511,24 @@ ECHO_CHUNK_UNROLL
           }
           const bool do_rope = grp < sec.rope_heads;
           const int hd2 = p.head_dim >> 1;
-          // after the transpose this lane owns columns 4*c4 .. 4*c4+3 of rows sub + 4i: RoPE pairs stay inside a lane
-          int pos[8];
+          // after the transpose this lane owns columns 4*c4 .. 4*c4+3 of rows sub + 4i: RoPE pairs stay inside a lane.
+          // Table offsets of the 8 rows in 32-bit arithmetic with ONE division (the first version took eight 64-bit
+          // modulos per tile, ~800 of the 2 400 instructions a warp spent on a tile); only the rotated groups pay it.
+          int roff[8];
+          if (do_rope) {
+            const uint32_t period = (uint32_t)p.pos_period;
+            uint32_t r = (uint32_t)(row0 + sub) % period;  // rows < 2^32
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            pos[i] = p.pos_offset + p.pos_mult * (int)((row0 + sub + 4 * i) % (size_t)p.pos_period);
+            for (int i = 0; i < 8; ++i) {
+              roff[i] = (p.pos_offset + p.pos_mult * (int)r) * hd2;
+              r += 4;
+              while (r >= period) r -= period;  // one subtraction unless the period is below 32 rows
+            }
+          }
+          const uint32_t rd_even = stg + sub * 128 + ((c4 ^ sub) << 4);  // rows sub + 4i: (sub + 4i) & 7 = sub | sub + 4
+          const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);
+          const bool all_rows = rows_left >= 32;  // warp-uniform
+          const size_t ostep = (size_t)4 * p.sec_width;
 ECHO_CHUNK_UNROLL
           for (int ch = 0; ch < 4; ++ch) {
             float v[32];
@@ -523,7 +536,7 @@ ECHO_CHUNK_UNROLL
             const int cc = cs + ch * 32;
             float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (sec.norm_w) w4 = __ldg(reinterpret_cast<const float4*>(sec.norm_w + cc + 4 * c4));
-            const int pi = ((cc % p.head_dim) >> 1) + 2 * c4;  // first of this lane's two rotation pairs
+            const int pi = ((cc & (p.head_dim - 1)) >> 1) + 2 * c4;  // first of this lane's two rotation pairs (head_dim is 64 / 128)
             // cos/sin of the 8 rows, requested up front and unconditionally (positions are always in range): with
             // 227 KB of smem there is no L1 left, every table read is an L2 round trip, and loads issued row by row
             // behind a predicate were serialised (8 exposed L2 latencies per chunk).
@@ -531,8 +544,8 @@ ECHO_CHUNK_UNROLL
             if (do_rope) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                rc[i] = __ldg(reinterpret_cast<const float2*>(p.rope_cos + (size_t)pos[i] * hd2 + pi));
-                rs[i] = __ldg(reinterpret_cast<const float2*>(p.rope_sin + (size_t)pos[i] * hd2 + pi));
+                rc[i] = __ldg(reinterpret_cast<const float2*>(p.rope_cos + roff[i] + pi));
+                rs[i] = __ldg(reinterpret_cast<const float2*>(p.rope_sin + roff[i] + pi));
               }
             }
             tc_wait_ld();
@@ -541,11 +554,10 @@ ECHO_CHUNK_UNROLL
               sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j] * rstd, v[4 * j + 1] * rstd, v[4 * j + 2] * rstd,
                      v[4 * j + 3] * rstd);
             __syncwarp();
-            bf16* op = sec.out + row0 * p.sec_width + cc + 4 * c4;
+            bf16* op = sec.out + (row0 + sub) * p.sec_width + cc + 4 * c4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int rr = sub + 4 * i;
-              float4 t = lds_v4(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+              float4 t = lds_v4(((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024);
               t.x *= w4.x; t.y *= w4.y; t.z *= w4.z; t.w *= w4.w;
               if (do_rope) {
                 const float x0 = t.x, y0 = t.y, x1 = t.z, y1 = t.w;
@@ -553,8 +565,9 @@ ECHO_CHUNK_UNROLL
                 t.z = x1 * rc[i].y - y1 * rs[i].y; t.w = x1 * rs[i].y + y1 * rc[i].y;
               }
               if (sec.sigmoid) { t.x = sigmoid_f(t.x); t.y = sigmoid_f(t.y); t.z = sigmoid_f(t.z); t.w = sigmoid_f(t.w); }
-              if (rr < rows_left)
-                *reinterpret_cast<uint2*>(op + (size_t)rr * p.sec_width) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
+              if (all_rows || sub + 4 * i < rows_left)
+                *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
+              op += ostep;
             }
             __syncwarp();
           }
