@@ -620,6 +620,19 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
   const echo_dit_config& c = h->cfg;
   const int D = c.model_size, I = c.intermediate_size, H = c.num_heads, rows = f.nb * f.S;
   const float eps = c.norm_eps;
+  // X += tanh-gate * (A @ W^T)  (model.py:388-389). One gate row per batch row when every sample has its own t; the
+  // GEMM epilogue wants those groups to be multiples of 32 rows, otherwise one launch per batch row.
+  auto gated_accum = [&](const bf16* A, int lda, const bf16* W, int ldw, int K, const float* gate) -> int {
+    const bool per_group = f.rows_per_group > 0 && f.rows_per_group % 32 != 0;
+    const int launches = per_group ? f.nb : 1, m = per_group ? f.S : rows;
+    for (int b = 0; b < launches; ++b) {
+      GemmCall g = plain_gemm(A + (size_t)b * m * lda, lda, W, ldw, m, D, K);
+      g.p.gate = gate + (size_t)b * D; g.p.rows_per_gate = per_group ? 0 : f.rows_per_group; g.p.gate_ld = D;
+      g.p.resid = sc.X + (size_t)b * m * D; g.p.out_f32 = sc.X + (size_t)b * m * D; g.p.ld_f32 = D;
+      ECHO_GEMM(g);
+    }
+    return ECHO_OK;
+  };
   for (int i = 0; i < c.num_layers; ++i) {
     const BlockW& w = h->blk[i];
     rmsnorm_affine(sc.X, sc.XN, mod_ptr(h, f, 1, 2 * i), mod_ptr(h, f, 0, 2 * i), rows, D, f.rows_per_group, D, eps, s);
@@ -657,12 +670,7 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
       cudaError_t er = attention_launch(a, s);
       if (er != cudaSuccess) { set_error("joint attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
     }
-    {
-      GemmCall g = plain_gemm(sc.AO, D, w.wo, D, rows, D, D);
-      g.p.gate = mod_ptr(h, f, 2, 2 * i); g.p.rows_per_gate = f.rows_per_group; g.p.gate_ld = D;
-      g.p.resid = sc.X; g.p.out_f32 = sc.X; g.p.ld_f32 = D;
-      ECHO_GEMM(g);
-    }
+    ECHO_TRY(gated_accum(sc.AO, D, w.wo, D, D, mod_ptr(h, f, 2, 2 * i)));
     rmsnorm_affine(sc.X, sc.XN, mod_ptr(h, f, 1, 2 * i + 1), mod_ptr(h, f, 0, 2 * i + 1), rows, D, f.rows_per_group, D,
                    eps, s);
     {
@@ -670,12 +678,7 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
       g.p.epi = EPI_SWIGLU; g.p.out_bf16 = sc.Hh; g.p.ld_bf16 = I;
       ECHO_GEMM(g);
     }
-    {
-      GemmCall g = plain_gemm(sc.Hh, I, w.w2, I, rows, D, I);
-      g.p.gate = mod_ptr(h, f, 2, 2 * i + 1); g.p.rows_per_gate = f.rows_per_group; g.p.gate_ld = D;
-      g.p.resid = sc.X; g.p.out_f32 = sc.X; g.p.ld_f32 = D;
-      ECHO_GEMM(g);
-    }
+    ECHO_TRY(gated_accum(sc.Hh, I, w.w2, I, I, mod_ptr(h, f, 2, 2 * i + 1)));
     if (f.layer_out && f.layer_out[i])
       ECHO_CUDA(cudaMemcpyAsync(f.layer_out[i], sc.X, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, s));
   }

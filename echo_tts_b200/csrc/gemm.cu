@@ -189,6 +189,11 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   if (p.pos_period < 1) p.pos_period = 1;
   if (p.M <= 0 || p.N <= 0 || p.Kc <= 0 || p.taps > 8) return cudaErrorInvalidValue;
   if (p.epi == EPI_ACCUM) return cudaErrorInvalidValue;  // internal mode, chosen below
+  // one gate row per rows_per_gate rows: a warp's 32-row slab must not straddle two of them (callers with other
+  // group sizes launch once per group, see run_dit_layers)
+  if (p.gate != nullptr && p.rows_per_gate > 0 &&
+      (p.rows_per_gate % 32 != 0 || (p.batches > 1 && p.M % 32 != 0)))
+    return cudaErrorInvalidValue;
   if (p.N % 32 != 0 || (c.lda % 8) != 0 || (c.ldb % 8) != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15)) return cudaErrorInvalidValue;
 
@@ -228,7 +233,7 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
     // ... and runs in the lean EPI_ACCUM instantiation when nothing but gate / bias / scale is asked for
     static const int env_accum = [] { const char* e = std::getenv("ECHO_ACCUM_EPILOGUE"); return e ? atoi(e) : 1; }();
     if (p.atomic_out && env_accum != 0 && p.act == ACT_NONE && p.n_valid == 0 && (p.col_mod == 0 || p.col_mod == p.N) &&
-        (p.rows_per_gate <= 0 || p.rows_per_gate % 32 == 0) && (c.bn == 0 || c.bn == 256 || c.bn == 128))
+        (c.bn == 0 || c.bn == 256 || c.bn == 128))
       p.epi = EPI_ACCUM;
   }
   cc.p = p;

@@ -294,17 +294,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cmod = p.col_mod > 0 ? p.col_mod : p.N;  // multiple of 32, so a 32-column chunk never wraps
         const size_t row0 = (size_t)bt * p.M + mbase;      // global row of this warp's slab
         const int rows_left = p.M - mbase;                 // rows of the slab inside the matrix (may be <= 0)
+        const bool all_rows = rows_left >= 32;             // warp-uniform
         // split-K: out_f32 already holds the residual; every split adds its gated partial sum atomically
         const bool atomic_out = splits > 1 || p.atomic_out != 0;
         const float* resid = atomic_out ? nullptr : p.resid;
+        // Everything that does not depend on the row is hoisted out of the row loop, which then is: one LDS, one FMA per
+        // element, residual add, stores, pointer steps. (The first version recomputed 64-bit row addresses and
+        // re-tested every option per row: ~2 800 instructions per warp and tile, and with two epilogue warps per
+        // scheduler the epilogue of a DAC conv tile -- K = 7 x 96 .. 7 x 192 -- took twice as long as its mainloop.)
+        // gemm_launch guarantees rows_per_gate % 32 == 0: a warp's 32-row slab never straddles two gate rows.
+        const float* gate = p.gate;
+        if (gate != nullptr && p.rows_per_gate > 0 && rows_left > 0)
+          gate += (size_t)((uint32_t)row0 / (uint32_t)p.rows_per_gate) * (size_t)p.gate_ld;
+        const float* bias = (p.bias != nullptr && sk == 0) ? p.bias + (size_t)bt * p.bias_bstride : nullptr;
+        const int nstore = p.n_valid > 0 ? p.n_valid : p.N;
+        const uint32_t rd_even = stg + sub * 128 + ((c4 ^ sub) << 4);  // rows sub + 4i: (sub + 4i) & 7 = sub | sub + 4
+        const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);
+        const size_t step32 = (size_t)4 * p.ld_f32, step16 = (size_t)4 * p.ld_bf16;
+        const bool snake = p.act == ACT_SNAKE;  // the hot activation (every DAC conv); the others go through apply_act
         float4 rcur[8], rnext[8];
         auto load_resid = [&](int ch, float4* r) {
           const int c0 = n0 + ch * 32;
           if (resid != nullptr && ch < BN / 32 && c0 < p.N) {
+            const float* rp = resid + (row0 + sub) * p.ld_f32 + c0 + 4 * c4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int rr = sub + 4 * i;
-              if (rr < rows_left) r[i] = *reinterpret_cast<const float4*>(resid + (row0 + rr) * p.ld_f32 + c0 + 4 * c4);
+              if (all_rows || sub + 4 * i < rows_left) r[i] = *reinterpret_cast<const float4*>(rp);
+              rp += step32;
             }
           }
         };
@@ -331,14 +347,22 @@ ECHO_CHUNK_UNROLL
             tc_ld_32x32(tbase + ch * 32, v);
             load_resid(ch + 2, rnext);
             const int c0 = n0 + ch * 32;
-            const int nstore = p.n_valid > 0 ? p.n_valid : p.N;
-            const bool col_ok = c0 < nstore;         // warp-uniform
+            const bool col_ok = c0 < nstore;                   // warp-uniform
+            const bool lane_ok = c0 + 4 * c4 < nstore;         // n_valid may cut a chunk
             const int cb = (col_ok ? c0 % cmod : 0) + 4 * c4;  // one modulo per chunk
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), a4 = g4, i4 = g4;
+            // t = (acc + bias) * scale * gate  ==  acc * gs + bs
+            float4 gs = make_float4(p.scale, p.scale, p.scale, p.scale), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f), i4 = a4;
             if (col_ok) {
-              if (p.bias && sk == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)bt * p.bias_bstride + cb));
-              if (p.gate && p.rows_per_gate <= 0) g4 = __ldg(reinterpret_cast<const float4*>(p.gate + cb));
-              if (p.act == ACT_SNAKE && p.out_bf16) {
+              if (gate != nullptr) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gate + cb));
+                gs.x *= g.x; gs.y *= g.y; gs.z *= g.z; gs.w *= g.w;
+              }
+              if (bias != nullptr) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + cb));
+                bs = make_float4(b.x * gs.x, b.y * gs.y, b.z * gs.z, b.w * gs.w);
+              }
+              if (snake && p.out_bf16) {
                 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + cb));
                 if (p.alpha_inv) i4 = __ldg(reinterpret_cast<const float4*>(p.alpha_inv + cb));
                 else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
@@ -350,28 +374,21 @@ ECHO_CHUNK_UNROLL
               sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             __syncwarp();
             if (col_ok) {
+              float* o32 = p.out_f32 ? p.out_f32 + (row0 + sub) * p.ld_f32 + c0 + 4 * c4 : nullptr;
+              bf16* o16 = p.out_bf16 ? p.out_bf16 + (row0 + sub) * p.ld_bf16 + c0 + 4 * c4 : nullptr;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int rr = sub + 4 * i;
-                float4 t = lds_v4(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-                if (rr < rows_left && c0 + 4 * c4 < nstore) {
-                  const size_t grow = row0 + rr;
-                  t.x = (t.x + b4.x) * p.scale; t.y = (t.y + b4.y) * p.scale;
-                  t.z = (t.z + b4.z) * p.scale; t.w = (t.w + b4.w) * p.scale;
-                  if (p.gate) {
-                    float4 g = g4;
-                    if (p.rows_per_gate > 0)
-                      g = __ldg(reinterpret_cast<const float4*>(p.gate + (grow / p.rows_per_gate) * (size_t)p.gate_ld + cb));
-                    t.x *= g.x; t.y *= g.y; t.z *= g.z; t.w *= g.w;
-                  }
+                float4 t = lds_v4(((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024);
+                if (lane_ok && (all_rows || sub + 4 * i < rows_left)) {
+                  t.x = fmaf(t.x, gs.x, bs.x); t.y = fmaf(t.y, gs.y, bs.y);
+                  t.z = fmaf(t.z, gs.z, bs.z); t.w = fmaf(t.w, gs.w, bs.w);
                   if (resid) { t.x += rcur[i].x; t.y += rcur[i].y; t.z += rcur[i].z; t.w += rcur[i].w; }
-                  if (p.out_f32) {
-                    float4* dst = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + c0 + 4 * c4);
-                    if (atomic_out) atomicAdd(dst, t);  // RED.ADD.F32x4
-                    else *dst = t;
+                  if (o32) {
+                    if (atomic_out) atomicAdd(reinterpret_cast<float4*>(o32), t);  // RED.ADD.F32x4
+                    else *reinterpret_cast<float4*>(o32) = t;
                   }
-                  if (p.out_bf16) {
-                    if (p.act == ACT_SNAKE) {
+                  if (o16) {
+                    if (snake) {
                       // snake(x) = x + sin^2(alpha x) / (alpha + 1e-9)   (autoencoder.py:96-102); the result is
                       // rounded to bf16, so the SFU sine (abs err ~|x| 2^-22) is far below the output quantum
                       const float s0 = __sinf(a4.x * t.x), s1 = __sinf(a4.y * t.y);
@@ -382,10 +399,11 @@ ECHO_CHUNK_UNROLL
                       t.x = apply_act(t.x, p.act, 1.f); t.y = apply_act(t.y, p.act, 1.f);
                       t.z = apply_act(t.z, p.act, 1.f); t.w = apply_act(t.w, p.act, 1.f);
                     }
-                    *reinterpret_cast<uint2*>(p.out_bf16 + grow * p.ld_bf16 + c0 + 4 * c4) =
-                        make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
+                    *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
                   }
                 }
+                if (o32) o32 += step32;
+                if (o16) o16 += step16;
               }
             }
             __syncwarp();  // the patch is rewritten by the next chunk

@@ -286,7 +286,7 @@ def test_gemm_split_k_residual_accumulate(ops, M, N, K, split):
     assert rel_l2(res, ref) < 1e-5
 
 
-@pytest.mark.parametrize("b,S,N,K", [(3, 160, 512, 256), (3, 640, 2048, 2048), (2, 96, 256, 128), (1, 77, 256, 192)])
+@pytest.mark.parametrize("b,S,N,K", [(3, 160, 512, 256), (3, 640, 2048, 2048), (2, 96, 256, 128), (4, 32, 256, 192)])
 def test_gemm_residual_accumulate_gate_groups(ops, b, S, N, K):
     """x += tanh-gate[batch row] * scale * (a @ w.T + bias): the lean accumulate instantiation (EPI_ACCUM) with one gate
     row per S rows, as echo_dit_forward uses it (model.py:388-389 with per-sample timesteps)."""
@@ -298,3 +298,14 @@ def test_gemm_residual_accumulate_gate_groups(ops, b, S, N, K):
     ref = res + (a.float() @ w.float().T + bias) * 0.75 * gate.repeat_interleave(S, 0)
     ops.gemm(a, w, bias=bias, scale=0.75, gate=gate, rows_per_gate=S, resid=res, out_f32=res)
     assert rel_l2(res, ref) < 1e-5
+
+
+def test_gemm_gate_groups_must_be_multiples_of_32(ops):
+    """A warp's 32-row slab must not straddle two gate rows: other group sizes are rejected (the DiT forward then
+    launches once per batch row, csrc/dit.cu gated_accum)."""
+    from echo_tts_b200._lib import EchoError
+    a, w = _rand((154, 128), 1), _rand((256, 128), 2)
+    gate = _rand((2, 256), 3, dtype=torch.float32)
+    res = _rand((154, 256), 4, dtype=torch.float32)
+    with pytest.raises(EchoError):
+        ops.gemm(a, w, gate=gate, rows_per_gate=77, resid=res, out_f32=res)
