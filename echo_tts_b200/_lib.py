@@ -68,7 +68,6 @@ class GemmDesc(C.Structure):
         ("sec_width", C.c_int), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("head_dim", C.c_int),
         ("pos_period", C.c_int), ("pos_offset", C.c_int), ("pos_mult", C.c_int), ("eps", C.c_float),
         ("bn", C.c_int), ("cg", C.c_int), ("dbg", C.c_int), ("trace", C.c_void_p), ("split_k", C.c_int),
-        ("tail_out", C.c_void_p), ("tail_a", C.c_void_p), ("tail_c", C.c_void_p), ("tail_eps", C.c_float),
     ]
 
 

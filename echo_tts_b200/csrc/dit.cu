@@ -622,25 +622,20 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
   const float eps = c.norm_eps;
   // X += tanh-gate * (A @ W^T)  (model.py:388-389). One gate row per batch row when every sample has its own t; the
   // GEMM epilogue wants those groups to be multiples of 32 rows, otherwise one launch per batch row.
-  // q_next: index of the AdaLN that follows (its modulate + RMSNorm is fused into the GEMM's tail), -1 = none.
-  auto gated_accum = [&](const bf16* A, int lda, const bf16* W, int ldw, int K, int q_gate, int q_next) -> int {
+  auto gated_accum = [&](const bf16* A, int lda, const bf16* W, int ldw, int K, const float* gate) -> int {
     const bool per_group = f.rows_per_group > 0 && f.rows_per_group % 32 != 0;
     const int launches = per_group ? f.nb : 1, m = per_group ? f.S : rows;
     for (int b = 0; b < launches; ++b) {
       GemmCall g = plain_gemm(A + (size_t)b * m * lda, lda, W, ldw, m, D, K);
-      g.p.gate = mod_ptr(h, f, 2, q_gate) + (size_t)b * D; g.p.rows_per_gate = per_group ? 0 : f.rows_per_group; g.p.gate_ld = D;
+      g.p.gate = gate + (size_t)b * D; g.p.rows_per_gate = per_group ? 0 : f.rows_per_group; g.p.gate_ld = D;
       g.p.resid = sc.X + (size_t)b * m * D; g.p.out_f32 = sc.X + (size_t)b * m * D; g.p.ld_f32 = D;
-      if (q_next >= 0) {
-        g.p.tail_out = sc.XN + (size_t)b * m * D; g.p.tail_eps = eps;
-        g.p.tail_a = mod_ptr(h, f, 1, q_next) + (size_t)b * D; g.p.tail_c = mod_ptr(h, f, 0, q_next) + (size_t)b * D;
-      }
       ECHO_GEMM(g);
     }
     return ECHO_OK;
   };
-  rmsnorm_affine(sc.X, sc.XN, mod_ptr(h, f, 1, 0), mod_ptr(h, f, 0, 0), rows, D, f.rows_per_group, D, eps, s);
   for (int i = 0; i < c.num_layers; ++i) {
     const BlockW& w = h->blk[i];
+    rmsnorm_affine(sc.X, sc.XN, mod_ptr(h, f, 1, 2 * i), mod_ptr(h, f, 0, 2 * i), rows, D, f.rows_per_group, D, eps, s);
     {
       GemmCall g = plain_gemm(sc.XN, D, w.wqkvg, D, rows, 4 * D, D);
       g.p.epi = EPI_QKV;
@@ -675,13 +670,15 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
       cudaError_t er = attention_launch(a, s);
       if (er != cudaSuccess) { set_error("joint attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
     }
-    ECHO_TRY(gated_accum(sc.AO, D, w.wo, D, D, 2 * i, 2 * i + 1));
+    ECHO_TRY(gated_accum(sc.AO, D, w.wo, D, D, mod_ptr(h, f, 2, 2 * i)));
+    rmsnorm_affine(sc.X, sc.XN, mod_ptr(h, f, 1, 2 * i + 1), mod_ptr(h, f, 0, 2 * i + 1), rows, D, f.rows_per_group, D,
+                   eps, s);
     {
       GemmCall g = plain_gemm(sc.XN, D, w.w13, D, rows, 2 * I, D);
       g.p.epi = EPI_SWIGLU; g.p.out_bf16 = sc.Hh; g.p.ld_bf16 = I;
       ECHO_GEMM(g);
     }
-    ECHO_TRY(gated_accum(sc.Hh, I, w.w2, I, I, 2 * i + 1, i + 1 < c.num_layers ? 2 * i + 2 : -1));
+    ECHO_TRY(gated_accum(sc.Hh, I, w.w2, I, I, mod_ptr(h, f, 2, 2 * i + 1)));
     if (f.layer_out && f.layer_out[i])
       ECHO_CUDA(cudaMemcpyAsync(f.layer_out[i], sc.X, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, s));
   }

@@ -12,7 +12,6 @@
 #include "counters.h"
 #include "profiler.h"
 #include "gemm_tc.cuh"
-#include "glue.h"
 
 namespace echo {
 
@@ -103,24 +102,6 @@ int gemm_num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
-}
-
-// {count, generation} of the grid barrier used by the fused norm tail, one pair per (device, stream) so that GEMMs on
-// different streams never share it. Allocated (and zeroed, in stream order) on first use, never freed.
-static uint32_t* get_tail_barrier(cudaStream_t s) {
-  static std::mutex mu;
-  static std::unordered_map<uint64_t, uint32_t*> table;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(s) * 64u + (uint64_t)dev;
-  std::lock_guard<std::mutex> g(mu);
-  auto it = table.find(key);
-  if (it != table.end()) return it->second;
-  uint32_t* p = nullptr;
-  if (cudaMalloc(&p, 64) != cudaSuccess) return nullptr;
-  if (cudaMemsetAsync(p, 0, 64, s) != cudaSuccess) return nullptr;
-  table[key] = p;
-  return p;
 }
 
 template <int BN, int BK, int ATOMS, int EPI, int CG>
@@ -255,21 +236,6 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
         (c.bn == 0 || c.bn == 256 || c.bn == 128))
       p.epi = EPI_ACCUM;
   }
-  // Fused norm tail (GemmParams::tail_out): only the accumulate kernel has it, and only for 2048-wide rows. Otherwise
-  // the norm runs as its own kernel right behind the GEMM -- same result, callers need not care.
-  bool norm_after = false;
-  if (p.tail_out != nullptr) {
-    static const int env_fuse = [] { const char* e = std::getenv("ECHO_FUSE_NORM"); return e ? atoi(e) : 1; }();
-    const bool fuse = env_fuse != 0 && p.epi == EPI_ACCUM && p.N == 2048 && p.ld_f32 == 2048 && p.tail_a && p.tail_c;
-    if (fuse) {
-      p.tail_bar = get_tail_barrier(s);
-      if (!p.tail_bar) return cudaErrorMemoryAllocation;
-    } else {
-      norm_after = true;
-    }
-  }
-  const GemmParams p_tail = p;
-  if (norm_after) p.tail_out = nullptr;
   cc.p = p;
   const TileCfg tc = pick_cfg(cc);
   const int bn = tc.bn, cg = tc.cg;
@@ -287,7 +253,6 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   if (!get_tensor_map(&mb, c.B, 2, (uint64_t)p.taps * p.Kc, b_rows, 1, (uint64_t)c.ldb * 2, 0, bk, bn / cg, bk * 2))
     return cudaErrorInvalidValue;
 
-  auto dispatch = [&]() -> cudaError_t {
   switch (p.epi) {
     case EPI_ACCUM:
       if (bn == 256) return cg == 2 ? launch_inst<256, 64, 1, EPI_ACCUM, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_ACCUM, 1>(ma, mb, p, s);
@@ -310,12 +275,6 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
       }
     default: return cudaErrorInvalidValue;
   }
-  };
-  const cudaError_t err = dispatch();
-  if (err == cudaSuccess && norm_after)
-    rmsnorm_affine(p_tail.out_f32, p_tail.tail_out, p_tail.tail_a, p_tail.tail_c, p_tail.M, p_tail.N, p_tail.rows_per_gate,
-                   p_tail.gate_ld, p_tail.tail_eps, s);
-  return err;
 }
 
 }  // namespace echo

@@ -50,15 +50,6 @@ struct GemmParams {
   int atomic_out;     // EPI_GENERIC, resid == out_f32: add gate * acc into out_f32 with fp32 vector reductions instead of load-add-store
   int no_b_prefetch;  // 1: B may have been written by the preceding kernel of the stream -> do not load it before the PDL wait
   int split_k;  // EPI_GENERIC with resid == out_f32 only: > 1 splits the K blocks over that many CTAs per tile (atomic adds)
-  // Residual accumulate (out_f32 == resid) with N == ld_f32 == 2048 only: after a grid-wide barrier the kernel also
-  // writes tail_out[r, :] = bf16(rmsnorm(out_f32[r, :]) * tail_a[g, :] + tail_c[g, :]) for every row (g = gate group,
-  // same rows_per_gate / gate_ld as the gate) -- the LowRankAdaLN modulate + RMSNorm that follows wo / w2.
-  // Ignored (gemm_launch returns cudaErrorNotSupported) when the launch is not eligible; callers then norm separately.
-  bf16* tail_out;
-  const float* tail_a;
-  const float* tail_c;
-  float tail_eps;
-  uint32_t* tail_bar;  // set by gemm_launch: {count, generation} of the grid barrier
   int n_valid;  // EPI_GENERIC: output columns >= n_valid are computed but not stored (N padded to a tile multiple); 0 = N
   // ---- EPI_SWIGLU: tile columns [0,BN/2) hold w1 rows, [BN/2,BN) the matching w3 rows;
   //      out_bf16[r, n0/2 + c] = silu(a) * b.     (uses out_bf16 / ld_bf16)

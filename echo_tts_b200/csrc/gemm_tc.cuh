@@ -72,15 +72,6 @@ __device__ __noinline__ float apply_act(float v, int act, float alpha) {
   }
 }
 
-ECHO_DEVICE uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-ECHO_DEVICE void st_release_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
 // each CTA stages its own 128 A rows and half of the B rows, the even CTA issues M=256 MMAs that read both CTAs'
 // shared memory and write both CTAs' TMEM, so the per-SM operand ingest drops from (128+BN) to (128+BN/2) rows per K.
@@ -609,60 +600,6 @@ ECHO_CHUNK_UNROLL
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_pair_leader(&tempty_bar[as]);  // the MMA issuer lives in the even CTA
         else mbar_arrive(&tempty_bar[as]);
-      }
-    }
-    if constexpr (EPI == EPI_ACCUM) {
-      if (p.tail_out != nullptr) {
-        // ---- fused LowRankAdaLN modulate + RMSNorm of the updated residual stream (model.py:64-83), the kernel that
-        // would otherwise follow wo / w2. Every CTA of this grid is resident (grid <= SM count, one CTA per SM), so
-        // a grid-wide barrier is safe; it costs ~1 us where the kernel boundary it replaces costs ~5 us at M = 640
-        // (tools/bench_layer.py: marginal cost of the two norm kernels in a plain step 15 us of 126).
-        // Sense-reversing barrier on two words, reusable across launches and graph replays: read the generation,
-        // arrive, and the last arriver resets the count and bumps the generation.
-        __threadfence();  // this thread's reductions into out_f32 are performed before the arrival below
-        asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
-        uint32_t* bar_count = p.tail_bar;
-        uint32_t* bar_gen = p.tail_bar + 1;
-        if (ew == 0 && lane == 0) {
-          const uint32_t gen = ld_acquire_u32(bar_gen);
-          __threadfence();
-          if (atomicAdd(bar_count, 1u) == gridDim.x - 1) {
-            *bar_count = 0u;
-            __threadfence();
-            st_release_u32(bar_gen, gen + 1u);
-          } else {
-            uint32_t spins = 0;
-            while (ld_acquire_u32(bar_gen) == gen) {
-              __nanosleep(32);
-              if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch instead of hanging the GPU
-            }
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
-        // one warp per row, the 2048-wide row in registers between the two passes (as rmsnorm_affine_warp_kernel)
-        constexpr int NV = 16;
-        for (int r = blockIdx.x * GEMM_EPI_WARPS + ew; r < p.M; r += gridDim.x * GEMM_EPI_WARPS) {
-          const float4* xr = reinterpret_cast<const float4*>(p.out_f32 + (size_t)r * p.ld_f32);
-          float4 v[NV];
-          float ss = 0.f;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) v[i] = __ldcg(xr + lane + 32 * i);  // L2: written by other SMs' reductions
-#pragma unroll
-          for (int i = 0; i < NV; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-          ss = warp_sum(ss);
-          const float rstd = rsqrtf(ss * (1.f / (128 * NV)) + p.tail_eps);
-          const size_t g = p.rows_per_gate > 0 ? (size_t)(r / p.rows_per_gate) * (size_t)p.gate_ld : 0;
-          const float4* ap = reinterpret_cast<const float4*>(p.tail_a + g);
-          const float4* cp = reinterpret_cast<const float4*>(p.tail_c + g);
-          uint2* op = reinterpret_cast<uint2*>(p.tail_out + (size_t)r * (128 * NV));
-#pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            const int c = lane + 32 * i;
-            const float4 av = __ldg(ap + c), cv = __ldg(cp + c);
-            op[c] = make_uint2(pack_bf16(fmaf(v[i].x * rstd, av.x, cv.x), fmaf(v[i].y * rstd, av.y, cv.y)),
-                               pack_bf16(fmaf(v[i].z * rstd, av.z, cv.z), fmaf(v[i].w * rstd, av.w, cv.w)));
-          }
-        }
       }
     }
   }

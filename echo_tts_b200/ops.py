@@ -24,7 +24,7 @@ def _stream() -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence[int] = (0,), bias=None,
          scale: float = 1.0, gate=None, rows_per_gate: int = 0, resid=None, out_f32=None, out_bf16=None,
          act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0, cg: int = 0, trace=None, dbg: int = 0,
-         split_k: int = 0, norm_out=None, norm_a=None, norm_c=None, norm_eps: float = 1e-5) -> None:
+         split_k: int = 0) -> None:
     """out = epilogue(sum_taps a[rows + shift] @ w[:, tap*Kc:(tap+1)*Kc].T).  a: (batches, M, Kc) or (M, Kc) bf16."""
     lib = _lib.load(strict=False)
     if a.dim() == 2:
@@ -48,8 +48,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence
     d.trace = _ptr(trace)
     d.dbg = dbg
     d.split_k = split_k
-    if norm_out is not None:  # fused LowRankAdaLN modulate + RMSNorm of the updated residual stream
-        d.tail_out, d.tail_a, d.tail_c, d.tail_eps = norm_out.data_ptr(), norm_a.data_ptr(), norm_c.data_ptr(), norm_eps
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm")
 
 

@@ -215,11 +215,6 @@ typedef struct echo_gemm_desc {
   int dbg;          /* tuning switches for the epilogue (0 in production) */
   long long* trace; /* optional device buffer, 16 clock64 stamps per CTA (kernel timeline for tuning); NULL normally */
   int split_k;      /* 0 = auto, 1 = off, n > 1 = n K-splits per tile (only when out_f32 == resid: atomic accumulate) */
-  /* optional, residual accumulate only (out_f32 == resid): also write
-     tail_out[r, :] = bf16(rmsnorm(out_f32[r, :], tail_eps) * tail_a[g, :] + tail_c[g, :]), g = r / rows_per_gate -- the
-     LowRankAdaLN modulate + RMSNorm that follows wo / w2 (model.py:64-83). Fused behind a grid barrier when N == 2048,
-     run as a separate kernel otherwise; same result either way. */
-  void* tail_out; const float* tail_a; const float* tail_c; float tail_eps;
 } echo_gemm_desc;
 int echo_op_gemm(const echo_gemm_desc* d, void* stream);
 

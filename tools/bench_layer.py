@@ -53,15 +53,11 @@ for b in (3, 1):
     eff = torch.tensor([36, 0, 36][:b], dtype=torch.int32, device=dev)
     effs = torch.tensor([53, 53, 0][:b], dtype=torch.int32, device=dev)
 
-    xn = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-
     def layer(i, parts):
-        # the two norms ride in the tails of wo / w2 (ECHO_FUSE_NORM=0: same calls, separate kernels)
-        nk = dict(norm_out=xn, norm_a=sc, norm_c=sh) if "rms" in parts else {}
-        if "rms" in parts and "wo" not in parts:
-            ops.rmsnorm_affine(X, sc, sh)
-        if "rms" in parts and "w2" not in parts:
-            ops.rmsnorm_affine(X, sc, sh)
+        if "rms" in parts:
+            xn = ops.rmsnorm_affine(X, sc, sh)
+        else:
+            xn = outs[0]
         if "qkvg" in parts:
             ops.gemm_qkv(xn, wq[i], outs, [nw, nw, None, None], [8, 8, 0, 0], [0, 0, 0, 1], D, cos, sin, 128, pos_period=640)
         if "attn" in parts:
@@ -69,11 +65,13 @@ for b in (3, 1):
             segs = [dict(k=k, v=v), dict(k=kt, v=kt, eff_len=eff, batch_mod=1), dict(k=ks, v=ks, eff_len=effs, batch_mod=1)]
             ops.attention(q, segs, ao.view(b, 640, H, 128), gate=g)
         if "wo" in parts:
-            ops.gemm(ao.view(M, D), wo[i], gate=gate, resid=X, out_f32=X, **nk)
+            ops.gemm(ao.view(M, D), wo[i], gate=gate, resid=X, out_f32=X)
+        if "rms" in parts:
+            xn = ops.rmsnorm_affine(X, sc, sh)
         if "w13" in parts:
             ops.gemm_swiglu(xn, w13[i], hh)
         if "w2" in parts:
-            ops.gemm(hh, w2[i], gate=gate, resid=X, out_f32=X, **nk)
+            ops.gemm(hh, w2[i], gate=gate, resid=X, out_f32=X)
 
     allp = ("rms", "qkvg", "attn", "wo", "w13", "w2")
     total = graph_ms(lambda: [layer(i, allp) for i in range(L)]) / L * 1e3
