@@ -191,7 +191,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "estimated_request_seconds": req_s}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -396,12 +396,26 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "setup_seconds": setup_s,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = 1
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Libraries print to stdout behind our back (NCCL: "NCCL version 2.28.9+cuda12.9" on the 8-GPU box). Keep the
+    # original stdout for the JSON line only and send everything else to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
