@@ -48,6 +48,7 @@ class SamplerArgs(C.Structure):
         ("speaker_kv_min_t", C.c_float),
         ("sequence_length", C.c_int), ("round_t_to_bf16", C.c_int),
         ("t_schedule", C.POINTER(C.c_float)),
+        ("speaker_K", C.POINTER(C.c_void_p)), ("speaker_V", C.POINTER(C.c_void_p)),
     ]
 
 

@@ -816,9 +816,29 @@ int sampler_prepare(echo_handle* h, const echo_sampler_args* a, const void* spea
   ECHO_TRY(build_mod_tables(h, t_dev, a->num_steps, a->round_t_to_bf16, &st->mod, s));
   // caches, computed once and shared by the CFG branches
   ECHO_TRY(alloc_kv(h, "smp.kt", B, Lt, &st->kt, s));
-  ECHO_TRY(alloc_kv(h, "smp.ks", B, st->Ps, &st->ks, s));
   ECHO_TRY(kv_text_impl(h, text_ids, text_mask, B, Lt, st->kt.K.data(), st->kt.V.data(), s));
-  ECHO_TRY(kv_patch_impl(h, 1, static_cast<const bf16*>(speaker_latent), B, Ls, st->ks.K.data(), st->ks.V.data(), s));
+  if (a->speaker_K != nullptr && a->speaker_V != nullptr) {
+    // per-voice persistence: the caller kept the cache echo_kv_speaker built for this speaker_latent. It is only
+    // read -- unless the sampler has to scale it (speaker_kv_scale), then it works on a copy.
+    const int L = c.num_layers;
+    for (int i = 0; i < L; ++i)
+      if (!a->speaker_K[i] || !a->speaker_V[i]) { set_error("sampler: null pointer in the cached speaker KV"); return ECHO_ERR_ARG; }
+    if (a->has_kv_scale) {
+      ECHO_TRY(alloc_kv(h, "smp.ks", B, st->Ps, &st->ks, s));
+      const size_t bytes = (size_t)B * st->Ps * c.model_size * 2;
+      for (int i = 0; i < L; ++i) {
+        ECHO_CUDA(cudaMemcpyAsync(st->ks.K[i], a->speaker_K[i], bytes, cudaMemcpyDeviceToDevice, s));
+        ECHO_CUDA(cudaMemcpyAsync(st->ks.V[i], a->speaker_V[i], bytes, cudaMemcpyDeviceToDevice, s));
+      }
+    } else {
+      st->ks.K.assign(a->speaker_K, a->speaker_K + L);
+      st->ks.V.assign(a->speaker_V, a->speaker_V + L);
+      st->ks.len = st->Ps;
+    }
+  } else {
+    ECHO_TRY(alloc_kv(h, "smp.ks", B, st->Ps, &st->ks, s));
+    ECHO_TRY(kv_patch_impl(h, 1, static_cast<const bf16*>(speaker_latent), B, Ls, st->ks.K.data(), st->ks.V.data(), s));
+  }
   // eff_len per row-batch: text [m, 0, m], speaker [m, m, 0]   (inference.py:474-475)
   st->eff3 = (int32_t*)h->wsget("smp.eff", (size_t)6 * B * 4, s);
   if (!st->eff3) { set_error("out of memory"); return ECHO_ERR_CUDA; }

@@ -148,6 +148,71 @@ def get_speaker_latent_and_mask(fish_ae, pca_state, audio: torch.Tensor,
     return speaker_latent, speaker_mask
 
 
+# ------------------------------------------------------------------------------------------------ per-voice cache
+class Voice:
+    """What a speaker reference costs once: PCA latents + mask (DAC encoder + RVQ) and the 24-layer speaker KV cache."""
+    __slots__ = ("speaker_latent", "speaker_mask", "kv", "nbytes")
+
+    def __init__(self, speaker_latent, speaker_mask, kv):
+        self.speaker_latent, self.speaker_mask, self.kv = speaker_latent, speaker_mask, kv
+        self.nbytes = speaker_latent.numel() * speaker_latent.element_size() + speaker_mask.numel() + sum(
+            k.numel() * k.element_size() + v.numel() * v.element_size() for k, v in kv)
+
+
+class VoiceCache:
+    """Per-voice persistence. The reference re-encodes the speaker audio and re-runs the speaker encoder
+    + 24 K/V projections on every request (inference.py:332-339, 465); a server that sees the same voices again keeps
+    both here: `get(voice_id, audio)` encodes on the first request and afterwards returns the stored latents, mask and
+    KV cache, which `sample_pipeline(..., voice=...)` / the samplers' `speaker_kv_cache=` consume without touching them
+    (the samplers copy the cache when they have to scale it). Least-recently-used voices are dropped once the stored
+    bytes exceed `max_bytes` (a 10 s reference is 10 MB, a 5-minute one 315 MB; a B200 has 180 GB).
+
+    `encode(audio) -> (speaker_latent, speaker_mask)` and `build_kv(speaker_latent) -> [(K, V)] * layers` default to
+    `get_speaker_latent_and_mask` and `model.get_kv_cache_speaker`."""
+
+    def __init__(self, model, fish_ae=None, pca_state=None, max_bytes: int = 8 << 30, encode: Optional[Callable] = None,
+                 build_kv: Optional[Callable] = None):
+        from collections import OrderedDict
+        self._voices: "OrderedDict[str, Voice]" = OrderedDict()
+        self.max_bytes, self.nbytes = int(max_bytes), 0
+        self.hits = self.misses = 0
+        self._encode = encode or (lambda audio: get_speaker_latent_and_mask(fish_ae, pca_state, audio.to(model.device)))
+        self._build_kv = build_kv or (lambda latent: model.get_kv_cache_speaker(latent.to(model.dtype)))
+
+    def __len__(self) -> int:
+        return len(self._voices)
+
+    def __contains__(self, voice_id: str) -> bool:
+        return voice_id in self._voices
+
+    def get(self, voice_id: str, audio: Optional[torch.Tensor] = None, speaker_latent: Optional[torch.Tensor] = None,
+            speaker_mask: Optional[torch.Tensor] = None) -> Voice:
+        """The stored voice, or encode `audio` ((1, L) @ 44.1 kHz) / take already-encoded latents + mask, build its KV
+        cache and store it. KeyError if the voice is unknown and nothing to build it from is given."""
+        v = self._voices.get(voice_id)
+        if v is not None:
+            self._voices.move_to_end(voice_id)
+            self.hits += 1
+            return v
+        if speaker_latent is None:
+            if audio is None:
+                raise KeyError(f"voice {voice_id!r} is not cached and no audio / latents were given")
+            speaker_latent, speaker_mask = self._encode(audio)
+        self.misses += 1
+        v = Voice(speaker_latent, speaker_mask, self._build_kv(speaker_latent))
+        self._voices[voice_id] = v
+        self.nbytes += v.nbytes
+        while self.nbytes > self.max_bytes and len(self._voices) > 1:
+            _, old = self._voices.popitem(last=False)
+            self.nbytes -= old.nbytes
+        return v
+
+    def drop(self, voice_id: str) -> None:
+        v = self._voices.pop(voice_id, None)
+        if v is not None:
+            self.nbytes -= v.nbytes
+
+
 # ------------------------------------------------------------------------------------------------ latents -> audio
 def find_flattening_point(data: torch.Tensor, target_value: float = 0.0, window_size: int = 20,
                           std_threshold: float = 0.05) -> int:
@@ -174,25 +239,29 @@ def sample_pipeline(model, fish_ae, pca_state, sample_fn: Callable, text_prompt:
                     speaker_latent: Optional[torch.Tensor] = None, speaker_mask: Optional[torch.Tensor] = None,
                     rng_seed: int = 0, pad_to_max_speaker_latent_length: Optional[int] = None,
                     pad_to_max_text_length: Optional[int] = None, normalize_text: bool = True,
-                    speaker_audio: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, str]:
+                    speaker_audio: Optional[torch.Tensor] = None, voice: Optional[Voice] = None) -> Tuple[torch.Tensor, str]:
     """One chunk: reference inference.py:309-347. The speaker reference is either raw audio (1, L) @ 44.1 kHz
-    (`speaker_audio`, encoded here like the reference does) or already-encoded PCA latents + mask (lets a server cache
-    them per voice). Returns (audio (1, 1, n) fp32, normalised text)."""
+    (`speaker_audio`, encoded here like the reference does), already-encoded PCA latents + mask, or a `Voice` from a
+    `VoiceCache` (latents, mask and the speaker KV cache: `sample_fn` must then accept `speaker_kv_cache=`, as the
+    samplers of this package do). Returns (audio (1, 1, n) fp32, normalised text)."""
     from .autoencoder import ae_decode
     device = model.device
     ids, mask, norm = get_text_input_ids_and_mask(
         [text_prompt], max_length=min(pad_to_max_text_length or MAX_TEXT_LENGTH, MAX_TEXT_LENGTH), device=device,
         normalize=normalize_text, return_normalized_text=True, pad_to_max=(pad_to_max_text_length is not None))
-    if speaker_audio is not None and speaker_latent is None:  # inference.py:332-339
+    if voice is None and speaker_audio is not None and speaker_latent is None:  # inference.py:332-339
         speaker_latent, speaker_mask = get_speaker_latent_and_mask(
             fish_ae, pca_state, speaker_audio.to(device),
             max_speaker_latent_length=pad_to_max_speaker_latent_length or MAX_SPEAKER_LATENT_LENGTH,
             pad_to_max=(pad_to_max_speaker_latent_length is not None))
-    if speaker_latent is None:  # inference.py:329-331
+    if voice is None and speaker_latent is None:  # inference.py:329-331
         n = pad_to_max_speaker_latent_length or 4
         speaker_latent = torch.zeros((1, n, 80), device=device, dtype=model.dtype)
         speaker_mask = torch.zeros((1, n), device=device, dtype=torch.bool)
-    latent = sample_fn(model, speaker_latent, speaker_mask, ids, mask, rng_seed)
+    if voice is not None:
+        latent = sample_fn(model, voice.speaker_latent, voice.speaker_mask, ids, mask, rng_seed, speaker_kv_cache=voice.kv)
+    else:
+        latent = sample_fn(model, speaker_latent, speaker_mask, ids, mask, rng_seed)
     audio = ae_decode(fish_ae, pca_state, latent)
     return crop_audio_to_flattening_point(audio, latent[0]), norm[0]
 

@@ -47,6 +47,25 @@ def _args(model: B200EchoDiT, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_
     return a
 
 
+def _attach_speaker_kv(a, model: B200EchoDiT, speaker_kv_cache, B: int, Ls: int) -> None:
+    """Point the sampler at a speaker KV cache kept from an earlier `model.get_kv_cache_speaker(speaker_latent)` (per-voice
+    persistence): list of num_layers (K, V), each (B, Ls/4, heads, 128) contiguous model-dtype on the
+    model's device -- the layout the reference's `get_kv_cache_speaker` returns (model.py:615-621)."""
+    L, P = model.cfg.num_layers, Ls // model.cfg.speaker_patch_size
+    if len(speaker_kv_cache) != L:
+        raise ValueError(f"speaker_kv_cache has {len(speaker_kv_cache)} layers, the model {L}")
+    Ks, Vs = (C.c_void_p * L)(), (C.c_void_p * L)()
+    for i, (k, v) in enumerate(speaker_kv_cache):
+        for t in (k, v):
+            if (t.device != model.device or t.dtype != torch.bfloat16 or not t.is_contiguous()
+                    or t.shape[0] != B or t.shape[1] != P):
+                raise ValueError(f"speaker_kv_cache[{i}]: expected contiguous bf16 ({B}, {P}, heads, head_dim) on "
+                                 f"{model.device}, got {tuple(t.shape)} {t.dtype} on {t.device}")
+        Ks[i], Vs[i] = k.data_ptr(), v.data_ptr()
+    a._kv_keepalive = (Ks, Vs, speaker_kv_cache)
+    a.speaker_K, a.speaker_V = C.cast(Ks, C.POINTER(C.c_void_p)), C.cast(Vs, C.POINTER(C.c_void_p))
+
+
 def _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask):
     dev = model.device
     spk = speaker_latent.to(dev, torch.bfloat16).contiguous()  # reference: speaker_latent.to(dtype) (inference.py:465)
@@ -78,7 +97,10 @@ def sample_euler_cfg_independent_guidances(
     sequence_length: Optional[int] = None,
     *,
     noise: Optional[torch.Tensor] = None,
+    speaker_kv_cache=None,
 ) -> torch.Tensor:
+    """`speaker_kv_cache` (optional, keyword-only extension): the result of an earlier
+    `model.get_kv_cache_speaker(speaker_latent)` for the same voice; the speaker encoder is then skipped."""
     if sequence_length is None:
         sequence_length = 640  # max sequence length during training (inference.py:449-450)
     dev = model.device
@@ -92,6 +114,8 @@ def sample_euler_cfg_independent_guidances(
     a = _args(model, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor, rescale_k,
               rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, sequence_length)
     spk, sm, ids, tm = _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask)
+    if speaker_kv_cache is not None:
+        _attach_speaker_kv(a, model, speaker_kv_cache, B, sm.shape[1])
     out = torch.empty_like(noise)
     with torch.cuda.device(dev):
         _lib.check(model.lib.echo_sample_euler(model.h.ptr, C.byref(a), spk.data_ptr(), sm.data_ptr(), sm.shape[1],
@@ -124,6 +148,7 @@ def sample_blockwise_euler_cfg_independent_guidances(
     *,
     noise_blocks: Optional[List[torch.Tensor]] = None,
     on_block=None,
+    speaker_kv_cache=None,
 ) -> torch.Tensor:
     """`on_block(index, start, length, prefix)` (optional, keyword-only extension): called on the host as soon as the
     kernels of a block have been enqueued; `prefix[:, :start + length]` is final in stream order, so the callback can
@@ -144,6 +169,8 @@ def sample_blockwise_euler_cfg_independent_guidances(
     a = _args(model, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor, rescale_k,
               rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, max(block_sizes))
     spk, sm, ids, tm = _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask)
+    if speaker_kv_cache is not None:  # same extension as in sample_euler_cfg_independent_guidances
+        _attach_speaker_kv(a, model, speaker_kv_cache, B, sm.shape[1])
     out = torch.empty(B, total, C_lat, device=dev, dtype=torch.float32)
     blocks = (C.c_int * len(block_sizes))(*[int(b) for b in block_sizes])
     errors = []

@@ -98,6 +98,13 @@ typedef struct echo_sampler_args {
                             model.dtype is bfloat16 (inference.py:489); 0: fp32 t */
   const float* t_schedule; /* optional HOST array of num_steps+1 floats (torch.linspace(1,0,n+1)*0.999 as the caller's
                               torch computes it, inference.py:459); NULL: the library's own fp32 closed form */
+  /* Optional per-voice persistence: HOST arrays of num_layers device pointers to a speaker KV cache built
+     earlier by echo_kv_speaker for the SAME speaker_latent (each (B, Ls/4, 16, 128) bf16 contiguous). When both are
+     non-NULL the samplers skip the speaker encoder + 24 K/V projections (the reference recomputes them on every call,
+     inference.py:465). The cache is never written: with speaker_kv_scale it is copied into the handle's workspace
+     first (the reference scales its per-call cache in place, inference.py:467-468, 511-513). */
+  void* const* speaker_K;
+  void* const* speaker_V;
 } echo_sampler_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

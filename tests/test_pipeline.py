@@ -152,3 +152,38 @@ def test_sharded_synthesis_equals_single_process(tmp_path, world):
     assert seeds == [42 + 1000 * i for i in range(len(chunks))]
     for r in range(world):
         assert res[r]["calls"] == [42 + 1000 * i for i in P.shard_units(len(chunks), r, world)]
+
+
+def test_voice_cache_lru_host_logic():
+    """VoiceCache bookkeeping on the CPU with stub encoders: hit/miss counting, least-recently-used eviction by bytes,
+    KeyError for an unknown voice with nothing to build it from (per-voice persistence)."""
+    from echo_tts_b200 import pipeline as P
+    calls = {"encode": 0, "kv": 0}
+
+    def encode(audio):
+        calls["encode"] += 1
+        n = audio.shape[1] // 2048 // 4 * 4
+        return torch.zeros(1, n, 80), torch.ones(1, n, dtype=torch.bool)
+
+    def build_kv(latent):
+        calls["kv"] += 1
+        p = latent.shape[1] // 4
+        return [(torch.zeros(1, p, 2, 128, dtype=torch.bfloat16), torch.zeros(1, p, 2, 128, dtype=torch.bfloat16))
+                for _ in range(3)]
+
+    one = P.Voice(*encode(torch.zeros(1, 2048 * 8)), build_kv(torch.zeros(1, 8, 80)))
+    cache = P.VoiceCache(model=None, max_bytes=int(2.5 * one.nbytes), encode=encode, build_kv=build_kv)
+    calls.update(encode=0, kv=0)
+    a = cache.get("a", audio=torch.zeros(1, 2048 * 8))
+    assert cache.get("a") is a and calls == {"encode": 1, "kv": 1} and (cache.hits, cache.misses) == (1, 1)
+    cache.get("b", audio=torch.zeros(1, 2048 * 8))
+    cache.get("a")                                        # a is now the most recently used
+    cache.get("c", audio=torch.zeros(1, 2048 * 8))        # 3 voices > 2.5: the least recently used (b) goes
+    assert "a" in cache and "c" in cache and "b" not in cache and len(cache) == 2
+    assert cache.nbytes == 2 * one.nbytes
+    with pytest.raises(KeyError):
+        cache.get("b")
+    cache.get("d", speaker_latent=one.speaker_latent, speaker_mask=one.speaker_mask)  # pre-encoded: no encode call
+    assert calls["encode"] == 3 and calls["kv"] == 4
+    cache.drop("d")
+    assert "d" not in cache

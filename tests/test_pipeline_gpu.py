@@ -115,3 +115,47 @@ def test_streaming_blockwise_equals_offline(stack):
     assert streamed.shape == full.shape == (1, 1, 20 * 2048)
     assert [a.shape[-1] for a, _ in parts] == [8 * 2048, 8 * 2048, 4 * 2048]
     assert torch.equal(streamed, full)  # exact: causal decoder, deterministic kernels
+
+
+def test_voice_cache_skips_the_speaker_encoder_and_changes_nothing(stack):
+    """SURVEY 8 f4, per-voice persistence: a cached speaker KV gives bit-identical latents (deterministic mode), for
+    the plain sampler, with speaker_kv_scale (the sampler must scale a COPY: the stored cache stays untouched) and for
+    the blockwise sampler; and it saves the speaker encoder's kernel launches."""
+    from echo_tts_b200.sampler import sample_blockwise_euler_cfg_independent_guidances as blockwise
+    from echo_tts_b200.sampler import sample_euler_cfg_independent_guidances as sample
+    from tests.util import EULER_KNOBS
+    model, dac, pca, _ = stack
+    ids, mask = P.get_text_input_ids_and_mask(["[S1] Same voice again."], 64, device="cuda")
+    spk = torch.randn(1, 16, 80, generator=torch.Generator().manual_seed(11)).cuda()
+    smask = torch.ones(1, 16, dtype=torch.bool, device="cuda")
+    cache = P.VoiceCache(model, dac, pca)
+    voice = cache.get("alice", speaker_latent=spk, speaker_mask=smask)
+    assert cache.get("alice") is voice and (cache.hits, cache.misses) == (1, 1)
+    assert len(voice.kv) == model.cfg.num_layers and voice.kv[0][0].shape[:2] == (1, 4)
+    pristine = [(k.clone(), v.clone()) for k, v in voice.kv]
+    noise = torch.randn(1, 24, 80, generator=torch.Generator().manual_seed(12))
+    for knobs in (dict(PLAIN_KNOBS, num_steps=4), dict(EULER_KNOBS, num_steps=4)):  # the latter scales the speaker KV
+        n0 = model.h.num_launches()
+        ref = sample(model, spk, smask, ids, mask, 0, sequence_length=24, noise=noise, **knobs)
+        n1 = model.h.num_launches()
+        got = sample(model, spk, smask, ids, mask, 0, sequence_length=24, noise=noise, speaker_kv_cache=voice.kv, **knobs)
+        n2 = model.h.num_launches()
+        assert torch.equal(got, ref)
+        assert n2 - n1 < n1 - n0  # no speaker encoder, no K/V projections
+        for (k, v), (k0, v0) in zip(voice.kv, pristine):
+            assert torch.equal(k, k0) and torch.equal(v, v0)
+    nb = [torch.randn((1, b, 80), generator=torch.Generator().manual_seed(13 + b)) for b in (8, 8)]
+    kn = dict(EULER_KNOBS, num_steps=4)
+    ref = blockwise(model, spk, smask, ids, mask, 0, [8, 8], noise_blocks=nb, **kn)
+    got = blockwise(model, spk, smask, ids, mask, 0, [8, 8], noise_blocks=nb, speaker_kv_cache=voice.kv, **kn)
+    assert torch.equal(got, ref)
+    # through sample_pipeline, as a server would use it
+    sample_fn = functools.partial(sample, **dict(PLAIN_KNOBS, num_steps=4), sequence_length=24)
+    a, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same voice again.", rng_seed=3, pad_to_max_text_length=64,
+                             voice=voice)
+    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same voice again.", spk, smask, rng_seed=3,
+                             pad_to_max_text_length=64)
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        sample(model, spk, smask, ids, mask, 0, sequence_length=24, noise=noise, speaker_kv_cache=voice.kv[:-1],
+               **dict(PLAIN_KNOBS, num_steps=4))
