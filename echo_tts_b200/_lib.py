@@ -68,7 +68,7 @@ class GemmDesc(C.Structure):
         ("sec_sigmoid", C.c_int * 4),
         ("sec_width", C.c_int), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("head_dim", C.c_int),
         ("pos_period", C.c_int), ("pos_offset", C.c_int), ("pos_mult", C.c_int), ("eps", C.c_float),
-        ("bn", C.c_int), ("cg", C.c_int), ("dbg", C.c_int), ("trace", C.c_void_p), ("split_k", C.c_int),
+        ("bn", C.c_int), ("cg", C.c_int), ("reserved0", C.c_int), ("trace", C.c_void_p), ("split_k", C.c_int),
     ]
 
 

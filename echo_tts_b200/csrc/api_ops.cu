@@ -57,7 +57,6 @@ extern "C" int echo_op_gemm(const echo_gemm_desc* d, void* stream) {
   p.pos_period = d->pos_period; p.pos_offset = d->pos_offset; p.pos_mult = d->pos_mult ? d->pos_mult : 1;
   p.eps = d->eps;
   p.trace = d->trace;
-  p.dbg = d->dbg;
   cudaError_t e = gemm_launch(c, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) {
     set_error("echo_op_gemm: %s (M=%d N=%d Kc=%d taps=%d epi=%d)", cudaGetErrorString(e), d->M, d->N, d->Kc, d->taps,

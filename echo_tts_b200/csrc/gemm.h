@@ -65,7 +65,6 @@ struct GemmParams {
   float eps;
   // optional debug trace: 8 clock64 stamps per CTA (see gemm_tc.cuh); null in production
   long long* trace;
-  int dbg;  // tuning only: bit0 skip resid load, bit1 skip global stores, bit2 skip gate, bit3 skip whole chunk body
 };
 
 struct GemmCall {

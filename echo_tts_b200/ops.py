@@ -23,7 +23,7 @@ def _stream() -> int:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence[int] = (0,), bias=None,
          scale: float = 1.0, gate=None, rows_per_gate: int = 0, resid=None, out_f32=None, out_bf16=None,
-         act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0, cg: int = 0, trace=None, dbg: int = 0,
+         act: int = ACT_NONE, alpha=None, col_mod: int = 0, bn: int = 0, cg: int = 0, trace=None,
          split_k: int = 0) -> None:
     """out = epilogue(sum_taps a[rows + shift] @ w[:, tap*Kc:(tap+1)*Kc].T).  a: (batches, M, Kc) or (M, Kc) bf16."""
     lib = _lib.load(strict=False)
@@ -46,7 +46,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence
     d.out_bf16, d.ld_bf16 = _ptr(out_bf16), (out_bf16.stride(-2) if out_bf16 is not None else 0)
     d.act, d.alpha, d.col_mod, d.bn, d.cg = act, _ptr(alpha), col_mod, bn, cg
     d.trace = _ptr(trace)
-    d.dbg = dbg
     d.split_k = split_k
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm")
 

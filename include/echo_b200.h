@@ -219,7 +219,7 @@ typedef struct echo_gemm_desc {
   int pos_mult; float eps;
   int bn; /* 0 = auto */
   int cg; /* 0 = auto, 1 = one CTA per tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
-  int dbg;          /* tuning switches for the epilogue (0 in production) */
+  int reserved0;    /* must be 0 */
   long long* trace; /* optional device buffer, 16 clock64 stamps per CTA (kernel timeline for tuning); NULL normally */
   int split_k;      /* 0 = auto, 1 = off, n > 1 = n K-splits per tile (only when out_f32 == resid: atomic accumulate) */
 } echo_gemm_desc;
