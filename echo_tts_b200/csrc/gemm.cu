@@ -204,6 +204,13 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   // to run in the last fp32 bit; after a few bf16 re-quantisations that decorrelates two runs down to the bf16
   // rounding-noise floor (same size as the error against the fp32 reference).
   // echo_set_deterministic(1) switches it off (bit-reproducible, ~4 % slower at batch 1).
+  // L2 eviction hints: B is "streamed" when it is a large weight matrix read once per launch (every DiT / encoder
+  // linear); the small, tile-after-tile reused conv weights of the DAC keep the default policy. ECHO_B_STREAM=0: off.
+  {
+    static const int env_bs = [] { const char* e = std::getenv("ECHO_B_STREAM"); return e ? atoi(e) : 1; }();
+    const size_t b_bytes = (size_t)p.N * p.taps * p.Kc * 2 * (p.b_batch_rows ? p.batches : 1);
+    p.b_stream = (env_bs != 0 && b_bytes >= ((size_t)4 << 20)) ? 1 : 0;
+  }
   GemmCall cc = c;
   p.split_k = 1;
   {

@@ -48,6 +48,7 @@ struct GemmParams {
   const float* alpha_inv;  // optional 1 / (alpha + 1e-9) [col_mod]
   int col_mod;
   int atomic_out;     // EPI_GENERIC, resid == out_f32: add gate * acc into out_f32 with fp32 vector reductions instead of load-add-store
+  int b_stream;       // set by gemm_launch: B is a large weight matrix read once per launch -> B loads L2 evict-first, A loads evict-last
   int no_b_prefetch;  // 1: B may have been written by the preceding kernel of the stream -> do not load it before the PDL wait
   int split_k;  // EPI_GENERIC with resid == out_f32 only: > 1 splits the K blocks over that many CTAs per tile (atomic adds)
   int n_valid;  // EPI_GENERIC: output columns >= n_valid are computed but not stored (N padded to a tile multiple); 0 = N

@@ -145,6 +145,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Everything above touched only shared memory / TMEM / the kernel parameters: it overlaps the predecessor's tail.
   // So does the first pipeline fill of the B operand: B is always a weight matrix (written at load time, never by a
   // kernel of the chain), so its TMA loads may start before the predecessor has finished; only A waits.
+  // Weights that are streamed once per launch (a DiT linear is 8-48 MB, the whole block 117 MB against 126 MB of L2) are
+  // loaded with evict-first priority so they do not push the activations the next kernels re-read out of L2; the
+  // activations (re-read by every column tile, written by the preceding kernel) with evict-last. Measured on whole
+  // requests, same box: 192.0 -> 189.8 ms for the weights, another 0.3 % for the activations.
+  const uint64_t b_policy = p.b_stream ? kL2EvictFirst : kL2EvictNormal;
+  const uint64_t a_policy = p.b_stream ? kL2EvictLast : kL2EvictNormal;
   int b_prefetched = 0;  // k-blocks of this CTA's first work unit whose B tiles are already in flight
   if (warp == 0 && lane == 0 && !p.no_b_prefetch && tile0 < num_tiles) {
     const int sk = tile0 % splits, tile = tile0 / splits;
@@ -162,8 +168,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* sb = smem + i * STAGE_BYTES + A_ATOM * ATOMS;
 #pragma unroll
       for (int a = 0; a < ATOMS; ++a) {
-        if constexpr (CG == 2) tma_load_2d_pair(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
-        else tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+        if constexpr (CG == 2) tma_load_2d_pair_hint(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
+        else tma_load_2d_hint(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
       }
     }
     b_prefetched = pre;
@@ -198,11 +204,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int a = 0; a < ATOMS; ++a) {
             if constexpr (CG == 2) {
-              tma_load_3d_pair(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
-              if (!b_done) tma_load_2d_pair(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+              tma_load_3d_pair_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
+              if (!b_done) tma_load_2d_pair_hint(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
             } else {
-              tma_load_3d(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div);
-              if (!b_done) tma_load_2d(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0);
+              tma_load_3d_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
+              if (!b_done) tma_load_2d_hint(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
             }
           }
           if (trace && kb == kb_lo && unit == tile0) trace[2] = clock64();
