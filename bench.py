@@ -372,7 +372,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"replicas x{world} (requests sharded, no collective per step)",
-                       "l2": "per step the kernels stream 5.6 GB of bf16 weights (>> 126 MB L2): inputs larger than L2",
+                       "l2": "per step the kernels stream the 2.7 GB of bf16 weights of the 24 DiT blocks (>> 126 MB L2): inputs larger than L2",
                        "p50_latency_ms": p50_ms, "requests_per_call": Bq,
                        "reproducibility": "default mode uses atomic split-K in the M=640 residual GEMMs (run-to-run "
                                           "differences at the bf16 noise floor); echo_set_deterministic(1) is bit-exact"},
