@@ -96,20 +96,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     __syncwarp();
     tmem_alloc<256>(&ctl->tmem_slot);
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // only shared memory / TMEM / kernel parameters were touched so far: overlaps the predecessor's tail
-  pdl_wait();
-  pdl_trigger();
-  if (trace && threadIdx.x == 64) trace[1] = clock64();
-  if (warp == 0 && lane == 0) {  // Q does not depend on the tile list: get it moving first
-    mbar_expect_tx(&ctl->q_full, Q_BYTES);
-    tma_load_3d(sQ, &maps.q, &ctl->q_full, h * 128, q0, b);
-    tma_load_3d(sQ + Q_BYTES / 2, &maps.q, &ctl->q_full, h * 128 + 64, q0, b);
-  }
-
-  // ---- tile list: (segment << 24 | first key) for every 64-key tile that can hold a valid key
+  // ---- tile list, built BEFORE the dependency wait: it reads only the descriptor and eff_len[], which the kernel
+  // chain computes once per request (mask_eff_len in sampler_prepare), never in the kernel right before this one.
+  // (Contract: eff_len must not be written by an immediate predecessor that triggers its dependents early.)
+  // (segment << 24 | first key) for every 64-key tile that can hold a valid key
   if (warp == 2) {
     int hi = 0;
     if (lane < d.nseg) {
@@ -135,7 +125,18 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     for (int i = 0; i < nt && off + i < AT_MAX_TILES; ++i) ctl->tiles[off + i] = (lane << 24) | (i * TK);
     if (lane == 0) ctl->ntiles = total < AT_MAX_TILES ? total : AT_MAX_TILES;
   }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  // only shared memory / TMEM / kernel parameters / eff_len were touched so far: overlaps the predecessor's tail
+  pdl_wait();
+  pdl_trigger();
+  if (trace && threadIdx.x == 64) trace[1] = clock64();
+  if (warp == 0 && lane == 0) {  // Q first; the K / V tiles follow from the producer loop below without another barrier
+    mbar_expect_tx(&ctl->q_full, Q_BYTES);
+    tma_load_3d(sQ, &maps.q, &ctl->q_full, h * 128, q0, b);
+    tma_load_3d(sQ + Q_BYTES / 2, &maps.q, &ctl->q_full, h * 128 + 64, q0, b);
+  }
   const int ntiles = lds_i32(&ctl->ntiles);
   const uint32_t tmem_base = (uint32_t)lds_i32(&ctl->tmem_slot);
   if (trace && threadIdx.x == 64) trace[2] = clock64();
