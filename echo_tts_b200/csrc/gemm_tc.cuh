@@ -486,28 +486,34 @@ ECHO_CHUNK_UNROLL
         // rows sub + 4i of the transposed patch: (sub + 4i) & 7 is sub for even i and sub + 4 for odd i
         const uint32_t rd_even = stg + sub * 128 + ((c4 ^ sub) << 4);
         const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);
+        // gate / bias of all this warp's chunks are fetched while the MMAs still run (they come from the AdaLN tables /
+        // the weights, never from the preceding kernel): behind the accumulator barrier there is no L2 round trip left
+        float4 gq[NCH], bq[NCH];
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c0 = n0 + (half + 2 * ci) * 32;
+          gq[ci] = make_float4(1.f, 1.f, 1.f, 1.f);
+          bq[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (half + 2 * ci < BN / 32 && c0 < p.N) {
+            if (gate != nullptr) gq[ci] = __ldg(reinterpret_cast<const float4*>(gate + c0 + 4 * c4));
+            if (add_bias) bq[ci] = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c4));
+          }
+        }
         mbar_wait(&tfull_bar[as], (it >> 1) & 1);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
           trace[5] = clock64();
           if (it < 4) trace[8 + 2 * it] = trace[5];
         }
-ECHO_CHUNK_UNROLL
+#pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int ch = half + 2 * ci;
           const int c0 = n0 + ch * 32;
           if (ch < BN / 32 && c0 < p.N) {
             float v[32];
             tc_ld_32x32(tbase + ch * 32, v);
-            float4 g4 = make_float4(p.scale, p.scale, p.scale, p.scale), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gate != nullptr) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(gate + c0 + 4 * c4));
-              g4.x *= g.x; g4.y *= g.y; g4.z *= g.z; g4.w *= g.w;
-            }
-            if (add_bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c4));
-              b4 = make_float4(b.x * g4.x, b.y * g4.y, b.z * g4.z, b.w * g4.w);
-            }
+            const float4 g4 = make_float4(gq[ci].x * p.scale, gq[ci].y * p.scale, gq[ci].z * p.scale, gq[ci].w * p.scale);
+            const float4 b4 = make_float4(bq[ci].x * g4.x, bq[ci].y * g4.y, bq[ci].z * g4.z, bq[ci].w * g4.w);
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 8; ++j)

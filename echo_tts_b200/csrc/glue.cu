@@ -107,12 +107,32 @@ __global__ void __launch_bounds__(256) rmsnorm_affine_warp_kernel(const float* _
                                                                   const float* __restrict__ a,
                                                                   const float* __restrict__ c0, int rows,
                                                                   int rows_per_group, int64_t group_ld, float eps) {
-  pdl_wait();
-  pdl_trigger();
   constexpr int W = 128 * NV;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= rows) return;
+  const bool live = r < rows;
+  // The modulation rows (a = 1 + scale, c0 = shift: AdaLN tables built once per request, or static norm weights) do
+  // not depend on the preceding kernel: they are in registers before the dependency wait returns, so that behind it
+  // there is one L2 round trip (the row of X) instead of two. Contract: a / c0 are not written by an immediate
+  // predecessor that triggers its dependents early.
+  float4 av[NV], cv[NV];
+  if (live) {
+    const size_t g = rows_per_group > 0 ? (size_t)(r / rows_per_group) * group_ld : 0;
+    const float4* ap = reinterpret_cast<const float4*>(a + g);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) av[i] = __ldg(ap + lane + 32 * i);
+    if (c0) {
+      const float4* cp = reinterpret_cast<const float4*>(c0 + g);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) cv[i] = __ldg(cp + lane + 32 * i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) cv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (!live) return;
   const float4* xr = reinterpret_cast<const float4*>(X + (size_t)r * W);
   float4 v[NV];
   float ss = 0.f;
@@ -122,21 +142,13 @@ __global__ void __launch_bounds__(256) rmsnorm_affine_warp_kernel(const float* _
   for (int i = 0; i < NV; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   ss = warp_sum_f(ss);
   const float rstd = rsqrtf(ss / (float)W + eps);
-  const size_t g = rows_per_group > 0 ? (size_t)(r / rows_per_group) * group_ld : 0;
-  const float4* ap = reinterpret_cast<const float4*>(a + g);
-  const float4* cp = c0 ? reinterpret_cast<const float4*>(c0 + g) : nullptr;
   uint2* op = reinterpret_cast<uint2*>(out + (size_t)r * W);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = lane + 32 * i;
-    const float4 av = __ldg(ap + c);
     float4 o;
-    o.x = v[i].x * rstd * av.x; o.y = v[i].y * rstd * av.y; o.z = v[i].z * rstd * av.z; o.w = v[i].w * rstd * av.w;
-    if (cp) {
-      const float4 cv = __ldg(cp + c);
-      o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
-    }
-    op[c] = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+    o.x = fmaf(v[i].x * rstd, av[i].x, cv[i].x); o.y = fmaf(v[i].y * rstd, av[i].y, cv[i].y);
+    o.z = fmaf(v[i].z * rstd, av[i].z, cv[i].z); o.w = fmaf(v[i].w * rstd, av[i].w, cv[i].w);
+    op[lane + 32 * i] = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
   }
 }
 
