@@ -375,7 +375,7 @@ def run_b200(args):
                        "l2": "per step the kernels stream the 2.7 GB of bf16 weights of the 24 DiT blocks (>> 126 MB L2): inputs larger than L2",
                        "p50_latency_ms": p50_ms, "requests_per_call": Bq,
                        "reproducibility": "default mode uses atomic split-K in the M=640 residual GEMMs (run-to-run "
-                                          "differences at the bf16 noise floor); echo_set_deterministic(1) is bit-exact"},
+                                          "differences at the bf16 noise floor); echo_set_deterministic(1) is bit-exact and ~1 % slower"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

@@ -7,7 +7,8 @@ __all__ = ["_lib", "ops", "set_deterministic"]
 
 
 def set_deterministic(on: bool = True) -> None:
-    """Process-wide switch: True = bit-reproducible results (no atomic split-K in the residual-accumulate GEMMs,
-    about 4 % slower at batch 1); False (default) = fastest. Both meet the same tolerances against the reference."""
+    """Process-wide switch: True = bit-reproducible results (the split-K slices of the residual-accumulate GEMMs are
+    summed in a fixed order instead of with fp32 atomics, about 1 % slower at batch 1); False (default) = fastest.
+    Both meet the same tolerances against the reference."""
     from . import _lib
     _lib.check(_lib.load().echo_set_deterministic(int(bool(on))), "echo_set_deterministic")

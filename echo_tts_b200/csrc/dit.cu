@@ -580,9 +580,10 @@ int dit_in_proj(echo_handle* h, const float* x, float* X, int rows, int copies, 
 }
 
 // out_norm + out_proj (model.py:601-604): RMSNorm with weight -> bf16, then a GEMM whose N is padded to 128.
-int dit_out_proj(echo_handle* h, const float* X, bf16* XN, float* v_out, int rows, cudaStream_t s) {
+int dit_out_proj(echo_handle* h, const float* X, bf16* XN, float* v_out, int rows, cudaStream_t s,
+                 const float* parts = nullptr, int nparts = 0, int64_t part_stride = 0) {
   const echo_dit_config& c = h->cfg;
-  rmsnorm_affine(X, XN, h->out_norm, nullptr, rows, c.model_size, 0, 0, c.norm_eps, s);
+  rmsnorm_affine(X, XN, h->out_norm, nullptr, rows, c.model_size, 0, 0, c.norm_eps, s, parts, nparts, part_stride);
   GemmCall g = plain_gemm(XN, c.model_size, h->out_proj_w, c.model_size, rows, 128, c.model_size);
   g.p.bias = h->out_proj_b; g.p.out_f32 = v_out; g.p.ld_f32 = c.latent_size; g.p.n_valid = c.latent_size;
   g.bn = 64;  // 2 x more CTAs than one 128-wide tile per row block; the GEMM is latency-bound either way
@@ -622,6 +623,15 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
   const float eps = c.norm_eps;
   // X += tanh-gate * (A @ W^T)  (model.py:388-389). One gate row per batch row when every sample has its own t; the
   // GEMM epilogue wants those groups to be multiples of 32 rows, otherwise one launch per batch row.
+  // Split-K planes: when wo / w2 split K (M <= ~1000 rows) the slices park their partial sums in `part` and the norm
+  // kernel that follows folds them into X -- no fp32 atomics. Not in the per-layer capture mode of the tests (X must
+  // be final right after w2 there) and not when the gate groups force one launch per batch row.
+  const int nv = D / 128;
+  const bool planes_ok = f.layer_out == nullptr && D % 128 == 0 && (nv == 2 || nv == 4 || nv == 8 || nv == 10 || nv == 16) &&
+                         !(f.rows_per_group > 0 && f.rows_per_group % 32 != 0) && rows <= 1280;
+  float* part = planes_ok ? (float*)h->wsget("dit.part", (size_t)4 * rows * D * 4, s) : nullptr;
+  const int64_t part_stride = (int64_t)rows * D;
+  int pending = 0;  // planes waiting to be folded into X by the next norm
   auto gated_accum = [&](const bf16* A, int lda, const bf16* W, int ldw, int K, const float* gate) -> int {
     const bool per_group = f.rows_per_group > 0 && f.rows_per_group % 32 != 0;
     const int launches = per_group ? f.nb : 1, m = per_group ? f.S : rows;
@@ -629,13 +639,18 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
       GemmCall g = plain_gemm(A + (size_t)b * m * lda, lda, W, ldw, m, D, K);
       g.p.gate = gate + (size_t)b * D; g.p.rows_per_gate = per_group ? 0 : f.rows_per_group; g.p.gate_ld = D;
       g.p.resid = sc.X + (size_t)b * m * D; g.p.out_f32 = sc.X + (size_t)b * m * D; g.p.ld_f32 = D;
+      if (part) { g.part_ws = part; g.part_stride = part_stride; g.parts_used = &pending; }
       ECHO_GEMM(g);
     }
     return ECHO_OK;
   };
+  auto norm = [&](const float* a, const float* c0, int rows_per_group, int64_t group_ld) {
+    rmsnorm_affine(sc.X, sc.XN, a, c0, rows, D, rows_per_group, group_ld, eps, s, part, pending, part_stride);
+    pending = 0;
+  };
   for (int i = 0; i < c.num_layers; ++i) {
     const BlockW& w = h->blk[i];
-    rmsnorm_affine(sc.X, sc.XN, mod_ptr(h, f, 1, 2 * i), mod_ptr(h, f, 0, 2 * i), rows, D, f.rows_per_group, D, eps, s);
+    norm(mod_ptr(h, f, 1, 2 * i), mod_ptr(h, f, 0, 2 * i), f.rows_per_group, D);
     {
       GemmCall g = plain_gemm(sc.XN, D, w.wqkvg, D, rows, 4 * D, D);
       g.p.epi = EPI_QKV;
@@ -671,8 +686,7 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
       if (er != cudaSuccess) { set_error("joint attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
     }
     ECHO_TRY(gated_accum(sc.AO, D, w.wo, D, D, mod_ptr(h, f, 2, 2 * i)));
-    rmsnorm_affine(sc.X, sc.XN, mod_ptr(h, f, 1, 2 * i + 1), mod_ptr(h, f, 0, 2 * i + 1), rows, D, f.rows_per_group, D,
-                   eps, s);
+    norm(mod_ptr(h, f, 1, 2 * i + 1), mod_ptr(h, f, 0, 2 * i + 1), f.rows_per_group, D);
     {
       GemmCall g = plain_gemm(sc.XN, D, w.w13, D, rows, 2 * I, D);
       g.p.epi = EPI_SWIGLU; g.p.out_bf16 = sc.Hh; g.p.ld_bf16 = I;
@@ -682,7 +696,7 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
     if (f.layer_out && f.layer_out[i])
       ECHO_CUDA(cudaMemcpyAsync(f.layer_out[i], sc.X, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, s));
   }
-  ECHO_TRY(dit_out_proj(h, sc.X, sc.XN, v_out, rows, s));
+  ECHO_TRY(dit_out_proj(h, sc.X, sc.XN, v_out, rows, s, part, pending, part_stride));  // folds the last w2's planes
   ECHO_CUDA(cudaGetLastError());
   return ECHO_OK;
 }

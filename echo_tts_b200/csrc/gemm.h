@@ -47,6 +47,8 @@ struct GemmParams {
   const float* alpha;  // snake alpha [col_mod]
   const float* alpha_inv;  // optional 1 / (alpha + 1e-9) [col_mod]
   int col_mod;
+  float* part_out;     // EPI_ACCUM with split-K, set by gemm_launch from GemmCall::part_ws: slice sk stores its gated partial
+  int64_t part_stride; // sum to part_out + sk * part_stride (same row / column layout as out_f32) instead of reducing into out_f32
   int atomic_out;     // EPI_GENERIC, resid == out_f32: add gate * acc into out_f32 with fp32 vector reductions instead of load-add-store
   int b_stream;       // set by gemm_launch: B is a large weight matrix read once per launch -> B loads L2 evict-first, A loads evict-last
   int no_b_prefetch;  // 1: B may have been written by the preceding kernel of the stream -> do not load it before the PDL wait
@@ -79,6 +81,13 @@ struct GemmCall {
   int bn;  // tile N override (0 = auto)
   int cg;  // CTA-group override: 0 = auto, 1 = single CTA tiles, 2 = CTA pairs (tcgen05 cta_group::2)
   int split_k;  // 0 = auto, 1 = off, n = force n splits (ignored unless the epilogue is a pure residual accumulate)
+  // Optional, residual accumulate only: a workspace of at least 4 planes of part_stride floats each (plane layout =
+  // out_f32's). When gemm_launch splits K it then makes every slice store its partial sum to its own plane instead of
+  // reducing into out_f32 with atomics, and reports the number of planes in *parts_used (0: out_f32 was updated as
+  // usual). The caller must add the planes to out_f32 (rmsnorm_affine does it on the fly).
+  float* part_ws;
+  int64_t part_stride;
+  int* parts_used;
 };
 
 cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s);

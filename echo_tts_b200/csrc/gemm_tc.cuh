@@ -519,16 +519,33 @@ ECHO_CHUNK_UNROLL
             for (int j = 0; j < 8; ++j)
               sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             __syncwarp();
-            float* dst = p.out_f32 + (row0 + sub) * (size_t)p.ld_f32 + c0 + 4 * c4;
             const size_t step = (size_t)4 * p.ld_f32;
             const bool all_rows = rows_left >= 32;  // warp-uniform
+            if (p.part_out != nullptr) {
+              // split-K without atomics: slice sk parks its gated partial sum in its own plane of a workspace and the
+              // LowRankAdaLN / RMSNorm kernel that follows adds the planes to the residual stream (glue.cu). The L2
+              // executes fp32 reductions element by element: %globaltimer stamps showed the dependent kernel's wait
+              // returning 8 us after the last CTA of a 3-way split wo had issued its reductions, against 1.2 us
+              // behind a kernel with plain stores (tools/trace_boundary.py). Fixed summation order: bit-reproducible.
+              float* dst = p.part_out + (size_t)sk * p.part_stride + (row0 + sub) * (size_t)p.ld_f32 + c0 + 4 * c4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 t = lds_v4(((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024);
-              t.x = fmaf(t.x, g4.x, b4.x); t.y = fmaf(t.y, g4.y, b4.y);
-              t.z = fmaf(t.z, g4.z, b4.z); t.w = fmaf(t.w, g4.w, b4.w);
-              if (all_rows || sub + 4 * i < rows_left) atomicAdd(reinterpret_cast<float4*>(dst), t);  // RED.ADD.F32x4
-              dst += step;
+              for (int i = 0; i < 8; ++i) {
+                float4 t = lds_v4(((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024);
+                t.x = fmaf(t.x, g4.x, b4.x); t.y = fmaf(t.y, g4.y, b4.y);
+                t.z = fmaf(t.z, g4.z, b4.z); t.w = fmaf(t.w, g4.w, b4.w);
+                if (all_rows || sub + 4 * i < rows_left) *reinterpret_cast<float4*>(dst) = t;
+                dst += step;
+              }
+            } else {
+              float* dst = p.out_f32 + (row0 + sub) * (size_t)p.ld_f32 + c0 + 4 * c4;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 t = lds_v4(((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024);
+                t.x = fmaf(t.x, g4.x, b4.x); t.y = fmaf(t.y, g4.y, b4.y);
+                t.z = fmaf(t.z, g4.z, b4.z); t.w = fmaf(t.w, g4.w, b4.w);
+                if (all_rows || sub + 4 * i < rows_left) atomicAdd(reinterpret_cast<float4*>(dst), t);  // RED.ADD.F32x4
+                dst += step;
+              }
             }
             __syncwarp();  // the patch is rewritten by the next chunk
           }

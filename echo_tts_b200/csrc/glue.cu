@@ -106,7 +106,9 @@ template <int NV>
 __global__ void __launch_bounds__(256) rmsnorm_affine_warp_kernel(const float* __restrict__ X, bf16* __restrict__ out,
                                                                   const float* __restrict__ a,
                                                                   const float* __restrict__ c0, int rows,
-                                                                  int rows_per_group, int64_t group_ld, float eps) {
+                                                                  int rows_per_group, int64_t group_ld, float eps,
+                                                                  const float* __restrict__ parts, int nparts,
+                                                                  int64_t part_stride) {
   constexpr int W = 128 * NV;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -138,6 +140,21 @@ __global__ void __launch_bounds__(256) rmsnorm_affine_warp_kernel(const float* _
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  if (nparts > 0) {
+    // the split-K planes of the wo / w2 GEMM right before this kernel: added in plane order (bit-reproducible), and the
+    // updated residual row goes back to X
+    for (int k = 0; k < nparts; ++k) {
+      const float4* pr = reinterpret_cast<const float4*>(parts + (size_t)k * part_stride + (size_t)r * W);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {  // (the compiler batches these loads as far as the 255 registers allow)
+        const float4 q = pr[lane + 32 * i];
+        v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+      }
+    }
+    float4* xw = reinterpret_cast<float4*>(const_cast<float*>(X) + (size_t)r * W);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xw[lane + 32 * i] = v[i];
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   ss = warp_sum_f(ss);
@@ -383,13 +400,14 @@ void embed_rows(const int32_t* ids, const bf16* table, float* X, int rows, int E
   count_launch();
 }
 void rmsnorm_affine(const float* X, bf16* out, const float* a, const float* c0, int rows, int W, int rows_per_group,
-                    int64_t group_ld, float eps, cudaStream_t s) {
+                    int64_t group_ld, float eps, cudaStream_t s, const float* parts, int nparts, int64_t part_stride) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   const dim3 grid((rows + 7) / 8), block(256);
   switch (W) {
 #define ECHO_RMS_CASE(NV)                                                                                       \
   case 128 * NV:                                                                                                \
-    launch_k(rmsnorm_affine_warp_kernel<NV>, grid, block, 0, s, 1, X, out, a, c0, rows, rows_per_group, group_ld, eps); \
+    launch_k(rmsnorm_affine_warp_kernel<NV>, grid, block, 0, s, 1, X, out, a, c0, rows, rows_per_group, group_ld, eps, \
+             parts, nparts, part_stride);                                                                           \
     break;
     ECHO_RMS_CASE(2) ECHO_RMS_CASE(4) ECHO_RMS_CASE(8) ECHO_RMS_CASE(10) ECHO_RMS_CASE(16)
 #undef ECHO_RMS_CASE

@@ -13,8 +13,11 @@ void embed_rows(const int32_t* ids, const bf16* table, float* X, int rows, int E
 
 // out[r, c] = x[r, c] * rsqrt(mean_c x^2 + eps) * a[g(r), c] + c0[g(r), c]     (model.py:76-79, 99-104)
 // a / c0 are fp32; g(r) = rows_per_group > 0 ? (r / rows_per_group) * group_ld : 0. c0 may be null.
+// Optional split-K planes (W == 2048 only): x[r, :] += sum_{k < nparts} parts[k * part_stride + r * W + :] is folded in
+// first and written back to X (the residual-stream update the preceding wo / w2 GEMM left in planes, see GemmCall::part_ws).
 void rmsnorm_affine(const float* X, bf16* out, const float* a, const float* c0, int rows, int W, int rows_per_group,
-                    int64_t group_ld, float eps, cudaStream_t s);
+                    int64_t group_ld, float eps, cudaStream_t s, const float* parts = nullptr, int nparts = 0,
+                    int64_t part_stride = 0);
 
 // X[c * rows + r, n] = sum_k x[r, k] W[n, k] + bias[n]   for c < copies          (EchoDiT.in_proj, model.py:586)
 void in_proj(const float* x, const bf16* W, const float* bias, float* X, int rows, int K, int D, int copies,

@@ -112,8 +112,9 @@ int echo_create(echo_handle** out, int device);
 int echo_destroy(echo_handle* h);
 const char* echo_last_error(void);
 int echo_num_launches(echo_handle* h, int64_t* out); /* kernels launched by this handle so far */
-/* Process-wide: 1 = bit-reproducible results (disables the atomic split-K of the residual-accumulate GEMMs, ~4 % slower
- * at batch 1); 0 (default) = fastest. Both settings meet the same tolerances against the reference. */
+/* Process-wide: 1 = bit-reproducible results (the split-K slices of the residual-accumulate GEMMs are summed in a
+ * fixed order instead of with fp32 atomics, ~1 % slower at batch 1); 0 (default) = fastest. ECHO_DETERMINISTIC=1 in the
+ * environment sets it at start-up. Both settings meet the same tolerances against the reference. */
 int echo_set_deterministic(int on);
 
 /* ---- weights: replaces load_state_dict (reference inference.py:14-47, 56-76) ---------------------------- */
