@@ -219,7 +219,7 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
     const bool eligible = p.epi == EPI_GENERIC && p.resid != nullptr && p.resid == p.out_f32 && p.out_bf16 == nullptr &&
                           p.taps == 1 && p.batches == 1 && p.N % 256 == 0;
     // partial planes: no atomics, fixed order -- used in deterministic mode only (in the default mode the atomics are
-    // faster: 181.9 vs 184.5 ms per request, the norm kernel pays four L2 round trips per row for the planes)
+    // faster: 179.7 vs 181.5 ms per request)
     static const int env_planes = [] { const char* e = std::getenv("ECHO_SPLITK_PLANES"); return e ? atoi(e) : -1; }();
     const bool parts_ok = c.part_ws != nullptr && c.parts_used != nullptr &&
                           (env_planes >= 0 ? env_planes != 0 : g_deterministic.load() != 0);

@@ -169,6 +169,85 @@ __global__ void __launch_bounds__(256) rmsnorm_affine_warp_kernel(const float* _
   }
 }
 
+// Variant for folding split-K planes (see GemmCall::part_ws): TWO warps per row, so that a lane holds only half as many
+// values per tensor and can have the row of X AND all (<= 4) planes in flight at once -- one L2 round trip behind the
+// dependency wait, like the plain kernel (with one warp per row the planes came in 4-7 dependent batches and the
+// fold cost more than the atomics it replaced). 4 rows per block of 256 threads; W = 256 * NH.
+template <int NH>
+__global__ void __launch_bounds__(256) rmsnorm_affine_planes_kernel(float* __restrict__ X, bf16* __restrict__ out,
+                                                                    const float* __restrict__ a,
+                                                                    const float* __restrict__ c0, int rows,
+                                                                    int rows_per_group, int64_t group_ld, float eps,
+                                                                    const float* __restrict__ parts, int nparts,
+                                                                    int64_t part_stride) {
+  constexpr int W = 256 * NH;
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * 4 + (warp >> 1);
+  const int hf = warp & 1;  // which half of the row
+  const bool live = r < rows;
+  float4 av[NH], cv[NH];
+  if (live) {
+    const size_t g = (rows_per_group > 0 ? (size_t)(r / rows_per_group) * group_ld : 0) + (size_t)hf * (W / 2);
+    const float4* ap = reinterpret_cast<const float4*>(a + g);
+#pragma unroll
+    for (int i = 0; i < NH; ++i) av[i] = __ldg(ap + lane + 32 * i);
+    if (c0) {
+      const float4* cp = reinterpret_cast<const float4*>(c0 + g);
+#pragma unroll
+      for (int i = 0; i < NH; ++i) cv[i] = __ldg(cp + lane + 32 * i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NH; ++i) cv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+  float4 v[NH];
+  float ss = 0.f;
+  if (live) {
+    const size_t off = (size_t)r * W + (size_t)hf * (W / 2);
+    const float4* xr = reinterpret_cast<const float4*>(X + off);
+    float4 q[4][NH];
+#pragma unroll
+    for (int i = 0; i < NH; ++i) v[i] = xr[lane + 32 * i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nparts) {
+        const float4* pr = reinterpret_cast<const float4*>(parts + (size_t)k * part_stride + off);
+#pragma unroll
+        for (int i = 0; i < NH; ++i) q[k][i] = pr[lane + 32 * i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nparts) {
+#pragma unroll
+        for (int i = 0; i < NH; ++i) { v[i].x += q[k][i].x; v[i].y += q[k][i].y; v[i].z += q[k][i].z; v[i].w += q[k][i].w; }
+      }
+    }
+    float4* xw = reinterpret_cast<float4*>(X + off);
+#pragma unroll
+    for (int i = 0; i < NH; ++i) {
+      xw[lane + 32 * i] = v[i];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    ss = warp_sum_f(ss);
+  }
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  if (!live) return;
+  const float rstd = rsqrtf((red[warp & ~1] + red[warp | 1]) / (float)W + eps);  // fixed order: same value in both warps
+  uint2* op = reinterpret_cast<uint2*>(out + (size_t)r * W + (size_t)hf * (W / 2));
+#pragma unroll
+  for (int i = 0; i < NH; ++i) {
+    float4 o;
+    o.x = fmaf(v[i].x * rstd, av[i].x, cv[i].x); o.y = fmaf(v[i].y * rstd, av[i].y, cv[i].y);
+    o.z = fmaf(v[i].z * rstd, av[i].z, cv[i].z); o.w = fmaf(v[i].w * rstd, av[i].w, cv[i].w);
+    op[lane + 32 * i] = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+  }
+}
+
 // 8 rows per block, 256 threads, K <= 128 (K % 8 == 0)
 __global__ void __launch_bounds__(256) in_proj_kernel(const float* __restrict__ x, const bf16* __restrict__ W,
                                                       const float* __restrict__ bias, float* __restrict__ X, int rows,
@@ -402,6 +481,12 @@ void embed_rows(const int32_t* ids, const bf16* table, float* X, int rows, int E
 void rmsnorm_affine(const float* X, bf16* out, const float* a, const float* c0, int rows, int W, int rows_per_group,
                     int64_t group_ld, float eps, cudaStream_t s, const float* parts, int nparts, int64_t part_stride) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
+  if (nparts > 0 && W == 2048 && nparts <= 4) {
+    launch_k(rmsnorm_affine_planes_kernel<8>, dim3((rows + 3) / 4), dim3(256), 0, s, 1, const_cast<float*>(X), out, a, c0,
+             rows, rows_per_group, group_ld, eps, parts, nparts, part_stride);
+    count_launch();
+    return;
+  }
   const dim3 grid((rows + 7) / 8), block(256);
   switch (W) {
 #define ECHO_RMS_CASE(NV)                                                                                       \
