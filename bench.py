@@ -7,9 +7,16 @@ cfg_scale_text 3.0 / cfg_scale_speaker 8.0 / cfg_min_t 0.5, 40 Euler steps at se
 by the Fish S1-DAC decode of the 640 latents to 1 310 720 samples @ 44.1 kHz = 29.72 s of audio.
 
   value  : audio-s/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e    : same metric through the public Python API with pinned HOST inputs (H2D) and the audio copied back (D2H)
+  e2e    : same metric through the public drop-in call `pipeline.sample_pipeline` (reference inference.py:309-347: host
+           text -> tokens -> H2D, pinned host speaker latents -> H2D, sampler, DAC decode, flattening-point crop on the
+           device) with the cropped audio copied back to pinned host memory (D2H), every step
   N > 1  : every rank is a full replica processing its own requests (no data-path collective): weak scaling
   --impl reference : the reference algorithm (oracle port, fp32 PyTorch on the host cores) on a bounded sample
+  config.extras    : the other BASELINE configs measured in the same run (not part of `value`):
+           N = 1: cfg5 = configs[4] blockwise streaming latency (first audio / total), batch4 = 4 requests per call
+           any N: cfg3 = configs[2], 32 requests sharded 32/N per GPU (4 per sampler call), aggregate audio-s/s
+                  cfg4 = configs[3], one ~3000-char prompt -> ~300-char chunks i % N -> NCCL gather -> host stitch,
+                         job wall-clock latency
 
 Weights are generated on rank 0 and broadcast over NCCL once at start-up (the only collective; none per step).
 """
@@ -188,7 +195,9 @@ def run_reference(args):
             "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample,
+                             "extrapolated": True},
+            "extrapolated": True,
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "estimated_request_seconds": req_s}
     emit(line)
@@ -205,15 +214,13 @@ def load_models(device, rank, world):
     cfg, dcfg = DitConfig.base(), DacConfig.base()
     model, dac = B200EchoDiT(cfg, device), B200DAC(dcfg, device)
 
-    def skip(k):
-        return k.startswith("latent_encoder.") or k.startswith("latent_norm") or ".wk_latent" in k or ".wv_latent" in k
-
+    # the latent_* (blockwise) tensors are loaded too: configs[4] (extras.cfg5) needs them, configs[1] never touches them
     if world == 1:
-        model.load_state_dict(iter_dit_weights(cfg, 1234, include_latent=False))
+        model.load_state_dict(iter_dit_weights(cfg, 1234, include_latent=True))
         dac.load_state_dict(make_dac_weights(dcfg, 4321))
     else:
-        specs = [(k, s) for k, s, _ in dit_param_specs(cfg) if not skip(k)]
-        gen = iter_dit_weights(cfg, 1234, include_latent=False) if rank == 0 else None
+        specs = [(k, s) for k, s, _ in dit_param_specs(cfg)]
+        gen = iter_dit_weights(cfg, 1234, include_latent=True) if rank == 0 else None
 
         def dit_items():
             for k, shape in specs:
@@ -238,6 +245,154 @@ def load_models(device, rank, world):
         dac.load_state_dict(dac_items())
     comps, mean, scale = make_pca_state(dcfg)
     return model, dac, PCAState(comps.to(device), mean.to(device), scale)
+
+
+LONG_PROMPT_SENTENCES = (
+    "The lighthouse keeper counted the ships that passed before dawn, and wrote each name in a ledger bound in green cloth.",
+    "When the fog came in from the north, nobody in the village could tell the harbour wall from the open sea.",
+    "She had promised her brother that the lamp would never go out, not for storms, not for sickness, not for grief.",
+    "Every winter the gulls grew bolder, stealing bread from the windowsill and shrieking at the cat until it fled.",
+    "A letter arrived in spring, stamped in a city she had never seen, asking whether the light was still for sale.",
+)
+
+
+def long_prompt(n_chars=3000):
+    """Deterministic ~3000-character prompt for BASELINE configs[3]."""
+    out, i = [], 0
+    while sum(len(x) + 1 for x in out) < n_chars:
+        out.append(LONG_PROMPT_SENTENCES[i % len(LONG_PROMPT_SENTENCES)])
+        i += 1
+    return " ".join(out)
+
+
+def run_extras(args, model, dac, pca, device, rank, world, barrier):
+    """config.extras: BASELINE configs[2], [3] (any N) and [4], batch 4 (N = 1), each with its own warm-up and timed on
+    the device (CUDA events, max over ranks) or -- for the chunked job latency -- by the wall clock of rank 0 between
+    two barriers. Every rank returns the same dict (rank 0 prints it)."""
+    import functools
+
+    import torch.distributed as dist
+    from echo_tts_b200 import pipeline as P
+    from echo_tts_b200.autoencoder import ae_decode
+    from echo_tts_b200.sampler import sample_blockwise_euler_cfg_independent_guidances as blockwise
+    from echo_tts_b200.sampler import sample_euler_cfg_independent_guidances as sample
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    out = {}
+    ids_h, mask_h = tokens(PROMPT)
+    spk1 = torch.randn(1, 212, 80, generator=torch.Generator().manual_seed(1)).to(device)
+    smask1 = torch.ones(1, 212, dtype=torch.bool, device=device)
+
+    # ---- configs[2]: 32 independent requests, request-sharded 32 / N per GPU, 4 requests per sampler call
+    n_req, per_call = 32, 4
+    mine = list(range(rank, n_req, world))
+    calls = [mine[i:i + per_call] for i in range(0, len(mine), per_call)]
+
+    def run_calls():
+        for c in calls:
+            b = len(c)
+            nz = torch.randn(b, 640, 80, device=device, generator=torch.Generator(device).manual_seed(c[0]))
+            lat = sample(model, spk1.repeat(b, 1, 1), smask1.repeat(b, 1), ids_h.repeat(b, 1).to(device),
+                         mask_h.repeat(b, 1).to(device), 0, sequence_length=640, noise=nz, **KNOBS)
+            ae_decode(dac, pca, lat)
+
+    run_calls()  # warm-up (workspaces grow to the batch-4 sizes)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_calls()
+    e1.record()
+    barrier()
+    ms3 = max_over_ranks(e0.elapsed_time(e1))
+    out["cfg3"] = {"workload": "configs[2]: 32 independent requests (each = configs[1]), sharded 32/N per GPU, 4 per sampler call",
+                   "audio_s_per_s": n_req * AUDIO_SECONDS / (ms3 / 1e3), "job_ms": ms3, "requests": n_req,
+                   "requests_per_gpu": len(mine), "requests_per_call": per_call}
+
+    # ---- configs[3]: one ~3000-char prompt -> ~300-char chunks -> chunk i on rank i % N -> gather -> host stitch
+    text = long_prompt()
+    sample_fn = functools.partial(sample, **KNOBS, sequence_length=640)
+
+    def synth_chunk(chunk, seed):
+        audio, _ = P.sample_pipeline(model, dac, pca, sample_fn, chunk, None, seed, speaker_latent=spk1, speaker_mask=smask1)
+        return audio[0]
+
+    # target_duration 25 s: chunk_text_for_audio caps chunks at 12 chars/s * target (handler.py:114), so ~300-char
+    # chunks (BASELINE configs[3]) need 25 s; the handler's 10 s default would give ~120-char chunks
+    job = functools.partial(P.synthesize, text, synth_chunk, seed=0, max_chars_per_chunk=300, target_duration=25.0)
+    n_chunks = len(P.chunk_text_for_audio(text, 300, 25.0))
+    job()  # warm-up
+    lat_s = []
+    stitched = None
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        stitched = job()
+        dt = time.perf_counter() - t0  # rank 0: includes the gather and the host stitching
+        barrier()
+        lat_s.append(dt)
+    job_s = min(lat_s) if rank == 0 else 0.0
+    if world > 1:
+        t = torch.tensor([job_s], device=device, dtype=torch.float64)
+        dist.broadcast(t, 0)
+        job_s = t.item()
+    audio_s = (stitched.shape[-1] / 44100.0) if stitched is not None else 0.0
+    if world > 1:
+        t = torch.tensor([audio_s], device=device, dtype=torch.float64)
+        dist.broadcast(t, 0)
+        audio_s = t.item()
+    out["cfg4"] = {"workload": f"configs[3]: one {len(text)}-char prompt, chunk_text_for_audio(300, target 25 s) -> {n_chunks} chunks, "
+                               f"chunk i on GPU i % N, NCCL all_gather of the audio, boundary normalisation + crossfade on rank 0's host",
+                   "job_latency_ms": job_s * 1e3, "chunks": n_chunks, "critical_path_chunks": -(-n_chunks // world),
+                   "stitched_audio_seconds": audio_s, "audio_s_per_s": audio_s / job_s if job_s > 0 else None,
+                   "timing": "wall clock on rank 0 between two barriers (min of 2 jobs after 1 warm-up job)"}
+
+    if world == 1:
+        # ---- 4 requests per call (one GPU)
+        def batch4():
+            nz = torch.randn(4, 640, 80, device=device, generator=torch.Generator(device).manual_seed(7))
+            lat = sample(model, spk1.repeat(4, 1, 1), smask1.repeat(4, 1), ids_h.repeat(4, 1).to(device),
+                         mask_h.repeat(4, 1).to(device), 0, sequence_length=640, noise=nz, **KNOBS)
+            return ae_decode(dac, pca, lat)
+
+        batch4()
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(3):
+            batch4()
+        e1.record()
+        torch.cuda.synchronize(device)
+        out["batch4_audio_s_per_s"] = 3 * 4 * AUDIO_SECONDS / (e0.elapsed_time(e1) / 1e3)
+
+        # ---- configs[4]: blockwise 4 x 160, 5-minute speaker reference (1600 KV patches), speaker_kv_scale 1.5 until
+        # t < 0.9, streaming DAC decode; device timeline of when each block's audio is complete
+        spk5 = torch.randn(1, 6400, 80, generator=torch.Generator().manual_seed(1)).to(device)
+        smask5 = torch.ones(1, 6400, dtype=torch.bool, device=device)
+        knobs5 = dict(KNOBS, speaker_kv_scale=1.5, speaker_kv_min_t=0.9, speaker_kv_max_layers=24)
+        ids, mask = ids_h.to(device), mask_h.to(device)
+        runs = []
+        for it in range(4):
+            torch.cuda.synchronize(device)
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            _, parts = P.stream_blockwise_audio(model, dac, pca, blockwise, spk5, smask5, ids, mask, it, [160] * 4, **knobs5)
+            torch.cuda.synchronize(device)
+            runs.append([ev0.elapsed_time(ev) for _, ev in parts])
+        runs = runs[1:]  # the first run sizes the workspaces
+        first = sorted(r[0] for r in runs)[len(runs) // 2]
+        total = sorted(r[-1] for r in runs)[len(runs) // 2]
+        out["cfg5"] = {"workload": "configs[4]: sample_blockwise 4 x 160 latents, 40 steps per block, 6400-latent (5 min) speaker "
+                                   "reference = 1600 speaker-KV patches, speaker_kv_scale 1.5 until t < 0.9, streaming DAC decode",
+                       "first_audio_ms": first, "total_ms": total, "block_ready_ms": runs[-1],
+                       "audio_s_per_s": AUDIO_SECONDS / (total / 1e3),
+                       "timing": "CUDA events on the stream (median of 3 runs after 1 warm-up); first audio includes the "
+                                 "text + 1600-patch speaker KV caches"}
+    return out
 
 
 def run_b200(args):
@@ -304,33 +459,51 @@ def run_b200(args):
     value = world * args.steps * Bq * AUDIO_SECONDS / (ms / 1e3)
     assert torch.isfinite(audio).all() and tuple(audio.shape) == (Bq, 1, 640 * 2048)
 
-    # ---- e2e: pinned host inputs -> H2D, public API, D2H of the audio, every step
-    pin = lambda t: t.pin_memory()
-    h_in = [pin(ids_h), pin(mask_h), pin(spk_h), pin(smask_h)]
-    h_noise = pin(noise_h)
-    h_audio = torch.empty(Bq, 1, 640 * 2048, dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in h_in) + noise_h[0].numel() * 4
-    d2h = h_audio.numel() * 4
+    # ---- e2e: the public drop-in call (pipeline.sample_pipeline == reference inference.sample_pipeline) with HOST inputs:
+    # prompt string -> tokens on the host -> H2D, pinned host speaker latents + mask -> H2D, noise drawn on the device
+    # from the seed exactly as the reference draws it (inference.py:457,477), sampler, DAC decode, flattening-point
+    # crop on the device (one int32 D2H), cropped audio -> pinned host memory (D2H). Every step.
+    import functools
+    from echo_tts_b200 import pipeline as P
+    sample_fn = functools.partial(sample, **KNOBS, sequence_length=640)  # as handler._build_sample_fn (handler.py:426-443)
+    h_spk, h_smask = spk_h[:1].pin_memory(), smask_h[:1].pin_memory()
+    h_audio = torch.empty(1, 1, 640 * 2048, dtype=torch.float32).pin_memory()
+    h2d = h_spk.numel() * 4 + h_smask.numel() + 768 * 4 + 768  # speaker latents fp32 + mask, token ids int32 + mask
+    d2h_box = [0]
 
     def request_e2e(i):
-        d = [t.to(device, non_blocking=True) for t in h_in]
-        nz = h_noise[i].to(device, non_blocking=True)
-        lat = sample(model, d[2], d[3], d[0], d[1], 0, sequence_length=640, noise=nz, **KNOBS)
-        h_audio.copy_(ae_decode(dac, pca, lat), non_blocking=True)
+        audio, _ = P.sample_pipeline(model, dac, pca, sample_fn, PROMPT, None, 1000 * rank + i,
+                                     speaker_latent=h_spk, speaker_mask=h_smask)
+        n = audio.shape[-1]
+        h_audio[..., :n].copy_(audio, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
+        d2h_box[0] = n * 4 + 4  # cropped audio + the flattening index
+        return n
 
-    request_e2e(0)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        request_e2e(args.warmup + i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-    e2e = world * args.steps * Bq * AUDIO_SECONDS / e2e_s
+    e2e = e2e_s = None
+    d2h = 0
+    if Bq == 1:
+        request_e2e(0)
+        barrier()
+        t0 = time.perf_counter()
+        samples = 0
+        for i in range(args.steps):
+            samples += request_e2e(args.warmup + i)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        d2h = d2h_box[0]
+        if world > 1:
+            t = torch.tensor([e2e_s], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = t.item()
+        # audio-seconds = what the call returned AFTER the crop (random-init latents never flatten, so normally all
+        # 1 310 720 samples of every request: then this is the same unit as `value`)
+        e2e = world * (samples / 44100.0) / e2e_s
+
+    # ---- extras: the other BASELINE configs, measured in the same run on the same model (never part of `value`)
+    extras = {}
+    if not args.no_extras and Bq == 1:
+        extras = run_extras(args, model, dac, pca, device, rank, world, barrier)
 
     # ---- roofline: one more request with per-launch CUDA events (same kernels, same stream)
     rep = _lib.ProfileReport()
@@ -361,8 +534,9 @@ def run_b200(args):
         dsd = make_dac_weights(DacConfig.base(), seed=4321)
         prepare, step = oracle_sample_seconds(sd, dsd, make_pca_state(DacConfig.base()), threads)
         prepare()
+        step(6)  # warm-up (thread pool, allocator)
         est, _ = step(7)
-        cpu = {"value": AUDIO_SECONDS / est, "unit": "audio-s/s", "cores": threads, "kind": "port",
+        cpu = {"value": AUDIO_SECONDS / est, "unit": "audio-s/s", "cores": threads, "kind": "port", "extrapolated": True,
                "sample": "one fp32 CFG forward (3 x 640 rows) + one plain forward + KV caches + DAC decode of 16 latents "
                          "with the oracle, extrapolated to a request (20 x each forward + 40 x decode(16))"}
 
@@ -373,10 +547,13 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"replicas x{world} (requests sharded, no collective per step)",
                        "l2": "per step the kernels stream the 2.7 GB of bf16 weights of the 24 DiT blocks (>> 126 MB L2): inputs larger than L2",
-                       "p50_latency_ms": p50_ms, "requests_per_call": Bq,
+                       "p50_latency_ms": p50_ms, "requests_per_call": Bq, "extras": extras,
                        "reproducibility": "default mode uses atomic split-K in the M=640 residual GEMMs (run-to-run "
                                           "differences at the bf16 noise floor); echo_set_deterministic(1) is bit-exact and ~1 % slower"},
-            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": ({"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "api": "echo_tts_b200.pipeline.sample_pipeline (== reference inference.sample_pipeline): host prompt + "
+                            "pinned host speaker latents in, sampler + DAC decode + flattening-point crop on the GPU, "
+                            "cropped audio to pinned host memory"} if e2e is not None else None),
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
@@ -387,10 +564,8 @@ def run_b200(args):
                          "gemm_launches": int(rep.launches[0]), "gemm_ms": rep.ms[0], "gemm_flops": rep.flops[0],
                          "attention_ms": rep.ms[1], "glue_ms": rep.ms[2],
                          "gemm_share_of_step": rep.ms[0] / prof_total if prof_total else None,
-                         # the per-launch events serialise the chain (no PDL overlap) and add ~2 us per launch; the
-                         # same FLOPs over the kernel's SHARE of the un-instrumented step time:
-                         "achieved_in_uninstrumented_step": (rep.flops[0] / (ms / args.steps * 1e-3 * rep.ms[0] / prof_total) / 1e12
-                                                             if prof_total and rep.ms[0] > 0 else None),
+                         "note": "achieved = algorithmic FLOPs / summed per-launch CUDA-event time of every GEMM launch of one "
+                                 "request (events serialise the chain: no PDL overlap, ~2 us per launch included)",
                          "request_algorithmic_tflop": Bq * fl["total"] / 1e12,
                          "request_frac_of_peak": Bq * fl["total"] / (ms / args.steps * 1e-3) / 1e12 / peak_tf},
             "cpu_baseline": cpu,
@@ -422,6 +597,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip config.extras (cfg3 / cfg4 / cfg5 / batch4)")
     ap.add_argument("--batch", type=int, default=1,
                     help="independent requests per sampler call on every GPU (1 = BASELINE configs[1]; > 1 = configs[2] style)")
     args = ap.parse_args()

@@ -118,6 +118,9 @@ SYMBOLS = {
     "echo_kv_latent": (C.c_int, [_P, _P, C.c_int, C.c_int, c_void_pp, c_void_pp, _P]),
     "echo_dit_forward": (C.c_int, [_P, _P, _P, _P, _P, c_void_pp, c_void_pp, C.c_int, c_void_pp, c_void_pp, C.c_int,
                                    c_void_pp, c_void_pp, C.c_int, C.c_int, C.c_int, C.c_int, _P, c_void_pp, _P]),
+    "echo_dit_forward_probe": (C.c_int, [_P, _P, _P, _P, _P, c_void_pp, c_void_pp, C.c_int, c_void_pp, c_void_pp, C.c_int,
+                                         c_void_pp, c_void_pp, C.c_int, C.c_int, C.c_int, C.c_int, _P, c_void_pp, c_void_pp,
+                                         _P]),
     "echo_sample_euler": (C.c_int, [_P, C.POINTER(SamplerArgs), _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "echo_sample_blockwise": (C.c_int, [_P, C.POINTER(SamplerArgs), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int, _P,
                                         _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
@@ -134,6 +137,7 @@ SYMBOLS = {
     "echo_op_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "echo_op_attention": (C.c_int, [C.POINTER(AttnDesc), _P]),
     "echo_op_rmsnorm_affine": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_float, _P]),
+    "echo_op_flattening_point": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, _P, _P]),
     "echo_op_cfg_euler_update": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
                                           C.c_float, C.c_float, _P]),
 }

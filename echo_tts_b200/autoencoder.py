@@ -163,19 +163,20 @@ class B200DAC:
 
 @torch.inference_mode()
 def ae_decode(fish_ae, pca_state: PCAState, z_q: torch.Tensor) -> torch.Tensor:
-    """reference inference.ae_decode (inference.py:226-229). With a B200DAC the PCA un-projection is fused."""
-    if isinstance(fish_ae, B200DAC):
-        return fish_ae.decode_latent(pca_state, z_q)
-    z = (z_q / pca_state.latent_scale) @ pca_state.pca_components + pca_state.pca_mean
-    return fish_ae.decode_zq(z.transpose(1, 2).to(fish_ae.dtype)).float()
+    """reference inference.ae_decode (inference.py:226-229); the PCA un-projection is fused into the decode kernels.
+    `fish_ae` must be a `B200DAC`: there is no second backend behind this API (no eager / CPU path)."""
+    if not isinstance(fish_ae, B200DAC):
+        raise TypeError(f"ae_decode: fish_ae must be a B200DAC (got {type(fish_ae).__name__}); echo_tts_b200 has no "
+                        "eager fallback -- build one with B200DAC.from_state_dict(reference_dac.state_dict())")
+    return fish_ae.decode_latent(pca_state, z_q)
 
 
 @torch.inference_mode()
 def ae_encode(fish_ae, pca_state: PCAState, audio: torch.Tensor) -> torch.Tensor:
-    """reference inference.ae_encode (inference.py:219-224): (B, 1, L) -> (B, T, 80). Fused with a B200DAC."""
+    """reference inference.ae_encode (inference.py:219-224): (B, 1, L) -> (B, T, 80), PCA projection fused.
+    `fish_ae` must be a `B200DAC` (no eager fallback)."""
     assert audio.ndim == 3 and audio.shape[1] == 1  # (b, 1, length)
-    if isinstance(fish_ae, B200DAC):
-        return fish_ae.encode_latent(pca_state, audio)
-    z_q = fish_ae.encode_zq(audio).float()
-    z_q = (z_q.transpose(1, 2) - pca_state.pca_mean) @ pca_state.pca_components.T
-    return z_q * pca_state.latent_scale
+    if not isinstance(fish_ae, B200DAC):
+        raise TypeError(f"ae_encode: fish_ae must be a B200DAC (got {type(fish_ae).__name__}); echo_tts_b200 has no "
+                        "eager fallback")
+    return fish_ae.encode_latent(pca_state, audio)

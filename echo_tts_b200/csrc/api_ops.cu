@@ -101,6 +101,15 @@ extern "C" int echo_op_cfg_euler_update(float* x, const float* v, int64_t n_per_
   return ECHO_OK;
 }
 
+extern "C" int echo_op_flattening_point(const float* latent, int T, int C, float target_value, int window_size,
+                                        float std_threshold, int32_t* out_index, void* stream) {
+  if (!latent || !out_index || T < 0 || C <= 0 || window_size <= 0) { set_error("echo_op_flattening_point: bad argument"); return ECHO_ERR_ARG; }
+  flattening_point(latent, T, C, window_size, target_value, std_threshold, out_index, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("echo_op_flattening_point: %s", cudaGetErrorString(e)); return ECHO_ERR_CUDA; }
+  return ECHO_OK;
+}
+
 extern "C" int echo_set_deterministic(int on) {
   gemm_set_deterministic(on);
   return ECHO_OK;

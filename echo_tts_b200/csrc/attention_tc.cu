@@ -1,8 +1,12 @@
-// Joint attention of the DiT blocks on tcgen05 tensor cores (head_dim 128, non-causal segments).
-//
-// Replaces cat([self, latent, text, speaker]) + bool key mask + F.scaled_dot_product_attention + "* sigmoid(gate)"
-// of the reference (model.py:246-266) for one (128 query rows, head, batch row) per CTA, without materialising the
-// concatenated K/V or the 3x CFG copies of the text/speaker caches.
+// Every attention of the hot path on tcgen05 tensor cores, one kernel template over the head dim (128 or 64):
+//   * joint attention of the DiT blocks: cat([self, latent, text, speaker]) + bool key mask +
+//     F.scaled_dot_product_attention + "* sigmoid(gate)" (model.py:246-266), without materialising the concatenated
+//     K/V or the 3x CFG copies of the text/speaker caches;
+//   * encoder self-attention (model.py:141-154): key mask (text) or causal (speaker / latent encoders);
+//   * the window-limited causal attention of the DAC transformers (autoencoder.py:698-702, 762-773; head_dim 64,
+//     window 128 in post_module / pre_module, 512 in the encoder): the tile list of a CTA only holds the key tiles its
+//     128 query rows can see, the diagonal / window edge tiles are masked per row.
+// One (128 query rows, head, batch row) per CTA.
 //
 // Data path per 64-key tile j (stage = j & 1):
 //   TMA        K_j, V_j  -> smem  (128B-swizzled boxes; rows beyond the tensor are zero-filled)
@@ -16,6 +20,8 @@
 // The MMA thread issues S_{j+1} before it waits for P_j, so the tensor pipe computes the next scores while the
 // softmax warps work; two CTAs are resident per SM (96 KB smem, 256 TMEM columns each), so one CTA's MMAs also
 // overlap the other's softmax.
+//
+// Head dim 64: Q / K / V tiles are one 64-column atom instead of two, S = QK^T takes 4 MMAs (K = 64) and O is 64 TMEM columns.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax,
 // O correction and epilogue (TMEM lane quarter = warp & 3).
@@ -38,12 +44,11 @@ constexpr int TQ = 128;  // query rows per CTA
 constexpr int TK = 64;   // keys per tile
 constexpr int AT_THREADS = 192;
 constexpr int AT_MAX_TILES = 120;
-constexpr int Q_BYTES = TQ * 128 * 2;   // 2 atoms [128 rows][64 d]
-constexpr int KSLOT = TK * 128 * 2;     // K tile: 2 atoms [64 keys][64 d]
-constexpr int VSLOT = TK * 128 * 2;     // V tile: 2 boxes [64 keys][64 d]
-constexpr int STAGE = KSLOT + VSLOT;
-constexpr int TILE_BYTES = Q_BYTES + 2 * STAGE;  // 96 KB
-constexpr int AT_SMEM = TILE_BYTES + 1024 /*align slack*/ + 1024 /*barriers + tile list*/;
+// per head dim D: Q = D/64 atoms [128 rows][64 d]; a K / V tile = D/64 atoms (boxes) [64 keys][64 d]
+__host__ __device__ constexpr int at_q_bytes(int D) { return TQ * D * 2; }
+__host__ __device__ constexpr int at_slot(int D) { return TK * D * 2; }
+__host__ __device__ constexpr int at_tile_bytes(int D) { return at_q_bytes(D) + 4 * at_slot(D); }  // 96 KB (D = 128) / 48 KB
+__host__ __device__ constexpr int at_smem(int D) { return at_tile_bytes(D) + 1024 /*align slack*/ + 1024 /*barriers + tile list*/; }
 constexpr float RESCALE_LOG2 = 8.f;  // O is rescaled only when a row max grows by more than 2^8
 
 struct AttnMaps {
@@ -61,8 +66,13 @@ struct SmemCtl {
 };
 static_assert(sizeof(SmemCtl) <= 1024, "control block");
 
+template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
+  static_assert(D == 128 || D == 64, "head dim");
+  constexpr int NA = D / 64;  // 64-column atoms per row
+  constexpr int Q_BYTES = at_q_bytes(D), KSLOT = at_slot(D), VSLOT = at_slot(D), STAGE = KSLOT + VSLOT;
+  constexpr int TILE_BYTES = at_tile_bytes(D);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -101,7 +111,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   // (Contract: eff_len must not be written by an immediate predecessor that triggers its dependents early.)
   // (segment << 24 | first key) for every 64-key tile that can hold a valid key
   if (warp == 2) {
-    int hi = 0;
+    int hi = 0, lo = 0;
     if (lane < d.nseg) {
       const echo_attn_segment& sg = d.seg[lane];
       hi = sg.len;
@@ -110,10 +120,19 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         const int lim = (sg.pos_limit + sg.pos_limit_mult - 1) / sg.pos_limit_mult;  // keys j with j*mult < pos_limit
         hi = lim < hi ? lim : hi;
       }
+      if (sg.causal) {  // keys this CTA's rows can see: j <= q (and j > q - window), q in [q0, min(q0 + 128, S))
+        const int qe = q0 + TQ < d.S ? q0 + TQ : d.S;
+        hi = qe < hi ? qe : hi;
+        if (sg.window > 0) {
+          lo = q0 - sg.window + 1;
+          lo = lo < 0 ? 0 : (lo & ~(TK - 1));
+        }
+      }
       if (hi < 0) hi = 0;
+      if (lo > hi) lo = hi;
       ctl->seg_hi[lane] = hi;
     }
-    const int nt = (hi + TK - 1) / TK;
+    const int nt = (hi - lo + TK - 1) / TK;
     int off = nt;  // inclusive prefix sum over the (<= 4) segment lanes
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
@@ -122,7 +141,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     }
     const int total = __shfl_sync(0xffffffffu, off, 3);
     off -= nt;
-    for (int i = 0; i < nt && off + i < AT_MAX_TILES; ++i) ctl->tiles[off + i] = (lane << 24) | (i * TK);
+    for (int i = 0; i < nt && off + i < AT_MAX_TILES; ++i) ctl->tiles[off + i] = (lane << 24) | (lo + i * TK);
     if (lane == 0) ctl->ntiles = total < AT_MAX_TILES ? total : AT_MAX_TILES;
   }
   tc_fence_before();
@@ -134,8 +153,8 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   if (trace && threadIdx.x == 64) trace[1] = clock64();
   if (warp == 0 && lane == 0) {  // Q first; the K / V tiles follow from the producer loop below without another barrier
     mbar_expect_tx(&ctl->q_full, Q_BYTES);
-    tma_load_3d(sQ, &maps.q, &ctl->q_full, h * 128, q0, b);
-    tma_load_3d(sQ + Q_BYTES / 2, &maps.q, &ctl->q_full, h * 128 + 64, q0, b);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) tma_load_3d(sQ + a * (Q_BYTES / NA), &maps.q, &ctl->q_full, h * D + a * 64, q0, b);
   }
   const int ntiles = lds_i32(&ctl->ntiles);
   const uint32_t tmem_base = (uint32_t)lds_i32(&ctl->tmem_slot);
@@ -153,13 +172,13 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         if (!is_v) {
           if (u > 0) mbar_wait(&ctl->s_full[st], (u - 1) & 1);  // S_{j-2} has consumed the slot
           mbar_expect_tx(&ctl->k_full[st], KSLOT);
-          tma_load_3d(sK(st), &maps.k[si], &ctl->k_full[st], h * 128, n0, cb);
-          tma_load_3d(sK(st) + KSLOT / 2, &maps.k[si], &ctl->k_full[st], h * 128 + 64, n0, cb);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) tma_load_3d(sK(st) + a * (KSLOT / NA), &maps.k[si], &ctl->k_full[st], h * D + a * 64, n0, cb);
         } else {
           if (u > 0) mbar_wait(&ctl->pv_done[st], (u - 1) & 1);  // PV_{j-2} has consumed the slot
           mbar_expect_tx(&ctl->v_full[st], VSLOT);
-          tma_load_3d(sV(st), &maps.v[si], &ctl->v_full[st], h * 128, n0, cb);
-          tma_load_3d(sV(st) + VSLOT / 2, &maps.v[si], &ctl->v_full[st], h * 128 + 64, n0, cb);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) tma_load_3d(sV(st) + a * (VSLOT / NA), &maps.v[si], &ctl->v_full[st], h * D + a * 64, n0, cb);
         }
       };
       // issue order K0 K1 V0 K2 V1 K3 ...: K_{j+2} only waits for S_j, which completes two tiles before S_{j+2} is issued
@@ -178,10 +197,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     // profiles/r01_attn_tc_timeline.txt); per tile it is now 12 MMAs, 2 commits and 3 barrier waits.
     if (ntiles > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK);
-      constexpr uint32_t idesc_o = make_idesc_bf16(TQ, 128) | kIdescBMajorMN;
+      constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D) | kIdescBMajorMN;
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t t_o = tmem_base + 128;
-      const uint64_t qd0 = make_smem_desc<128>(q_addr), qd1 = make_smem_desc<128>(q_addr + Q_BYTES / 2);
+      const uint64_t qd0 = make_smem_desc<128>(q_addr), qd1 = make_smem_desc<128>(q_addr + Q_BYTES / NA * (NA - 1));
       mbar_wait(&ctl->q_full, 0);
       if (trace && lane == 0) trace[3] = clock64();
       auto issue_s = [&](int j) {
@@ -190,12 +209,14 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         tc_fence_after();
         if (trace && lane == 0 && j < 13) trace[32 + j] = clock64();
         const uint32_t k_addr = smem_u32(sK(st));
-        const uint64_t kd0 = make_smem_desc<128>(k_addr), kd1 = make_smem_desc<128>(k_addr + KSLOT / 2);
+        const uint64_t kd0 = make_smem_desc<128>(k_addr), kd1 = make_smem_desc<128>(k_addr + KSLOT / NA * (NA - 1));
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd0 + 2 * k, kd0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          if constexpr (NA == 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd1 + 2 * k, kd1 + 2 * k, idesc_s, 1u);
+            for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd1 + 2 * k, kd1 + 2 * k, idesc_s, 1u);
+          }
           tc_commit(&ctl->s_full[st]);  // scores ready; also releases K_j's smem slot to the producer
         }
         __syncwarp();
@@ -209,7 +230,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         tc_fence_after();
         if (trace && lane == 0 && j < 13) trace[48 + j] = clock64();
         const uint32_t p_tmem = tmem_base + st * TK;  // bf16 P_j, packed 2 keys per column over S_j's first 32 columns
-        const uint64_t vd = make_smem_desc_mn(smem_u32(sV(st)), VSLOT / 2, 1024);
+        const uint64_t vd = make_smem_desc_mn(smem_u32(sV(st)), VSLOT / NA, 1024);  // LBO = next 64-wide d group (D = 128 only)
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -255,15 +276,33 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       tc_ld_32x32(tmem_base + lane_base + st * TK, v);
       tc_ld_32x32(tmem_base + lane_base + st * TK + 32, v + 32);
       tc_wait_ld();
-      const bool full = (vm_lo & vm_hi) == 0xffffffffu;  // warp-uniform
+      // causal / window segments: rows of this warp's slab see keys j with q - window < j <= q. Tiles entirely below the
+      // diagonal and inside the window of all 32 rows take the row-uniform path; edge tiles are masked per row.
+      int r_lo = 0, r_hi = TK;  // this row's valid key range inside the tile: [r_lo, r_hi)
+      bool per_row = false;     // warp-uniform
+      if (sg.causal) {
+        const int qw0 = q0 + quarter * 32;  // first query row of the slab
+        per_row = (n0 + TK - 1 > qw0) || (sg.window > 0 && n0 < qw0 + 31 - sg.window + 1);
+        const int q = q0 + row;
+        r_hi = q - n0 + 1;
+        if (sg.window > 0) r_lo = q - sg.window + 1 - n0;
+      }
+      const bool full = (vm_lo & vm_hi) == 0xffffffffu && !per_row;  // warp-uniform
       float tmax = -INFINITY;
       if (full) {
 #pragma unroll
         for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, v[i]);
-      } else {
+      } else if (!per_row) {
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
           const bool ok = ((i < 32 ? vm_lo >> i : vm_hi >> (i - 32)) & 1u) != 0;
+          v[i] = ok ? v[i] : -INFINITY;
+          tmax = fmaxf(tmax, v[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const bool ok = ((i < 32 ? vm_lo >> i : vm_hi >> (i - 32)) & 1u) != 0 && i >= r_lo && i < r_hi;
           v[i] = ok ? v[i] : -INFINITY;
           tmax = fmaxf(tmax, v[i]);
         }
@@ -284,7 +323,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
           mbar_wait(&ctl->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < D / 32; ++c) {
             float o[32];
             tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
             tc_wait_ld();
@@ -319,15 +358,19 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     // The 16 gate vectors this lane needs are requested BEFORE waiting for the last PV (4.3 us of exposed L2 round
     // trips otherwise: the loop below was load -> multiply -> store, one row pair at a time).
     const bool have = ntiles > 0;
-    const size_t HD = (size_t)d.H * 128;
-    const int rsel = lane >> 4, ch = lane & 15;
-    const size_t off0 = ((size_t)b * d.S + q0 + quarter * 32 + rsel) * HD + (size_t)h * 128 + ch * 8;
+    constexpr int CPR = D / 8;      // 16-byte chunks per output row (one head)
+    constexpr int RPI = 32 / CPR;   // rows written per warp instruction (2 for D = 128, 4 for D = 64)
+    constexpr int NIT = 32 / RPI;
+    constexpr int ROWB = D * 2;     // bytes of one staged row
+    const size_t HD = (size_t)d.H * D;
+    const int rsel = lane / CPR, ch = lane % CPR;
+    const size_t off0 = ((size_t)b * d.S + q0 + quarter * 32 + rsel) * HD + (size_t)h * D + ch * 8;
     const int rows_ok = d.S - (q0 + quarter * 32);  // rows of this warp's slab inside the sequence
-    uint4 gv[16];
+    uint4 gv[NIT];
     if (d.gate) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (2 * i + rsel < rows_ok) gv[i] = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + off0 + (size_t)(2 * i) * HD);
+      for (int i = 0; i < NIT; ++i)
+        if (RPI * i + rsel < rows_ok) gv[i] = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + off0 + (size_t)(RPI * i) * HD);
     }
     if (have) {
       mbar_wait(&ctl->pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
@@ -335,10 +378,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     }
     if (trace && threadIdx.x == 64) trace[30] = clock64();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    const uint32_t stg = smem_u32(smem + Q_BYTES + (warp - 2) * 8192);  // 32 rows x 256 B, private to this warp; all tiles are dead
-    const uint32_t srow = stg + lane * 256;
+    const uint32_t stg = smem_u32(smem + Q_BYTES + (warp - 2) * (32 * ROWB));  // 32 staged rows, private to this warp; all tiles are dead
+    const uint32_t srow = stg + lane * ROWB;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < D / 32; ++c) {
       float o[32];
       if (have) {
         tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
@@ -357,10 +400,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int r = 2 * i + rsel;
+    for (int i = 0; i < NIT; ++i) {
+      const int r = RPI * i + rsel;
       if (r < rows_ok) {
-        uint4 val = lds_u4(stg + r * 256 + ((ch ^ (r & 7)) << 4));
+        uint4 val = lds_u4(stg + r * ROWB + ((ch ^ (r & 7)) << 4));
         if (d.gate) {
           const uint32_t* vi = reinterpret_cast<const uint32_t*>(&val);
           const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gv[i]);
@@ -372,7 +415,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
           }
           val = make_uint4(rr[0], rr[1], rr[2], rr[3]);
         }
-        *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off0 + (size_t)(2 * i) * HD) = val;
+        *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off0 + (size_t)(RPI * i) * HD) = val;
       }
     }
   }
@@ -385,31 +428,37 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
 
 }  // namespace
 
-bool attention_tc_supported(const echo_attn_desc& d) {
-  if (d.D != 128 || d.nseg < 1 || d.nseg > 4) return false;
-  if ((reinterpret_cast<uintptr_t>(d.Q) & 15) || (d.q_row_stride % 8) || (d.q_batch_stride % 8)) return false;
+// Worst-case number of 64-key tiles one CTA walks, or -1 when the descriptor cannot run on this kernel.
+static int attention_tile_bound(const echo_attn_desc& d) {
+  if ((d.D != 128 && d.D != 64) || d.nseg < 1 || d.nseg > 4) return -1;
+  if ((reinterpret_cast<uintptr_t>(d.Q) & 15) || (d.q_row_stride % 8) || (d.q_batch_stride % 8)) return -1;
   int tiles = 0;
   for (int i = 0; i < d.nseg; ++i) {
     const echo_attn_segment& g = d.seg[i];
-    if (g.causal || g.len <= 0) return false;
+    if (g.len <= 0 || g.len > (1 << 24) - 1) return -1;
     if ((reinterpret_cast<uintptr_t>(g.K) & 15) || (reinterpret_cast<uintptr_t>(g.V) & 15) || (g.row_stride % 8) ||
         (g.batch_stride % 8))
-      return false;
-    tiles += (g.len + TK - 1) / TK;
+      return -1;
+    int keys = g.len;
+    if (g.causal) {
+      keys = keys < d.S ? keys : d.S;
+      if (g.window > 0 && g.window + TQ + TK < keys) keys = g.window + TQ + TK;  // window + the CTA's rows + alignment
+    }
+    tiles += (keys + TK - 1) / TK;
   }
-  return tiles <= AT_MAX_TILES;
+  return tiles;
 }
 
-cudaError_t attention_tc_launch(const echo_attn_desc& d, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+template <int D>
+static cudaError_t attention_tc_launch_d(const echo_attn_desc& d, cudaStream_t s) {
+  static std::atomic<uint64_t> configured{0};  // per device, see ensure_dyn_smem
+  {
+    cudaError_t e = ensure_dyn_smem(configured, attn_tc_kernel<D>, at_smem(D));
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   AttnMaps maps;
   std::memset(&maps, 0, sizeof(maps));
-  const uint64_t W = (uint64_t)d.H * 128;
+  const uint64_t W = (uint64_t)d.H * D;
   const uint64_t qbs = d.b > 1 ? (uint64_t)d.q_batch_stride : (uint64_t)d.S * d.q_row_stride;
   if (!tma_map_bf16(&maps.q, d.Q, 3, W, (uint64_t)d.S, (uint64_t)d.b, (uint64_t)d.q_row_stride * 2, qbs * 2, 64, TQ, 128))
     return cudaErrorInvalidValue;
@@ -426,15 +475,27 @@ cudaError_t attention_tc_launch(const echo_attn_desc& d, cudaStream_t s) {
   cudaError_t err;
   {
     char tag[64];
-    if (prof_enabled()) snprintf(tag, sizeof(tag), "attn_tc D=128 b=%d S=%d H=%d nseg=%d", d.b, d.S, d.H, d.nseg);
+    if (prof_enabled()) snprintf(tag, sizeof(tag), "attn_tc D=%d b=%d S=%d H=%d nseg=%d", D, d.b, d.S, d.H, d.nseg);
     else tag[0] = 0;
-    double keys = 0;
-    for (int i = 0; i < d.nseg; ++i) keys += d.seg[i].len;
-    ProfScope ps(PROF_ATTN, 4.0 * d.b * d.H * (double)d.S * keys * 128.0, 0.0, s, tag);
-    err = launch_k(attn_tc_kernel, grid, dim3(AT_THREADS), (size_t)AT_SMEM, s, 1, maps, d);
+    double keys = 0;  // keys a query can see (upper bound for masked segments)
+    for (int i = 0; i < d.nseg; ++i) {
+      const echo_attn_segment& g = d.seg[i];
+      keys += g.causal ? (g.window > 0 && g.window < d.S ? (double)g.window : 0.5 * d.S) : (double)g.len;
+    }
+    ProfScope ps(PROF_ATTN, 4.0 * d.b * d.H * (double)d.S * keys * D, 0.0, s, tag);
+    err = launch_k(attn_tc_kernel<D>, grid, dim3(AT_THREADS), (size_t)at_smem(D), s, 1, maps, d);
   }
   count_launch();
   return err;
+}
+
+// The one attention entry of the library. A descriptor whose worst-case tile list does not fit the kernel's control
+// block (more than AT_MAX_TILES * 64 = 7680 visible keys per query tile) is rejected, never truncated.
+cudaError_t attention_launch(const echo_attn_desc& d, cudaStream_t s) {
+  if (d.b <= 0 || d.S <= 0 || d.H <= 0) return cudaErrorInvalidValue;
+  const int tiles = attention_tile_bound(d);
+  if (tiles < 0 || tiles > AT_MAX_TILES) return cudaErrorInvalidValue;
+  return d.D == 128 ? attention_tc_launch_d<128>(d, s) : attention_tc_launch_d<64>(d, s);
 }
 
 }  // namespace echo

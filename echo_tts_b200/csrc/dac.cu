@@ -1063,6 +1063,7 @@ extern "C" int echo_dac_decode(echo_handle* h, const float* z, const float* pca_
   ECHO_TRY(dac_check(h, "echo_dac_decode"));
   if (!z || !pca_components || !pca_mean || !audio || B <= 0 || T <= 0) { set_error("echo_dac_decode: bad argument"); return ECHO_ERR_ARG; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
   const int C = h->dcfg.latent_dim, Kp = h->dcfg.pca_dim;
   float* X = (float*)h->wsget("dac.X", (size_t)B * T * C * 4, s);
   if (!X) { set_error("dac: out of memory"); return ECHO_ERR_CUDA; }
@@ -1075,6 +1076,7 @@ extern "C" int echo_dac_decode_zq(echo_handle* h, const float* zq, int B, int T,
   ECHO_TRY(dac_check(h, "echo_dac_decode_zq"));
   if (!zq || !audio || B <= 0 || T <= 0) { set_error("echo_dac_decode_zq: bad argument"); return ECHO_ERR_ARG; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
   const int C = h->dcfg.latent_dim;
   float* X = (float*)h->wsget("dac.X", (size_t)B * T * C * 4, s);
   if (!X) { set_error("dac: out of memory"); return ECHO_ERR_CUDA; }
@@ -1259,6 +1261,7 @@ extern "C" int echo_dac_encode_zq(echo_handle* h, const float* audio, int B, int
   ECHO_TRY(dac_enc_check(h, "echo_dac_encode_zq"));
   if (!audio || !zq || B <= 0) { set_error("echo_dac_encode_zq: bad argument"); return ECHO_ERR_ARG; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
   const int C = h->dcfg.latent_dim;
   int hop = 1;
   for (int i = 0; i < h->dcfg.num_enc_rates; ++i) hop *= h->dcfg.enc_rates[i];
@@ -1281,6 +1284,7 @@ extern "C" int echo_dac_encode(echo_handle* h, const float* audio, const float* 
   ECHO_TRY(dac_enc_check(h, "echo_dac_encode"));
   if (!audio || !pca_components || !pca_mean || !latent || B <= 0) { set_error("echo_dac_encode: bad argument"); return ECHO_ERR_ARG; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
   const int C = h->dcfg.latent_dim, Kp = h->dcfg.pca_dim;
   int hop = 1;
   for (int i = 0; i < h->dcfg.num_enc_rates; ++i) hop *= h->dcfg.enc_rates[i];

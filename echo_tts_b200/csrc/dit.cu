@@ -1,5 +1,5 @@
 // EchoDiT on B200: weight packing, the three KV-cache builders, forward, and both Euler/CFG samplers.
-// Orchestration only -- the math lives in gemm_tc.cuh (tcgen05 GEMM + fused epilogues), attention.cu and glue.cu.
+// Orchestration only -- the math lives in gemm_tc.cuh (tcgen05 GEMM + fused epilogues), attention_tc.cu and glue.cu.
 //
 // Differences from the reference's execution (not from its math):
 //   * wq|wk|wv|gate and w1|w3 are fused GEMMs; RMSNorm(q,k) + RoPE + sigmoid(gate) run in the GEMM epilogue.
@@ -72,6 +72,7 @@ extern "C" int echo_destroy(echo_handle* h) {
   for (void* p : h->owned) cudaFree(p);
   for (auto& kv : h->ws) if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->dac_raw) if (kv.second.p) cudaFree(kv.second.p);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
   delete h;
   return ECHO_OK;
 }
@@ -482,6 +483,7 @@ int kv_text_impl(echo_handle* h, const int32_t* ids, const uint8_t* mask, int B,
                  cudaStream_t s) {
   const EncoderW& e = h->enc[0];
   const int rows = B * Lt;
+  if (Lt > h->rope_positions) { set_error("text length %d exceeds the RoPE table (%d positions)", Lt, h->rope_positions); return ECHO_ERR_ARG; }
   Scratch sc;
   ECHO_TRY(get_scratch(h, "enc", rows, e.E, e.inter, &sc, s));
   int32_t* eff = nullptr;
@@ -501,6 +503,10 @@ int kv_patch_impl(echo_handle* h, int which, const bf16* latent, int B, int L, v
   const int ps = h->cfg.speaker_patch_size;
   if (L % ps != 0 || L <= 0) { set_error("latent length %d must be a positive multiple of %d", L, ps); return ECHO_ERR_ARG; }
   const int P = L / ps, rows = B * P, kin = h->cfg.latent_size * ps;
+  // encoder RoPE positions run to P, the latent-prefix keys of the DiT are rotated at ps * patch index (model.py:286-290)
+  if (P * (which == 2 ? ps : 1) > h->rope_positions) {
+    set_error("latent length %d exceeds the RoPE table (%d positions)", L, h->rope_positions); return ECHO_ERR_ARG;
+  }
   Scratch sc;
   ECHO_TRY(get_scratch(h, "enc", rows, e.E, e.inter, &sc, s));
   {  // x = (in_proj(patches) + b) / 6   (model.py:459-462)
@@ -608,7 +614,8 @@ struct FwdCtx {
   int mod_j = 0;               // row of the table used when all rows share one t
   int rows_per_group = 0;      // S when every row-batch has its own t (table row = row-batch), else 0
   KvSide text, spk, lat;
-  void* const* layer_out = nullptr;
+  void* const* layer_out = nullptr;  // parity probes: the stream after each block ...
+  void* const* layer_mid = nullptr;  // ... and after each block's attention branch (before mlp_adaln, model.py:388)
 };
 
 const float* mod_ptr(const echo_handle* h, const FwdCtx& f, int part, int q) {
@@ -627,7 +634,7 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
   // kernel that follows folds them into X -- no fp32 atomics. Not in the per-layer capture mode of the tests (X must
   // be final right after w2 there) and not when the gate groups force one launch per batch row.
   const int nv = D / 128;
-  const bool planes_ok = f.layer_out == nullptr && D % 128 == 0 && (nv == 2 || nv == 4 || nv == 8 || nv == 10 || nv == 16) &&
+  const bool planes_ok = f.layer_out == nullptr && f.layer_mid == nullptr && D % 128 == 0 && (nv == 2 || nv == 4 || nv == 8 || nv == 10 || nv == 16) &&
                          !(f.rows_per_group > 0 && f.rows_per_group % 32 != 0) && rows <= 1280;
   float* part = planes_ok ? (float*)h->wsget("dit.part", (size_t)4 * rows * D * 4, s) : nullptr;
   const int64_t part_stride = (int64_t)rows * D;
@@ -686,6 +693,8 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
       if (er != cudaSuccess) { set_error("joint attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
     }
     ECHO_TRY(gated_accum(sc.AO, D, w.wo, D, D, mod_ptr(h, f, 2, 2 * i)));
+    if (f.layer_mid && f.layer_mid[i])
+      ECHO_CUDA(cudaMemcpyAsync(f.layer_mid[i], sc.X, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, s));
     norm(mod_ptr(h, f, 1, 2 * i + 1), mod_ptr(h, f, 0, 2 * i + 1), f.rows_per_group, D);
     {
       GemmCall g = plain_gemm(sc.XN, D, w.w13, D, rows, 2 * I, D);
@@ -715,6 +724,7 @@ extern "C" int echo_kv_text(echo_handle* h, const int32_t* ids, const uint8_t* m
                             void* const* V, void* stream) {
   ECHO_TRY(check_ready(h, "echo_kv_text"));
   if (!ids || B <= 0 || Lt <= 0 || !K || !V) { set_error("echo_kv_text: bad argument"); return ECHO_ERR_ARG; }
+  HandleScope scope(h, static_cast<cudaStream_t>(stream));
   return kv_text_impl(h, ids, mask, B, Lt, K, V, static_cast<cudaStream_t>(stream));
 }
 
@@ -722,6 +732,7 @@ extern "C" int echo_kv_speaker(echo_handle* h, const void* latent, int B, int Ls
                                void* stream) {
   ECHO_TRY(check_ready(h, "echo_kv_speaker"));
   if (!latent || B <= 0 || !K || !V) { set_error("echo_kv_speaker: bad argument"); return ECHO_ERR_ARG; }
+  HandleScope scope(h, static_cast<cudaStream_t>(stream));
   return kv_patch_impl(h, 1, static_cast<const bf16*>(latent), B, Ls, K, V, static_cast<cudaStream_t>(stream));
 }
 
@@ -730,6 +741,7 @@ extern "C" int echo_kv_latent(echo_handle* h, const void* prefix, int B, int Lp,
   ECHO_TRY(check_ready(h, "echo_kv_latent"));
   if (!h->has_latent) { set_error("echo_kv_latent: latent_* weights were not loaded (delete_blockwise_modules)"); return ECHO_ERR_STATE; }
   if (!prefix || B <= 0 || !K || !V) { set_error("echo_kv_latent: bad argument"); return ECHO_ERR_ARG; }
+  HandleScope scope(h, static_cast<cudaStream_t>(stream));
   return kv_patch_impl(h, 2, static_cast<const bf16*>(prefix), B, Lp, K, V, static_cast<cudaStream_t>(stream));
 }
 
@@ -738,8 +750,18 @@ extern "C" int echo_dit_forward(echo_handle* h, const float* x, const float* t, 
                                 const uint8_t* speaker_mask, void* const* Kt, void* const* Vt, int Lt, void* const* Ks,
                                 void* const* Vs, int Ls, void* const* Kl, void* const* Vl, int Pl, int start_pos, int b,
                                 int S, float* out, void* const* layer_out, void* stream) {
+  return echo_dit_forward_probe(h, x, t, text_mask, speaker_mask, Kt, Vt, Lt, Ks, Vs, Ls, Kl, Vl, Pl, start_pos, b, S, out,
+                                layer_out, nullptr, stream);
+}
+
+extern "C" int echo_dit_forward_probe(echo_handle* h, const float* x, const float* t, const uint8_t* text_mask,
+                                      const uint8_t* speaker_mask, void* const* Kt, void* const* Vt, int Lt,
+                                      void* const* Ks, void* const* Vs, int Ls, void* const* Kl, void* const* Vl, int Pl,
+                                      int start_pos, int b, int S, float* out, void* const* layer_out,
+                                      void* const* layer_mid, void* stream) {
   ECHO_TRY(check_ready(h, "echo_dit_forward"));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
   const echo_dit_config& c = h->cfg;
   if (!x || !t || !text_mask || !speaker_mask || !Kt || !Vt || !Ks || !Vs || !out || b <= 0 || S <= 0 || Lt <= 0 || Ls <= 0) {
     set_error("echo_dit_forward: bad argument"); return ECHO_ERR_ARG;
@@ -765,6 +787,7 @@ extern "C" int echo_dit_forward(echo_handle* h, const float* x, const float* t, 
   f.spk.mask_stride = c.speaker_patch_size; f.spk.eff = eff + b;
   if (Kl && Vl && Pl > 0) { f.lat.K = Kl; f.lat.V = Vl; f.lat.len = Pl; }
   f.layer_out = layer_out;
+  f.layer_mid = layer_mid;
   return run_dit_layers(h, f, sc, out, s);
 }
 
@@ -866,7 +889,8 @@ int sampler_prepare(echo_handle* h, const echo_sampler_args* a, const void* spea
 
 void scale_speaker_cache(echo_handle* h, const echo_sampler_args* a, SamplerState* st, float factor, cudaStream_t s) {
   const int L = h->cfg.num_layers;
-  const int n = (a->speaker_kv_max_layers > 0 && a->speaker_kv_max_layers < L) ? a->speaker_kv_max_layers : L;
+  // inference.py:408-414: None -> every layer (here: a negative value), else min(max_layers, num_layers) -- 0 scales none
+  const int n = a->speaker_kv_max_layers < 0 ? L : (a->speaker_kv_max_layers < L ? a->speaker_kv_max_layers : L);
   const int64_t numel = (int64_t)st->B * st->Ps * h->cfg.model_size;
   for (int i = 0; i < n; ++i) {
     scale_bf16((bf16*)st->ks.K[i], numel, factor, s);
@@ -927,6 +951,7 @@ extern "C" int echo_sample_euler(echo_handle* h, const echo_sampler_args* a, con
     set_error("echo_sample_euler: null argument"); return ECHO_ERR_ARG;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
   const int S = a->sequence_length > 0 ? a->sequence_length : 640;
   if (S > h->rope_positions) { set_error("sequence_length too large"); return ECHO_ERR_ARG; }
   SamplerState st;
@@ -957,6 +982,7 @@ extern "C" int echo_sample_blockwise_stream(echo_handle* h, const echo_sampler_a
     set_error("echo_sample_blockwise: null argument"); return ECHO_ERR_ARG;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
   const echo_dit_config& c = h->cfg;
   const int C = c.latent_size;
   int total = Lc > 0 ? Lc : 0;
@@ -1008,6 +1034,7 @@ extern "C" int echo_sample_euler_host(echo_handle* h, const echo_sampler_args* a
     set_error("echo_sample_euler_host: null argument"); return ECHO_ERR_ARG;
   }
   cudaStream_t s = 0;
+  HandleScope scope(h, s);
   const int C = h->cfg.latent_size;
   const int S = a->sequence_length > 0 ? a->sequence_length : 640;
   const size_t n_spk = (size_t)B * Ls * C, n_x = (size_t)B * S * C;

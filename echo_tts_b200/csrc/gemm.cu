@@ -94,26 +94,28 @@ static std::atomic<int> g_deterministic{[] { const char* e = std::getenv("ECHO_D
 void gemm_set_deterministic(int on) { g_deterministic.store(on ? 1 : 0); }
 int gemm_get_deterministic() { return g_deterministic.load(); }
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device, cached per device (one process may drive several GPUs)
 int gemm_num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
-  return g_num_sms;
+  return n;
 }
 
 template <int BN, int BK, int ATOMS, int EPI, int CG>
 static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
-  static bool configured = false;
+  static std::atomic<uint64_t> configured{0};  // per device, see ensure_dyn_smem
   constexpr int SMEM = gemm_smem_bytes(BN, BK, ATOMS, CG, EPI);
   auto kern = gemm_tc_kernel<BN, BK, ATOMS, EPI, CG>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {
+    cudaError_t e = ensure_dyn_smem(configured, kern, SMEM);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * p.batches * ((p.N + BN - 1) / BN) *
                     (p.split_k > 1 ? p.split_k : 1);

@@ -541,6 +541,55 @@ void scale_bf16(bf16* p, int64_t n, float sc, cudaStream_t s) {
   launch_k(scale_bf16_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, p, n, sc);
   count_launch();
 }
+// ---- find_flattening_point (inference.py:288-296): first i whose `window` rows i .. i+window-1 of the zero-padded
+// (T + window, C) latent are flat: unbiased std over all window*C elements < thr and |mean - target| < 0.1.
+// One warp per window; sums in fp64 (the decision is a threshold test: it must not depend on summation order), then
+// rounded to fp32 before the comparisons exactly as torch compares its fp32 0-dim results with the Python scalars.
+__global__ void flat_init_kernel(int32_t* out, int T) {
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) *out = T;
+}
+__global__ void flat_scan_kernel(const float* __restrict__ x, int T, int C, int window, float target, float thr,
+                                 int32_t* out) {
+  pdl_wait();
+  pdl_trigger();
+  const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= T) return;
+  const int r_hi = w + window < T ? w + window : T;  // rows >= T are the zero padding
+  const int64_t n_valid = (int64_t)(r_hi - w) * C;
+  const float* p = x + (int64_t)w * C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t i = lane; i < n_valid; i += 32) {
+    const double v = (double)p[i];
+    s1 += v;
+    s2 += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    const double n = (double)window * (double)C;
+    const double mean = s1 / n;
+    double var = n > 1.0 ? (s2 - s1 * mean) / (n - 1.0) : 0.0;
+    if (var < 0.0) var = 0.0;
+    const float sd = (float)sqrt(var), m = (float)mean;
+    if (sd < thr && fabsf(m - target) < 0.1f) atomicMin(out, w);
+  }
+}
+void flattening_point(const float* latent, int T, int C, int window, float target, float std_threshold, int32_t* out,
+                      cudaStream_t s) {
+  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
+  launch_k(flat_init_kernel, dim3(1), dim3(32), 0, s, 1, out, T);
+  count_launch();
+  if (T > 0) {
+    launch_k(flat_scan_kernel, dim3((T + 7) / 8), dim3(256), 0, s, 1, latent, T, C, window, target, std_threshold, out);
+    count_launch();
+  }
+}
+
 void scale_copy_f32(const float* src, float* dst, int64_t n, float sc, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   launch_k(scale_copy_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, src, dst, n, sc);

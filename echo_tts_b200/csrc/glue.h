@@ -51,6 +51,11 @@ void mask_eff_len(const uint8_t* mask, int32_t* eff, int n, int len, int ld, int
 void pack_rows(const void* src, int src_is_bf16, void* dst, int dst_is_bf16, int64_t rows, int64_t cols, int64_t dst_ld,
                int64_t blk, int64_t blk_stride, int64_t blk_off, cudaStream_t s);
 
+// *out = first i in [0, T) whose window of `window` rows (zero padded past T) of latent (T, C) fp32 is flat, else T
+// (find_flattening_point, inference.py:288-296)
+void flattening_point(const float* latent, int T, int C, int window, float target, float std_threshold, int32_t* out,
+                      cudaStream_t s);
+
 int64_t glue_launch_count();
 
 }  // namespace echo

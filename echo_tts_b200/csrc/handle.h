@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -147,11 +148,46 @@ struct echo_handle {
   float* pre_final_norm = nullptr;
   std::vector<echo::DacVqW> vq;  // [0] semantic, [1 ..] residual
 
+  // ---- serialisation of the public entry points (see echo::HandleScope)
+  std::recursive_mutex mu;
+  int depth = 0;
+  bool used = false;
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t order_ev = nullptr;
+
   void* wsget(const char* name, size_t bytes, cudaStream_t s);
   void* dalloc(size_t bytes);
 };
 
 namespace echo {
+// Every compute entry point of the C ABI opens one of these. The named workspace buffers (activations, KV scratch,
+// AdaLN tables) are shared by all calls on a handle, so (1) host threads are serialised by a per-handle mutex and
+// (2) when a call arrives on a different stream than the previous one, the new stream first waits for everything the
+// handle enqueued on the old stream (one event, no host synchronisation). Calls on ONE stream -- the normal case --
+// pay a mutex lock and a pointer compare. Contract for callers: a stream handed to the library must stay alive until
+// the next call on the same handle has been issued.
+struct HandleScope {
+  echo_handle* h;
+  HandleScope(echo_handle* hh, cudaStream_t s) : h(hh) {
+    h->mu.lock();
+    if (h->depth++ == 0) {
+      if (h->used && h->last_stream != s) {
+        if (!h->order_ev) cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming);
+        if (h->order_ev && cudaEventRecord(h->order_ev, h->last_stream) == cudaSuccess) cudaStreamWaitEvent(s, h->order_ev, 0);
+        else cudaGetLastError();  // the old stream is gone: everything on it has completed or was abandoned
+      }
+      h->last_stream = s;
+      h->used = true;
+    }
+  }
+  ~HandleScope() {
+    --h->depth;
+    h->mu.unlock();
+  }
+  HandleScope(const HandleScope&) = delete;
+  HandleScope& operator=(const HandleScope&) = delete;
+};
+
 // dac.cu
 int dac_set_weight(echo_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype,
                    cudaStream_t s);

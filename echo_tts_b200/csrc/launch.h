@@ -12,6 +12,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <cstdint>
 #include <cstdlib>
 #include <utility>
 
@@ -51,6 +53,22 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cfg.attrs = at;
   cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE (context) property of a kernel: a process that drives
+// several GPUs (a threaded server instead of one process per GPU) must set it once on every device it launches on.
+// `done` is a bit mask indexed by the current device; racing threads may both set the attribute, which is harmless.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(std::atomic<uint64_t>& done, K kern, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  done.fetch_or(bit, std::memory_order_release);
+  return cudaSuccess;
 }
 
 #ifdef __CUDACC__

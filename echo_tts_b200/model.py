@@ -160,7 +160,10 @@ class B200EchoDiT:
     @torch.inference_mode()
     def forward(self, x: torch.Tensor, t: torch.Tensor, text_mask: torch.Tensor, speaker_mask: torch.Tensor,
                 kv_cache_text: KVCache, kv_cache_speaker: KVCache, start_pos: Optional[int] = None,
-                kv_cache_latent: Optional[KVCache] = None, layer_outputs: Optional[list] = None) -> torch.Tensor:
+                kv_cache_latent: Optional[KVCache] = None, layer_outputs: Optional[list] = None,
+                layer_mids: Optional[list] = None) -> torch.Tensor:
+        """`layer_outputs` / `layer_mids` (optional lists, parity probes): receive the fp32 stream after every block /
+        after every block's attention branch (model.py:388-389)."""
         dev = self.device
         xf = x.to(dev, torch.float32).contiguous()
         b, S, _ = xf.shape
@@ -183,12 +186,18 @@ class B200EchoDiT:
                     for _ in range(self.cfg.num_layers)]
             layer_outputs.extend(bufs)
             lo = _ptr_array(bufs)
+        lm = None
+        if layer_mids is not None:
+            mids = [torch.empty(b, S, self.cfg.model_size, device=dev, dtype=torch.float32)
+                    for _ in range(self.cfg.num_layers)]
+            layer_mids.extend(mids)
+            lm = _ptr_array(mids)
         with torch.cuda.device(dev):
-            _lib.check(self.lib.echo_dit_forward(
+            _lib.check(self.lib.echo_dit_forward_probe(
                 self.h.ptr, xf.data_ptr(), tf.data_ptr(), tm.data_ptr(), sm.data_ptr(),
                 _ptr_array([k for k, _ in kv_cache_text]), _ptr_array([v for _, v in kv_cache_text]), Lt,
                 _ptr_array([k for k, _ in kv_cache_speaker]), _ptr_array([v for _, v in kv_cache_speaker]), Ls,
-                kl, vl, Pl, int(start_pos or 0), b, S, out.data_ptr(), lo, _stream(dev)), "echo_dit_forward")
+                kl, vl, Pl, int(start_pos or 0), b, S, out.data_ptr(), lo, lm, _stream(dev)), "echo_dit_forward")
         return out
 
     __call__ = forward

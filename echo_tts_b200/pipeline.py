@@ -217,11 +217,24 @@ class VoiceCache:
 def find_flattening_point(data: torch.Tensor, target_value: float = 0.0, window_size: int = 20,
                           std_threshold: float = 0.05) -> int:
     """First index whose `window_size`-latent window (zero padded past the end) is flat: std < std_threshold and
-    |mean - target| < 0.1. All windows are evaluated in one vectorised pass and the result leaves the device once
-    (the reference syncs the device twice per window)."""
+    |mean - target| < 0.1 (reference inference.py:288-296; the reference loops over the windows with two device syncs
+    each). Latents on the GPU -- the sampler's output, the product path -- go through one warp-per-window kernel
+    (`echo_op_flattening_point`) and the index leaves the device once. Host tensors (the stitching side of the
+    pipeline works on the host) are evaluated in one vectorised pass."""
     n = data.shape[0]
     if n == 0:
         return 0
+    if data.is_cuda:
+        import ctypes as C
+
+        from . import _lib
+        x = data.reshape(n, -1).to(torch.float32).contiguous()
+        out = torch.empty(1, dtype=torch.int32, device=data.device)
+        with torch.cuda.device(data.device):
+            _lib.check(_lib.load().echo_op_flattening_point(
+                x.data_ptr(), n, x.shape[1], C.c_float(target_value), int(window_size), C.c_float(std_threshold),
+                out.data_ptr(), torch.cuda.current_stream(data.device).cuda_stream), "echo_op_flattening_point")
+        return int(out.item())
     padded = torch.cat([data, data.new_zeros((window_size,) + tuple(data.shape[1:]))])
     win = padded.reshape(padded.shape[0], -1).unfold(0, window_size, 1)[:n]  # (n, features, window)
     win = win.reshape(n, -1).float()
@@ -236,14 +249,17 @@ def crop_audio_to_flattening_point(audio: torch.Tensor, latent: torch.Tensor) ->
 
 @torch.inference_mode()
 def sample_pipeline(model, fish_ae, pca_state, sample_fn: Callable, text_prompt: str,
+                    speaker_audio: Optional[torch.Tensor] = None, rng_seed: int = 0,
+                    pad_to_max_speaker_latent_length: Optional[int] = None,
+                    pad_to_max_text_length: Optional[int] = None, normalize_text: bool = True, *,
                     speaker_latent: Optional[torch.Tensor] = None, speaker_mask: Optional[torch.Tensor] = None,
-                    rng_seed: int = 0, pad_to_max_speaker_latent_length: Optional[int] = None,
-                    pad_to_max_text_length: Optional[int] = None, normalize_text: bool = True,
-                    speaker_audio: Optional[torch.Tensor] = None, voice: Optional[Voice] = None) -> Tuple[torch.Tensor, str]:
-    """One chunk: reference inference.py:309-347. The speaker reference is either raw audio (1, L) @ 44.1 kHz
-    (`speaker_audio`, encoded here like the reference does), already-encoded PCA latents + mask, or a `Voice` from a
-    `VoiceCache` (latents, mask and the speaker KV cache: `sample_fn` must then accept `speaker_kv_cache=`, as the
-    samplers of this package do). Returns (audio (1, 1, n) fp32, normalised text)."""
+                    voice: Optional[Voice] = None) -> Tuple[torch.Tensor, str]:
+    """One chunk: reference inference.py:309-347, same positional order (model, fish_ae, pca_state, sample_fn,
+    text_prompt, speaker_audio, rng_seed, pad_..., normalize_text). The speaker reference is raw audio (1, L) @ 44.1 kHz
+    (`speaker_audio`, encoded here like the reference does) or, through the keyword-only extensions, already-encoded
+    PCA latents + mask, or a `Voice` from a `VoiceCache` (latents, mask and the speaker KV cache: `sample_fn` must
+    then accept `speaker_kv_cache=`, as the samplers of this package do). Returns (audio (1, 1, n) fp32, normalised
+    text)."""
     from .autoencoder import ae_decode
     device = model.device
     ids, mask, norm = get_text_input_ids_and_mask(

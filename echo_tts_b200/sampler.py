@@ -35,7 +35,8 @@ def _args(model: B200EchoDiT, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_
         # the reference evaluates `t_next < None` and raises (inference.py:511)
         raise TypeError("'<' not supported between instances of 'Tensor' and 'NoneType' (speaker_kv_min_t is None)")
     a.speaker_kv_scale = float(speaker_kv_scale or 0.0)
-    a.speaker_kv_max_layers = int(speaker_kv_max_layers) if speaker_kv_max_layers is not None else 0
+    # None -> every layer (C side: negative); an explicit n scales min(n, num_layers) layers, n <= 0 none (inference.py:408-414)
+    a.speaker_kv_max_layers = max(int(speaker_kv_max_layers), 0) if speaker_kv_max_layers is not None else -1
     a.speaker_kv_min_t = float(speaker_kv_min_t or 0.0)
     a.sequence_length = int(sequence_length)
     a.round_t_to_bf16 = int(model.round_t_to_model_dtype)

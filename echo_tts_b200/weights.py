@@ -111,16 +111,24 @@ def _make(key, shape, kind, seed):
     raise ValueError(kind)
 
 
-def iter_dit_weights(cfg: DitConfig, seed: int = 1234, include_latent: bool = True):
+def iter_dit_weights(cfg: DitConfig, seed: int = 1234, include_latent: bool = True, branch_gain: float = 1.0):
+    """`branch_gain` (a power of two, so the bf16 rounding of the values is unchanged) multiplies the output
+    projections `attention.wo` / `mlp.w2` of the DiT blocks. With the default-style init each residual branch adds only
+    ~1 % to the stream, which hides branch-level errors behind the stream itself; gain 32 gives "trained-like" blocks
+    whose branches are O(0.3) of the stream (tests/test_full_gpu.py: dit_full_cfg2t golden)."""
     for key, shape, kind in dit_param_specs(cfg):
         if not include_latent and (key.startswith("latent_encoder.") or key.startswith("latent_norm")
                                    or ".wk_latent" in key or ".wv_latent" in key):
             continue  # mirrors delete_blockwise_modules (reference inference.py:28-34)
-        yield key, _make(key, shape, kind, seed)
+        w = _make(key, shape, kind, seed)
+        if branch_gain != 1.0 and key.startswith("blocks.") and key.endswith(("attention.wo.weight", "mlp.w2.weight")):
+            w = w * branch_gain
+        yield key, w
 
 
-def make_dit_weights(cfg: DitConfig, seed: int = 1234, include_latent: bool = True) -> Dict[str, torch.Tensor]:
-    return dict(iter_dit_weights(cfg, seed, include_latent))
+def make_dit_weights(cfg: DitConfig, seed: int = 1234, include_latent: bool = True,
+                     branch_gain: float = 1.0) -> Dict[str, torch.Tensor]:
+    return dict(iter_dit_weights(cfg, seed, include_latent, branch_gain))
 
 
 # ----------------------------------------------------------------------------------------------- DAC (decode path)

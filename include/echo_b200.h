@@ -13,7 +13,11 @@
  *   - all data pointers are CUDA DEVICE pointers owned by the caller unless a parameter says "host".
  *   - `stream` is a cudaStream_t passed as void*; the library never synchronises the device behind the caller's
  *     back except in the *_host entry points (documented there).
- *   - a handle is bound to one device and is not thread-safe; use one handle per (device, thread).
+ *   - a handle is bound to one device. Its compute entry points are serialised by a per-handle mutex, and a call on
+ *     a different stream than the previous call first waits (on the device) for the work the handle enqueued on the old
+ *     stream: the activation / KV workspaces are per handle. For concurrency use one handle per worker. A stream
+ *     handed to the library must stay alive until the next call on the same handle has been issued.
+ *   - one process may drive several devices (one handle each); per-device kernel attributes are set on first use.
  *   - there is NO CPU fallback: without an sm_100 device echo_create fails with ECHO_ERR_DEVICE.
  */
 #ifndef ECHO_B200_H
@@ -92,7 +96,7 @@ typedef struct echo_sampler_args {
   float cfg_max_t;
   int has_truncation; float truncation_factor;
   int has_rescale;    float rescale_k; float rescale_sigma;
-  int has_kv_scale;   float speaker_kv_scale; int speaker_kv_max_layers; /* <=0: all layers */ float speaker_kv_min_t;
+  int has_kv_scale;   float speaker_kv_scale; int speaker_kv_max_layers; /* < 0: all layers (None); else min(n, num_layers), 0 = none */ float speaker_kv_min_t;
   int sequence_length;   /* latents to generate (<= 640 in the reference) */
   int round_t_to_bf16;   /* 1: t is rounded to bf16 before the timestep embedding, as the reference does when
                             model.dtype is bfloat16 (inference.py:489); 0: fp32 t */
@@ -143,6 +147,14 @@ int echo_dit_forward(echo_handle* h, const float* x, const float* t, const uint8
                      const uint8_t* speaker_mask, void* const* Kt, void* const* Vt, int Lt, void* const* Ks,
                      void* const* Vs, int Ls_unstrided, void* const* Kl, void* const* Vl, int Pl, int start_pos,
                      int b, int S, float* out, void* const* layer_out, void* stream);
+
+/* Same call with a second probe array: layer_mid[i] (optional, (b,S,D) fp32) receives the stream after block i's
+ * attention branch, i.e. the input of mlp_adaln (model.py:388), so that parity tests can compare the two residual
+ * increments of every block (attention and MLP, model.py:384-389) with the reference's separately. */
+int echo_dit_forward_probe(echo_handle* h, const float* x, const float* t, const uint8_t* text_mask,
+                           const uint8_t* speaker_mask, void* const* Kt, void* const* Vt, int Lt, void* const* Ks,
+                           void* const* Vs, int Ls_unstrided, void* const* Kl, void* const* Vl, int Pl, int start_pos,
+                           int b, int S, float* out, void* const* layer_out, void* const* layer_mid, void* stream);
 
 /* ---- samplers: replace inference.py:427-517 and inference_blockwise.py:15-123 -------------------------- */
 /* noise: (B, sequence_length, 80) fp32 drawn by the caller (torch.randn with the reference's generator, so seeds
@@ -260,6 +272,13 @@ int echo_op_rmsnorm_affine(const float* x, void* out_bf16, const float* a, const
 int echo_op_cfg_euler_update(float* x, const float* v, int64_t n_per_branch, int has_cfg, float cfg_scale_text,
                              float cfg_scale_speaker, int has_rescale, float one_minus_t, float ratio, float dt,
                              void* stream);
+
+/* find_flattening_point (reference inference.py:288-296; the step after ae_decode in sample_pipeline, :345): *out_index
+ * (device int32) = first i in [0, T) whose window of window_size rows of latent (T, C) fp32 -- zero padded past the
+ * end -- has unbiased std < std_threshold and |mean - target_value| < 0.1, else T. One warp per window, no host sync
+ * (the reference loops over up to 640 windows with two device syncs each). */
+int echo_op_flattening_point(const float* latent, int T, int C, float target_value, int window_size,
+                             float std_threshold, int32_t* out_index, void* stream);
 
 #ifdef __cplusplus
 }

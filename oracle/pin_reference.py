@@ -321,8 +321,26 @@ def run_full(which: str):
         print("dac T=64 decode", time.time() - t1, "s; rms", audio.pow(2).mean().sqrt().item())
         torch.save(dict(z=z, audio=audio.clone()), os.path.join(GOLD, "dac_full_T64.pt"))
         return
+    if which == "dac640":
+        # the full-length decode of BASELINE configs[1] (640 latents -> 1 310 720 samples), stored as fp16 (2.6 MB):
+        # the waveform is tanh-bounded, fp16 keeps ~1e-3 relative precision per sample (rel-L2 ~3e-4 overall)
+        dcfg = DacConfig.base()
+        dsd = make_dac_weights(dcfg, seed=4321)
+        ae = build_ref_dac(refae, dcfg, dsd)
+        comps, mean, scale = make_pca_state(dcfg)
+        pca = refinf.PCAState(pca_components=comps, pca_mean=mean, latent_scale=scale)
+        z = torch.randn(1, 640, 80, generator=torch.Generator().manual_seed(6))
+        t1 = time.time()
+        audio = refinf.ae_decode(ae, pca, z)
+        dt = time.time() - t1
+        a16 = audio.to(torch.float16)
+        print(f"dac T=640 decode {dt:.1f} s; rms {audio.pow(2).mean().sqrt().item():.4f}; fp16 storage rel-L2 "
+              f"{rel(a16.float(), audio):.2e}")
+        torch.save(dict(z=z, audio_f16=a16.clone(), seconds=torch.tensor(dt)), os.path.join(GOLD, "dac_full_T640.pt"))
+        return
     cfg = DitConfig.base()
-    sd = make_dit_weights(cfg, seed=1234)
+    gain = 32.0 if which == "cfg2t" else 1.0  # cfg2t: "trained-like" blocks, see weights.iter_dit_weights
+    sd = make_dit_weights(cfg, seed=1234, branch_gain=gain)
     m = build_ref_dit(refmodel, cfg, sd)
     print("weights + reference model ready", time.time() - t0, "s")
     ids, tmask = text_ids_mask(refinf, [BASE_PROMPT], 768)  # sample_pipeline always pads to 768 (inference.py:327)
@@ -331,7 +349,7 @@ def run_full(which: str):
     if which == "cfg1":
         spk = torch.zeros(1, 4, 80)
         smask = torch.zeros(1, 4, dtype=torch.bool)  # no speaker audio (inference.py:329-331)
-    elif which == "cfg2":
+    elif which in ("cfg2", "cfg2t"):
         spk = torch.randn(1, 212, 80, generator=torch.Generator().manual_seed(1))
         smask = torch.ones(1, 212, dtype=torch.bool)
     elif which == "cfg5":
@@ -349,22 +367,43 @@ def run_full(which: str):
         return
     else:
         raise SystemExit(which)
-    layers = []
-    first_call = {"done": False}
+    # Per-block probes on rows 0 / 319 / 639 of every batch row, at two model calls of the sampler: call 0 (step 0, the
+    # three CFG branches, t = 0.999) and call PLAIN_CALL (a plain b = 1 step, t < cfg_min_t). For every block the stream
+    # BEFORE the block, AFTER the attention branch (= the input of mlp_adaln, model.py:388) and AFTER the MLP branch
+    # (model.py:389) are kept, so that the tests can compare the two residual INCREMENTS of each block separately.
+    PLAIN_CALL = 30
+    ROWS = [0, 319, 639]
+    call = {"i": -1}
+    probes = {0: dict(mid=[], out=[]), PLAIN_CALL: dict(mid=[], out=[])}
 
-    def hook(_m, _i, o):
-        if not first_call["done"]:
-            layers.append(o[:, [0, 319, 639]].clone())
+    def want():
+        return probes.get(call["i"])
 
-    hooks = [blk.register_forward_hook(hook) for blk in m.blocks]
+    def pre_block0(_m, args, kwargs):
+        if want() is not None:
+            want()["x0"] = (args[0] if args else kwargs["x"])[:, ROWS].clone()
+
+    def pre_mlp_adaln(_m, args):
+        if want() is not None:
+            want()["mid"].append(args[0][:, ROWS].clone())
+
+    def post_block(_m, _i, o):
+        if want() is not None:
+            want()["out"].append(o[:, ROWS].clone())
+
+    hooks = [m.blocks[0].register_forward_pre_hook(pre_block0, with_kwargs=True)]
+    for blk in m.blocks:
+        hooks.append(blk.mlp_adaln.register_forward_pre_hook(pre_mlp_adaln))
+        hooks.append(blk.register_forward_hook(post_block))
     orig_forward = m.forward
-    vs = []
 
     def fwd(*a, **k):
+        call["i"] += 1
+        if want() is not None:
+            want()["x"], want()["t"] = k["x"].clone(), k["t"].clone()
         r = orig_forward(*a, **k)
-        if not first_call["done"]:
-            vs.append(r.clone())
-        first_call["done"] = True
+        if want() is not None:
+            want()["v"] = r.clone()
         return r
 
     m.forward = fwd
@@ -374,16 +413,29 @@ def run_full(which: str):
     dt = time.time() - t1
     for h in hooks:
         h.remove()
-    print(f"{which}: reference fp32 sampler {dt:.1f} s on {torch.get_num_threads()} threads")
-    res.update(latent=lat.clone(), step0_v=vs[0], step0_layers_rows=torch.stack(layers), seconds=torch.tensor(dt),
-               threads=torch.tensor(torch.get_num_threads()))
+    print(f"{which}: reference fp32 sampler {dt:.1f} s on {torch.get_num_threads()} threads, {call['i'] + 1} model calls")
+    p0, p1 = probes[0], probes[PLAIN_CALL]
+    assert p1["x"].shape[0] == 1 and float(p1["t"][0]) < 0.5 and p0["x"].shape[0] == 3
+    for name, p in (("step0", p0), ("plain", p1)):
+        mid, out = torch.stack(p["mid"]), torch.stack(p["out"])
+        xin = torch.cat([p["x0"][None], out[:-1]])
+        ra = ((mid - xin).flatten(1).norm(dim=1) / xin.flatten(1).norm(dim=1))
+        rm = ((out - mid).flatten(1).norm(dim=1) / mid.flatten(1).norm(dim=1))
+        print(f"  {name}: |attention increment| / |stream| per block: min {ra.min():.3f} max {ra.max():.3f}; "
+              f"|mlp increment| / |stream|: min {rm.min():.3f} max {rm.max():.3f}")
+    res.update(latent=lat.clone(), step0_v=p0["v"], step0_layers_rows=torch.stack(p0["out"]),
+               step0_x0_rows=p0["x0"], step0_mid_rows=torch.stack(p0["mid"]),
+               plain_x=p1["x"], plain_t=p1["t"], plain_v=p1["v"], plain_x0_rows=p1["x0"],
+               plain_mid_rows=torch.stack(p1["mid"]), plain_out_rows=torch.stack(p1["out"]),
+               plain_call=torch.tensor(PLAIN_CALL), branch_gain=torch.tensor(gain),
+               seconds=torch.tensor(dt), threads=torch.tensor(torch.get_num_threads()))
     torch.save(res, os.path.join(GOLD, f"dit_full_{which}.pt"))
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiny", action="store_true")
-    ap.add_argument("--full", choices=["cfg1", "cfg2", "cfg5", "dac"])
+    ap.add_argument("--full", choices=["cfg1", "cfg2", "cfg2t", "cfg5", "dac", "dac640"])
     ap.add_argument("--encode", choices=["tiny", "full"])
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)

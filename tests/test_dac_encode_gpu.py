@@ -50,7 +50,10 @@ def test_dac_encode_stages(which):
     assert e_pre < Z_TOL, e_pre
     assert same_input > 0.999, same_input      # only exact fp32 near-ties may differ
     assert rel_l2(zq, zq_o) < 1e-5
-    assert first > 0.6, first                   # bf16 operand noise upstream flips near-tie codes; most must survive
+    # bf16 operand noise upstream may flip exact near-ties only. Measured on B200 (the encode path has no atomics, so
+    # this is reproducible): tiny 0.993 of all codes (5 of 740) / semantic 1.000, full size 0.998 / 1.000.
+    assert first >= 0.99, first
+    assert agree >= (0.985 if which == "tiny" else 0.99), agree
 
 
 def test_ae_encode_and_speaker_latents_tiny():

@@ -63,3 +63,22 @@ def test_dac_full_T640_roundtrip_properties():
     assert rel_l2(audio[..., : 64 * 2048], g["audio"]) < AUDIO_TOL
     two = ae_decode(dac, pca, torch.cat([z[:, :128], z[:, 128:256]], 0))
     assert rel_l2(two[0], audio[0, :, : 128 * 2048]) < 1e-3
+
+
+def test_dac_full_T640_vs_reference():
+    """The full-length decode of BASELINE configs[1] (640 latents -> 1 310 720 samples) against the REAL reference's
+    fp32 `ae_decode` (oracle/pin_reference.py --full dac640; 44 s on the build container's CPU), over the WHOLE
+    waveform. The golden is stored as fp16 (tanh-bounded samples; storage error 2e-4 rel-L2, far below the bar)."""
+    from echo_tts_b200.autoencoder import ae_decode
+    cfg = DacConfig.base()
+    dac, pca = _build(cfg)
+    g = gold("dac_full_T640.pt")
+    audio = ae_decode(dac, pca, g["z"])
+    ref = g["audio_f16"].float()
+    assert tuple(audio.shape) == tuple(ref.shape) == (1, 1, 640 * 2048)
+    e = rel_l2(audio, ref)
+    # the error must not grow along the sequence (window-128 transformer, conv stack): every tenth is within the bar
+    tenths = [rel_l2(audio[..., i * 131072:(i + 1) * 131072], ref[..., i * 131072:(i + 1) * 131072]) for i in range(10)]
+    print(f"dac T=640 whole-waveform rel-L2 {e:.3e}; per tenth max {max(tenths):.3e}")
+    assert e < AUDIO_TOL, e
+    assert max(tenths) < AUDIO_TOL, tenths

@@ -156,3 +156,95 @@ def test_kv_scale_requires_min_t(tiny):
     with pytest.raises(TypeError):
         sample(model, g["kv_spk"], g["eu_smask"], g["kv_ids"], g["kv_tmask"], 0, sequence_length=8,
                **dict(PLAIN_KNOBS, speaker_kv_scale=1.5))
+
+
+def test_sample_euler_host_entry_is_bit_equal_to_the_device_entry(tiny):
+    """`echo_sample_euler_host` (the entry a non-PyTorch host binds, INTEGRATION.md section 2: plain host pointers in,
+    host pointer out, synchronous) must give exactly what `echo_sample_euler` gives on device tensors. Deterministic
+    mode, so that bit equality is meaningful."""
+    import ctypes as C
+
+    import echo_tts_b200
+    from echo_tts_b200 import _lib
+    from echo_tts_b200.sampler import _args, sample_euler_cfg_independent_guidances as sample
+    cfg, sd, model, g = tiny
+    S = int(g["eu_S"])
+    noise = torch.randn((2, S, 80), generator=torch.Generator().manual_seed(int(g["eu_seed"])))
+    spk, smask, ids, tmask = g["kv_spk"], g["eu_smask"], g["kv_ids"], g["kv_tmask"]
+    try:
+        echo_tts_b200.set_deterministic(True)
+        dev = sample(model, spk, smask, ids, tmask, 0, sequence_length=S, noise=noise, **EULER_KNOBS).cpu()
+        a = _args(model, sequence_length=S, **EULER_KNOBS)
+        # the host entry takes the fp32 speaker latents and rounds them to bf16 itself (inference.py:465)
+        spk_h = spk.float().contiguous()
+        sm_h = smask.to(torch.uint8).contiguous()
+        ids_h = ids.to(torch.int32).contiguous()
+        tm_h = tmask.to(torch.uint8).contiguous()
+        nz_h = noise.float().contiguous()
+        out_h = torch.empty(2, S, 80, dtype=torch.float32)
+        with torch.cuda.device(model.device):
+            _lib.check(model.lib.echo_sample_euler_host(model.h.ptr, C.byref(a), spk_h.data_ptr(), sm_h.data_ptr(),
+                                                        sm_h.shape[1], ids_h.data_ptr(), tm_h.data_ptr(), tm_h.shape[1], 2,
+                                                        nz_h.data_ptr(), out_h.data_ptr()), "echo_sample_euler_host")
+    finally:
+        echo_tts_b200.set_deterministic(False)
+    assert torch.equal(out_h, dev)
+    assert rel_l2(out_h, g["eu_latent"]) < LATENT_TOL
+
+
+def test_speaker_kv_max_layers_zero_scales_no_layer(tiny):
+    """reference `_multiply_kv_cache(cache, s, max_layers)` scales min(max_layers, L) layers: None = all, 0 = none
+    (inference.py:408-414). With 0 layers the scaling knobs must change nothing."""
+    import echo_tts_b200
+    from echo_tts_b200.sampler import sample_euler_cfg_independent_guidances as sample
+    cfg, sd, model, g = tiny
+    S = 16
+    noise = torch.randn((2, S, 80), generator=torch.Generator().manual_seed(3))
+    args = (model, g["kv_spk"], g["eu_smask"], g["kv_ids"], g["kv_tmask"], 0)
+    try:
+        echo_tts_b200.set_deterministic(True)
+        base = sample(*args, sequence_length=S, noise=noise, **dict(PLAIN_KNOBS, num_steps=4))
+        zero = sample(*args, sequence_length=S, noise=noise,
+                      **dict(PLAIN_KNOBS, num_steps=4, speaker_kv_scale=1.5, speaker_kv_min_t=0.6, speaker_kv_max_layers=0))
+        allv = sample(*args, sequence_length=S, noise=noise,
+                      **dict(PLAIN_KNOBS, num_steps=4, speaker_kv_scale=1.5, speaker_kv_min_t=0.6, speaker_kv_max_layers=None))
+        huge = sample(*args, sequence_length=S, noise=noise,
+                      **dict(PLAIN_KNOBS, num_steps=4, speaker_kv_scale=1.5, speaker_kv_min_t=0.6, speaker_kv_max_layers=99))
+    finally:
+        echo_tts_b200.set_deterministic(False)
+    assert torch.equal(zero, base)
+    assert not torch.equal(allv, base) and torch.equal(allv, huge)
+
+
+def test_two_handles_two_streams_one_process(tiny):
+    """Two handles in one process, each on its own CUDA stream (and on a second device when there is one): per-device
+    kernel attributes and SM counts, and no shared scratch between handles."""
+    from echo_tts_b200.model import B200EchoDiT
+    from echo_tts_b200.sampler import sample_euler_cfg_independent_guidances as sample
+    cfg, sd, model, g = tiny
+    dev2 = "cuda:1" if torch.cuda.device_count() > 1 else "cuda:0"
+    other = B200EchoDiT.from_state_dict(sd, cfg, dev2)
+    S = 16
+    noise = torch.randn((2, S, 80), generator=torch.Generator().manual_seed(4))
+    kn = dict(PLAIN_KNOBS, num_steps=4)
+    args = (g["kv_spk"], g["eu_smask"], g["kv_ids"], g["kv_tmask"], 0)
+    ref = sample(model, *args, sequence_length=S, noise=noise, **kn).cpu()
+    s1, s2 = torch.cuda.Stream(model.device), torch.cuda.Stream(other.device)
+    outs = []
+    for _ in range(3):  # interleave the two handles; nothing synchronises between the calls
+        with torch.cuda.stream(s1):
+            a = sample(model, *args, sequence_length=S, noise=noise, **kn)
+        with torch.cuda.device(other.device), torch.cuda.stream(s2):
+            b = sample(other, *args, sequence_length=S, noise=noise, **kn)
+        outs.append((a, b))
+    torch.cuda.synchronize(model.device)
+    torch.cuda.synchronize(other.device)
+    for a, b in outs:
+        assert rel_l2(a, ref) < 5e-3 and rel_l2(b, ref) < 5e-3  # atomics: run-to-run noise only
+    # one handle, two streams back to back: the second call must wait for the first (shared workspace)
+    with torch.cuda.stream(s1):
+        a = sample(model, *args, sequence_length=S, noise=noise, **kn)
+    with torch.cuda.stream(torch.cuda.Stream(model.device)):
+        b = sample(model, *args, sequence_length=S, noise=noise, **kn)
+    torch.cuda.synchronize(model.device)
+    assert rel_l2(a, ref) < 5e-3 and rel_l2(b, ref) < 5e-3

@@ -185,10 +185,13 @@ def test_attention_joint(ops, S, Lt, Ls, D, H):
     assert rel_l2(out, ref) < 6e-3
 
 
-@pytest.mark.parametrize("S,D,H,window", [(200, 128, 2, 0), (640, 64, 4, 128), (53, 128, 10, 0)])
+@pytest.mark.parametrize("S,D,H,window", [(200, 128, 2, 0), (640, 64, 4, 128), (53, 128, 10, 0), (1600, 128, 2, 0),
+                                          (640, 64, 16, 128), (2048, 64, 2, 512), (160, 64, 3, 128), (100, 64, 2, 7),
+                                          (300, 128, 1, 64), (129, 64, 1, 128), (1, 64, 2, 128)])
 def test_attention_causal_window(ops, S, D, H, window):
-    """Causal (speaker/latent encoders, model.py:148-154) and window-limited causal (DAC post_module,
-    autoencoder.py:762-773) self attention."""
+    """Causal (speaker/latent encoders, model.py:148-154) and window-limited causal (DAC post_module / pre_module /
+    encoder transformer, autoencoder.py:762-773; head_dim 64) self attention on the tcgen05 kernel: per-CTA tile
+    lists limited to the visible keys, diagonal / window-edge tiles masked per row."""
     b = 2
     q, k, v = _rand((b, S, H, D), 51), _rand((b, S, H, D), 52), _rand((b, S, H, D), 53)
     out = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
@@ -218,22 +221,53 @@ def test_attention_tc_growing_max(ops, b, S, H, L2):
     assert rel_l2(out, ref.reshape(b, S, H * D)) < 6e-3
 
 
-def test_attention_tc_matches_mma_sync_kernel(ops, monkeypatch):
-    """Both attention kernels (tcgen05 and the mma.sync one kept for causal / head_dim 64) agree on a joint-attention
-    case; the dispatch is decided once per process, so the mma.sync result is obtained through a causal-free D=128
-    call with a window that covers every key... not expressible -> compare both against the fp32 reference instead."""
+def test_attention_causal_last_row_equals_full_attention(ops):
+    """The last query row of a causal attention sees every key: it must equal the same row of the unmasked attention
+    (same kernel, different tile-list / masking path)."""
     b, S, H, D = 3, 256, 2, 128
     q, k, v = _rand((b, S, H, D), 71), _rand((b, S, H, D), 72), _rand((b, S, H, D), 73)
-    out_tc = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
-    ops.attention(q, [dict(k=k, v=v)], out_tc)
-    out_causal = torch.empty_like(out_tc)
-    ops.attention(q, [dict(k=k, v=v, causal=1, window=0)], out_causal)  # mma.sync path
+    out_full = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, [dict(k=k, v=v)], out_full)
+    out_causal = torch.empty_like(out_full)
+    ops.attention(q, [dict(k=k, v=v, causal=1, window=0)], out_causal)
     full = torch.ones(b, S, S, dtype=torch.bool, device="cuda")
     ref = _sdpa_ref(q, [k], [v], [full], D ** -0.5).reshape(b, S, H * D)
-    assert rel_l2(out_tc, ref) < 6e-3
-    # the last query row of a causal attention sees every key: identical problem, different kernel
+    assert rel_l2(out_full, ref) < 6e-3
     assert rel_l2(out_causal[:, -1], ref[:, -1]) < 6e-3
-    assert rel_l2(out_causal[:, -1], out_tc[:, -1].float()) < 8e-3
+    assert torch.equal(out_causal[:, -1], out_full[:, -1])
+
+
+def test_attention_d64_joint_with_gate_and_mask(ops):
+    """head_dim 64 on the non-causal path too: two segments, a ragged key mask with eff_len, and the output gate."""
+    b, S, H, D, L2 = 2, 200, 3, 64, 150
+    q, k, v = _rand((b, S, H, D), 81), _rand((b, S, H, D), 82), _rand((b, S, H, D), 83)
+    k2, v2 = _rand((b, L2, H, D), 84), _rand((b, L2, H, D), 85)
+    gate = torch.sigmoid(_rand((b, S, H * D), 86).float()).to(torch.bfloat16)
+    m2 = torch.zeros(b, L2, dtype=torch.bool, device="cuda")
+    m2[0, :97] = True
+    m2[1, :31] = True
+    eff = torch.tensor([97, 31], dtype=torch.int32, device="cuda")
+    out = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, [dict(k=k, v=v), dict(k=k2, v=v2, mask=m2, eff_len=eff)], out, gate=gate)
+    masks = [torch.ones(b, S, S, dtype=torch.bool, device="cuda"), m2[:, None, :].expand(b, S, L2)]
+    ref = _sdpa_ref(q, [k, k2], [v, v2], masks, D ** -0.5).reshape(b, S, H * D) * gate.float()
+    assert rel_l2(out, ref) < 6e-3
+
+
+def test_attention_rejects_what_it_cannot_run(ops):
+    """No silent truncation: more visible keys per query tile than the kernel's tile list holds (7680) is an error,
+    and so is a head dim other than 64 / 128."""
+    from echo_tts_b200._lib import EchoError
+    b, H, D = 1, 1, 128
+    q = _rand((b, 64, H, D), 91)
+    k, v = _rand((b, 7744, H, D), 92), _rand((b, 7744, H, D), 93)
+    out = torch.empty(b, 64, H * D, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(EchoError):
+        ops.attention(q, [dict(k=k, v=v)], out)
+    q32 = _rand((b, 64, H, 32), 94)
+    with pytest.raises(EchoError):
+        ops.attention(q32, [dict(k=_rand((b, 64, H, 32), 95), v=_rand((b, 64, H, 32), 96))],
+                      torch.empty(b, 64, H * 32, device="cuda", dtype=torch.bfloat16))
 
 
 @pytest.mark.parametrize("rows,W,groups", [(1920, 2048, 0), (640, 2048, 0), (768, 1280, 0), (53, 1280, 0), (640, 1024, 0),

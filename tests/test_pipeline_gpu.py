@@ -50,8 +50,9 @@ def test_sample_pipeline_with_speaker_latents(stack):
     model, dac, pca, sample_fn = stack
     spk = torch.randn(1, 16, 80, generator=torch.Generator().manual_seed(3)).cuda()
     smask = torch.ones(1, 16, dtype=torch.bool, device="cuda")
-    a, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same text.", spk, smask, rng_seed=1, pad_to_max_text_length=64)
-    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same text.", None, None, rng_seed=1, pad_to_max_text_length=64)
+    a, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same text.", rng_seed=1, pad_to_max_text_length=64,
+                             speaker_latent=spk, speaker_mask=smask)
+    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same text.", None, 1, pad_to_max_text_length=64)  # the reference's positional order
     assert torch.isfinite(a).all() and a.abs().max() <= 1.0
     n = min(a.shape[-1], b.shape[-1])
     assert n == 0 or not torch.equal(a[..., :n], b[..., :n])  # the speaker condition changes the result
@@ -88,7 +89,8 @@ def test_sample_pipeline_with_speaker_audio(stack):
     assert spk.shape[1] == 68 and bool(smask.all())  # 70 complete frames -> trimmed to a multiple of 4
     a, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] With a voice.", rng_seed=3, pad_to_max_text_length=64,
                              speaker_audio=wav)
-    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] With a voice.", spk, smask, rng_seed=3, pad_to_max_text_length=64)
+    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] With a voice.", rng_seed=3, pad_to_max_text_length=64,
+                             speaker_latent=spk, speaker_mask=smask)
     assert torch.equal(a, b) and torch.isfinite(a).all()
 
 
@@ -153,9 +155,104 @@ def test_voice_cache_skips_the_speaker_encoder_and_changes_nothing(stack):
     sample_fn = functools.partial(sample, **dict(PLAIN_KNOBS, num_steps=4), sequence_length=24)
     a, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same voice again.", rng_seed=3, pad_to_max_text_length=64,
                              voice=voice)
-    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same voice again.", spk, smask, rng_seed=3,
-                             pad_to_max_text_length=64)
+    b, _ = P.sample_pipeline(model, dac, pca, sample_fn, "[S1] Same voice again.", rng_seed=3,
+                             pad_to_max_text_length=64, speaker_latent=spk, speaker_mask=smask)
     assert torch.equal(a, b)
     with pytest.raises(ValueError):
         sample(model, spk, smask, ids, mask, 0, sequence_length=24, noise=noise, speaker_kv_cache=voice.kv[:-1],
                **dict(PLAIN_KNOBS, num_steps=4))
+
+
+# ------------------------------------------------------------------------------------------------ N > 1 over NCCL
+NCCL_TEXT = ("This is the first sentence of a long prompt. " * 8).strip()
+
+
+def _tiny_synth_chunk(device):
+    """The real tiny sampler + DAC decode on `device`, as a `synth_chunk(chunk_text, seed)` for pipeline.synthesize."""
+    from echo_tts_b200.autoencoder import B200DAC, PCAState
+    from echo_tts_b200.model import B200EchoDiT
+    from echo_tts_b200.sampler import sample_euler_cfg_independent_guidances as sample
+    cfg, dcfg = DitConfig.tiny(), DacConfig.tiny()
+    model = B200EchoDiT.from_state_dict(make_dit_weights(cfg, 1234), cfg, device)
+    dac = B200DAC.from_state_dict(make_dac_weights(dcfg, 4321), dcfg, device)
+    comps, mean, scale = make_pca_state(dcfg)
+    pca = PCAState(comps.to(device), mean.to(device), scale)
+    sample_fn = functools.partial(sample, **dict(PLAIN_KNOBS, num_steps=4), sequence_length=24)
+
+    def synth_chunk(chunk, seed):
+        audio, _ = P.sample_pipeline(model, dac, pca, sample_fn, chunk, rng_seed=seed, pad_to_max_text_length=160)
+        return audio[0]
+
+    return synth_chunk
+
+
+def _nccl_worker(rank, world, port, out_path):
+    import os
+    import sys
+
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    echo_tts_b200.set_deterministic(True)
+    calls = []
+    synth = _tiny_synth_chunk(f"cuda:{rank}")
+
+    def synth_chunk(chunk, seed):
+        calls.append(seed)
+        return synth(chunk, seed)
+
+    audio = P.synthesize(NCCL_TEXT, synth_chunk, seed=11)  # chunks i % world, NCCL all_gather of the audio, rank 0 stitches
+    torch.save({"audio": audio, "calls": calls}, f"{out_path}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_sharded_synthesis_over_nccl_equals_single_process(tmp_path):
+    """BASELINE configs[3] in small: the chunks of one long prompt sharded over 2 GPUs (one process per GPU, NCCL
+    gather of the finished audio, host stitching on rank 0) must equal the single-process job bit for bit
+    (deterministic mode), with the reference's seed progression seed + 1000 * idx (handler.py:746-768)."""
+    import socket
+
+    import torch.multiprocessing as mp
+    echo_tts_b200.set_deterministic(True)
+    try:
+        single = P.synthesize(NCCL_TEXT, _tiny_synth_chunk("cuda:0"), seed=11)
+    finally:
+        echo_tts_b200.set_deterministic(False)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "nccl")
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    res = [torch.load(f"{out}.{r}") for r in range(2)]
+    chunks = P.chunk_text_for_audio(NCCL_TEXT, 300, 10.0)
+    assert len(chunks) >= 3
+    assert res[1]["audio"] is None and torch.equal(res[0]["audio"], single)
+    for r in range(2):
+        assert res[r]["calls"] == [11 + 1000 * i for i in P.shard_units(len(chunks), r, 2)]
+
+
+def test_flattening_point_kernel_bit_exact_vs_reference_goldens():
+    """SURVEY 8 f2 on the device: `find_flattening_point` of GPU latents (one warp-per-window kernel through the C
+    ABI) must return exactly the reference's index on the fixtures lifted from inference.py:288-301
+    (tests/golden/host_pipeline.pt), agree with the host evaluation on random cases, and handle the edges."""
+    from oracle import host_oracle as H
+    from tests.util import gold
+    g = gold("host_pipeline.pt")
+    for x, ref in zip(g["flat_latents"], g["flat_points"]):
+        assert P.find_flattening_point(x.cuda()) == ref
+    audio = torch.zeros(1, 1, 64 * 2048, device="cuda")
+    assert P.crop_audio_to_flattening_point(audio, g["flat_latents"][0].cuda()).shape[-1] == g["crop_audio_len"]
+    gen = torch.Generator().manual_seed(5)
+    for T, cut in ((640, 400), (640, 0), (640, 640), (37, 20), (19, 3), (1, 0), (1, 1), (160, 159)):
+        x = torch.randn(T, 80, generator=gen)
+        x[cut:] = 0.02 * torch.randn(T - cut, 80, generator=gen)  # flat tail: std 0.02 < 0.05, mean ~ 0
+        assert P.find_flattening_point(x.cuda()) == H.find_flattening_point(x) == P.find_flattening_point(x), (T, cut)
+    # near the thresholds: windows whose std straddles 0.05
+    x = 0.05 * torch.randn(300, 80, generator=gen) * torch.linspace(1.2, 0.8, 300)[:, None]
+    assert P.find_flattening_point(x.cuda()) == H.find_flattening_point(x)
+    assert P.find_flattening_point(torch.zeros(0, 80, device="cuda")) == 0
