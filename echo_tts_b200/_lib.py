@@ -79,6 +79,7 @@ class AttnSegment(C.Structure):
         ("len", C.c_int), ("eff_len", C.c_void_p),
         ("mask", C.c_void_p), ("mask_ld", C.c_int), ("mask_stride", C.c_int),
         ("pos_limit_mult", C.c_int), ("pos_limit", C.c_int), ("causal", C.c_int), ("window", C.c_int),
+        ("q_offset", C.c_int),
     ]
 
 
@@ -88,6 +89,7 @@ class AttnDesc(C.Structure):
         ("gate", C.c_void_p), ("out", C.c_void_p),
         ("b", C.c_int), ("S", C.c_int), ("H", C.c_int), ("D", C.c_int), ("scale", C.c_float),
         ("nseg", C.c_int), ("seg", AttnSegment * 4), ("trace", C.c_void_p),
+        ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_int64), ("nsplit", C.c_int),
     ]
 
 

@@ -60,10 +60,13 @@ struct AttnMaps {
 struct SmemCtl {
   uint64_t q_full, k_full[2], v_full[2], s_full[2], p_ready[2], pv_done[2];
   uint32_t tmem_slot;
-  int ntiles;
+  int ntiles;   // tiles of THIS CTA (its share of the list when the keys are split over several CTAs)
+  int t_lo;     // first list entry of this CTA
+  int is_last;  // split-KV: this CTA arrived last and merges
   int seg_hi[4];
   int tiles[AT_MAX_TILES];
 };
+constexpr int AT_COUNTER_BYTES = 64 * 1024;  // arrival counters at the start of the split-KV workspace
 static_assert(sizeof(SmemCtl) <= 1024, "control block");
 
 template <int D>
@@ -81,7 +84,8 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   auto sV = [&](int st) { return smem + Q_BYTES + st * STAGE + KSLOT; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  const int nsplit = d.nsplit > 1 ? d.nsplit : 1;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = (int)blockIdx.z / nsplit, sp = (int)blockIdx.z % nsplit;
   // timeline (tuning): 0 entry, 1 setup done, 2 tile list done, 3 Q landed (MMA thread), 4+2j / 5+2j = softmax of
   // tile j starts (scores ready) / ends (P published), 30 O complete, 31 epilogue done   -- stamps of warp 2 lane 0
   long long* trace = d.trace ? d.trace + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -120,12 +124,12 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         const int lim = (sg.pos_limit + sg.pos_limit_mult - 1) / sg.pos_limit_mult;  // keys j with j*mult < pos_limit
         hi = lim < hi ? lim : hi;
       }
-      if (sg.causal) {  // keys this CTA's rows can see: j <= q (and j > q - window), q in [q0, min(q0 + 128, S))
-        const int qe = q0 + TQ < d.S ? q0 + TQ : d.S;
+      if (sg.causal) {  // keys this CTA's rows can see: j <= q (and j > q - window), q = q_offset + [q0, min(q0 + 128, S))
+        const int qe = sg.q_offset + (q0 + TQ < d.S ? q0 + TQ : d.S);
         hi = qe < hi ? qe : hi;
         if (sg.window > 0) {
-          lo = q0 - sg.window + 1;
-          lo = lo < 0 ? 0 : (lo & ~(TK - 1));
+          lo = sg.q_offset + q0 - sg.window + 1;
+          lo = lo < 0 ? 0 : (lo & ~(TK - 1));  // tile boundaries stay multiples of 64 on the KEY axis for every CTA
         }
       }
       if (hi < 0) hi = 0;
@@ -142,7 +146,12 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     const int total = __shfl_sync(0xffffffffu, off, 3);
     off -= nt;
     for (int i = 0; i < nt && off + i < AT_MAX_TILES; ++i) ctl->tiles[off + i] = (lane << 24) | (lo + i * TK);
-    if (lane == 0) ctl->ntiles = total < AT_MAX_TILES ? total : AT_MAX_TILES;
+    if (lane == 0) {
+      const int all = total < AT_MAX_TILES ? total : AT_MAX_TILES;
+      const int t_lo = all * sp / nsplit, t_hi = all * (sp + 1) / nsplit;  // this CTA's share of the key tiles
+      ctl->t_lo = t_lo;
+      ctl->ntiles = t_hi - t_lo;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -157,6 +166,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     for (int a = 0; a < NA; ++a) tma_load_3d(sQ + a * (Q_BYTES / NA), &maps.q, &ctl->q_full, h * D + a * 64, q0, b);
   }
   const int ntiles = lds_i32(&ctl->ntiles);
+  const int t_lo = lds_i32(&ctl->t_lo);
   const uint32_t tmem_base = (uint32_t)lds_i32(&ctl->tmem_slot);
   if (trace && threadIdx.x == 64) trace[2] = clock64();
 
@@ -165,7 +175,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     if (lane == 0) {
       auto load_kv = [&](int j, bool is_v) {
         const int st = j & 1, u = j >> 1;
-        const int e = lds_i32(&ctl->tiles[j]);
+        const int e = lds_i32(&ctl->tiles[t_lo + j]);
         const int si = e >> 24, n0 = e & 0xFFFFFF;
         const int bm = d.seg[si].batch_mod;
         const int cb = d.seg[si].batch_stride == 0 ? 0 : (bm > 0 ? b % bm : b);  // stride 0: one cache for all rows
@@ -253,7 +263,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     for (int j = 0; j < ntiles; ++j) {
       const int st = j & 1, u = j >> 1;
       // ---- key validity of this tile as a 64-bit mask (before the scores are ready)
-      const int e = lds_i32(&ctl->tiles[j]);
+      const int e = lds_i32(&ctl->tiles[t_lo + j]);
       const int si = e >> 24, n0 = e & 0xFFFFFF;
       const echo_attn_segment& sg = d.seg[si];
       const int hi = lds_i32(&ctl->seg_hi[si]);
@@ -281,9 +291,9 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       int r_lo = 0, r_hi = TK;  // this row's valid key range inside the tile: [r_lo, r_hi)
       bool per_row = false;     // warp-uniform
       if (sg.causal) {
-        const int qw0 = q0 + quarter * 32;  // first query row of the slab
+        const int qw0 = sg.q_offset + q0 + quarter * 32;  // first query row of the slab, on the key axis
         per_row = (n0 + TK - 1 > qw0) || (sg.window > 0 && n0 < qw0 + 31 - sg.window + 1);
-        const int q = q0 + row;
+        const int q = sg.q_offset + q0 + row;
         r_hi = q - n0 + 1;
         if (sg.window > 0) r_lo = q - sg.window + 1 - n0;
       }
@@ -377,13 +387,88 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       tc_fence_after();
     }
     if (trace && threadIdx.x == 64) trace[30] = clock64();
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    // ---- split-KV: park this CTA's un-normalised O row and (max, sum); the last CTA of the group to arrive merges all
+    // shares in share order (deterministic) and alone runs the epilogue
+    bool write_out = true;
+    float w_self[8];   // merge weights 2^(m_i - M) of the shares (nsplit <= 8)
+    float* part_o = nullptr;
+    float l_tot = l_run;
+    if (nsplit > 1) {
+      const size_t group = ((size_t)b * gridDim.y + h) * gridDim.x + blockIdx.x;
+      int* counter = reinterpret_cast<int*>(d.split_ws) + group;
+      float* ml = reinterpret_cast<float*>(static_cast<uint8_t*>(d.split_ws) + AT_COUNTER_BYTES);
+      const size_t n_groups = (size_t)gridDim.x * gridDim.y * d.b;
+      part_o = ml + n_groups * nsplit * (TQ * 2);                        // [group][share][row][D] fp32
+      float* my_ml = ml + (group * nsplit + sp) * (TQ * 2) + row * 2;   // [group][share][row][2]
+      float* my_o = part_o + ((group * nsplit + sp) * TQ + row) * D;
+      __stcg(reinterpret_cast<float2*>(my_ml), make_float2(have ? m_used : -INFINITY, have ? l_run : 0.f));
+      if (have) {
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          float o[32];
+          tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4*>(my_o + c * 32) + i, make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps
+      if (threadIdx.x == 64) {
+        const int prev = atomicAdd(counter, 1);
+        const int last = prev == nsplit - 1;
+        if (last) *counter = 0;  // every share has arrived: leave the counter ready for the next launch
+        ctl->is_last = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      write_out = lds_i32(&ctl->is_last) != 0;
+      if (write_out) {
+        __threadfence();
+        float mx = -INFINITY;
+        float mi[8], li[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          mi[i] = -INFINITY; li[i] = 0.f;
+          if (i < nsplit) {
+            const float2 t = __ldcg(reinterpret_cast<const float2*>(ml + (group * nsplit + i) * (TQ * 2) + row * 2));
+            mi[i] = t.x; li[i] = t.y;
+            if (t.y > 0.f) mx = fmaxf(mx, t.x);
+          }
+        }
+        l_tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          w_self[i] = (li[i] > 0.f) ? fast_exp2(mi[i] - mx) : 0.f;
+          l_tot += w_self[i] * li[i];
+        }
+        part_o += (group * nsplit * TQ + row) * D;  // share i of this row: + i * TQ * D
+      }
+    }
+    if (write_out) {
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
     const uint32_t stg = smem_u32(smem + Q_BYTES + (warp - 2) * (32 * ROWB));  // 32 staged rows, private to this warp; all tiles are dead
     const uint32_t srow = stg + lane * ROWB;
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
       float o[32];
-      if (have) {
+      if (nsplit > 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          if (sidx >= nsplit) break;
+          const float wgt = w_self[sidx];
+          if (wgt > 0.f) {  // a share without keys (or fully masked for this row) parked no O
+            const float4* src = reinterpret_cast<const float4*>(part_o + (size_t)sidx * TQ * D + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t = __ldcg(src + i);
+              o[4 * i] = fmaf(wgt, t.x, o[4 * i]); o[4 * i + 1] = fmaf(wgt, t.y, o[4 * i + 1]);
+              o[4 * i + 2] = fmaf(wgt, t.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(wgt, t.w, o[4 * i + 3]);
+            }
+          }
+        }
+      } else if (have) {
         tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
         tc_wait_ld();
       } else {
@@ -418,6 +503,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off0 + (size_t)(RPI * i) * HD) = val;
       }
     }
+    }  // write_out
   }
 
   if (trace && threadIdx.x == 64) trace[31] = clock64();

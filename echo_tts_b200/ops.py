@@ -88,9 +88,11 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoi
 
 
 def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch.Tensor] = None,
-              scale: Optional[float] = None, trace: Optional[torch.Tensor] = None) -> None:
+              scale: Optional[float] = None, trace: Optional[torch.Tensor] = None,
+              split_ws: Optional[torch.Tensor] = None, nsplit: int = 0) -> None:
     """q: (b, S, H, D) bf16. segments: list of dicts with keys k, v ((b, L, H, D) bf16) and optional mask (b, L) bool,
-    eff_len (b,) int32, pos_limit_mult, pos_limit, causal, window."""
+    eff_len (b,) int32, pos_limit_mult, pos_limit, causal, window, q_offset. split_ws: optional ZEROED uint8 device
+    workspace enabling split-KV (nsplit 0 = auto, n = force)."""
     lib = _lib.load(strict=False)
     b, S, H, D = q.shape
     d = AttnDesc()
@@ -100,6 +102,9 @@ def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch
     d.scale = scale if scale is not None else D ** -0.5
     d.nseg = len(segments)
     d.trace = _ptr(trace)
+    if split_ws is not None:
+        d.split_ws, d.split_ws_bytes = split_ws.data_ptr(), split_ws.numel() * split_ws.element_size()
+    d.nsplit = int(nsplit)
     keep = []
     for i, sg in enumerate(segments):
         k, v = sg["k"], sg["v"]
@@ -117,6 +122,7 @@ def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch
             s.eff_len = e.data_ptr()
         s.pos_limit_mult, s.pos_limit = sg.get("pos_limit_mult", 0), sg.get("pos_limit", 0)
         s.causal, s.window = int(sg.get("causal", 0)), int(sg.get("window", 0))
+        s.q_offset = int(sg.get("q_offset", 0))
         s.batch_mod = int(sg.get("batch_mod", 0))
     _lib.check(lib.echo_op_attention(C.byref(d), _stream()), "echo_op_attention")
 

@@ -248,8 +248,10 @@ typedef struct echo_attn_segment {
   int mask_ld; int mask_stride;   /* key j reads mask[b*mask_ld + j*mask_stride] */
   int pos_limit_mult;             /* >0: key j valid iff j*pos_limit_mult < pos_limit (latent prefix, model.py:243-244) */
   int pos_limit;
-  int causal;                     /* 1: key j valid iff j <= query index (+ window) */
+  int causal;                     /* 1: key j valid iff j <= q (+ window), q = query row + q_offset */
   int window;                     /* >0 with causal: also j > q - window */
+  int q_offset;                   /* causal only: index of query row 0 on this segment's key axis (streaming decode: the
+                                     keys are a growing cache, the queries its newest rows); 0 = plain self attention */
 } echo_attn_segment;
 typedef struct echo_attn_desc {
   const void* Q; int64_t q_batch_stride; int64_t q_row_stride; /* bf16 (b, S, H, D) */
@@ -259,6 +261,15 @@ typedef struct echo_attn_desc {
   float scale;       /* softmax scale, 1/sqrt(D) */
   int nseg; echo_attn_segment seg[4];
   long long* trace;  /* optional device buffer, 64 clock64 stamps per CTA (tcgen05 kernel timeline); NULL normally */
+  /* Split-KV (optional): when one CTA per (128 queries, head, batch row) leaves most SMs idle and every CTA walks a long
+     key list (blockwise S = 160 against ~2700 keys: 32 CTAs x 43 tiles), the key tiles of a CTA are divided over nsplit
+     CTAs; each parks its un-normalised fp32 O and (max, sum) per row in split_ws and the last one to arrive merges them in
+     a fixed order (deterministic) and runs the epilogue. split_ws: device buffer whose first 64 KB (arrival counters)
+     are ZERO before the first use (the kernel leaves them zero); split_ws_bytes its size. nsplit: 0 = auto (1 without a
+     workspace), 1 = off, n = force. */
+  void* split_ws;
+  int64_t split_ws_bytes;
+  int nsplit;
 } echo_attn_desc;
 int echo_op_attention(const echo_attn_desc* d, void* stream);
 

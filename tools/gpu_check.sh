@@ -6,7 +6,7 @@ what=${1:-all}
 shift || true
 mkdir -p gpurun_out
 if [ "$what" = tests ] || [ "$what" = all ]; then
-  timeout 1200 python -m pytest tests -m gpu -x -q -s "$@" > gpurun_out/tests.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q -s "$@" > gpurun_out/tests.log 2>&1
   echo "pytest rc=$?" | tee -a gpurun_out/tests.log
   tail -25 gpurun_out/tests.log
 fi
