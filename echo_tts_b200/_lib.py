@@ -129,6 +129,11 @@ SYMBOLS = {
     "echo_sample_blockwise_stream": (C.c_int, [_P, C.POINTER(SamplerArgs), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int,
                                                _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, BLOCK_CB, _P, _P]),
     "echo_dac_decode": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),
+    "echo_dac_stream_create": (C.c_int, [_P, C.c_int, C.POINTER(_P), _P]),
+    "echo_dac_stream_reset": (C.c_int, [_P, _P, _P]),
+    "echo_dac_stream_decode": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P]),
+    "echo_dac_stream_position": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "echo_dac_stream_destroy": (C.c_int, [_P, _P]),
     "echo_dac_encode_zq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "echo_dac_encode": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),
     "echo_dac_decode_zq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

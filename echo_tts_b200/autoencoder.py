@@ -144,6 +144,10 @@ class B200DAC:
                        "echo_dac_encode")
         return out
 
+    def new_stream(self, max_latents: int = 640) -> "DacStream":
+        """A streaming-decode state for one sequence of up to `max_latents` latents (see `DacStream`)."""
+        return DacStream(self, max_latents)
+
     @torch.inference_mode()
     def decode_latent(self, pca_state: PCAState, z: torch.Tensor) -> torch.Tensor:
         """Fused PCA un-projection + decode: z (B, T, 80) fp32 -> (B, 1, 2048 T) fp32."""
@@ -159,6 +163,61 @@ class B200DAC:
                                                 float(pca_state.latent_scale), B, T, audio.data_ptr(), _stream(dev)),
                        "echo_dac_decode")
         return audio
+
+
+class DacStream:
+    """Stateful streaming decode: feed the latents of ONE sequence block by block, get its audio block by
+    block -- each block costs what its own latents cost, and the samples are bit-identical to an offline
+    `ae_decode` of the whole sequence. The state (the window-128 keys / values of the post_module, the input halos of
+    every causal conv) lives in the library (`echo_dac_stream_*`). One sequence per stream; `reset()` starts a new one."""
+
+    def __init__(self, dac: "B200DAC", max_latents: int = 640):
+        self.dac, self.max_latents = dac, int(max_latents)
+        self.ptr = C.c_void_p()
+        with torch.cuda.device(dac.device):
+            _lib.check(dac.lib.echo_dac_stream_create(dac.h.ptr, self.max_latents, C.byref(self.ptr), _stream(dac.device)),
+                       "echo_dac_stream_create")
+
+    @property
+    def position(self) -> int:
+        n = C.c_int()
+        _lib.check(self.dac.lib.echo_dac_stream_position(self.dac.h.ptr, self.ptr, C.byref(n)), "echo_dac_stream_position")
+        return n.value
+
+    def reset(self) -> None:
+        with torch.cuda.device(self.dac.device):
+            _lib.check(self.dac.lib.echo_dac_stream_reset(self.dac.h.ptr, self.ptr, _stream(self.dac.device)),
+                       "echo_dac_stream_reset")
+
+    @torch.inference_mode()
+    def decode(self, pca_state: PCAState, z: torch.Tensor) -> torch.Tensor:
+        """z (1, T, 80) or (T, 80): the NEXT T latents of the sequence -> (1, 1, 2048 T) fp32, the next samples."""
+        dac, dev = self.dac, self.dac.device
+        zf = z.to(dev, torch.float32).contiguous()
+        if zf.dim() == 2:
+            zf = zf.unsqueeze(0)
+        assert zf.dim() == 3 and zf.shape[0] == 1, "one sequence per stream"
+        T, K = zf.shape[1], zf.shape[2]
+        comps = pca_state.pca_components.to(dev, torch.float32).contiguous()
+        mean = pca_state.pca_mean.to(dev, torch.float32).contiguous()
+        assert comps.shape == (K, dac.cfg.latent_dim)
+        audio = torch.empty(1, 1, T * dac.cfg.hop, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(dac.lib.echo_dac_stream_decode(dac.h.ptr, self.ptr, zf.data_ptr(), comps.data_ptr(), mean.data_ptr(),
+                                                      float(pca_state.latent_scale), T, audio.data_ptr(), _stream(dev)),
+                       "echo_dac_stream_decode")
+        return audio
+
+    def close(self) -> None:
+        if getattr(self, "ptr", None) and self.ptr.value and getattr(self.dac.h, "ptr", None) and self.dac.h.ptr.value:
+            self.dac.lib.echo_dac_stream_destroy(self.dac.h.ptr, self.ptr)
+        self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 @torch.inference_mode()

@@ -28,11 +28,13 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "attention.h"
 #include "common.cuh"
 #include "counters.h"
+#include "gemm.h"
 #include "launch.h"
 #include "profiler.h"
 
@@ -377,7 +379,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     const size_t off0 = ((size_t)b * d.S + q0 + quarter * 32 + rsel) * HD + (size_t)h * D + ch * 8;
     const int rows_ok = d.S - (q0 + quarter * 32);  // rows of this warp's slab inside the sequence
     uint4 gv[NIT];
-    if (d.gate) {
+    if (d.gate && nsplit == 1) {
 #pragma unroll
       for (int i = 0; i < NIT; ++i)
         if (RPI * i + rsel < rows_ok) gv[i] = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + off0 + (size_t)(RPI * i) * HD);
@@ -387,21 +389,24 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       tc_fence_after();
     }
     if (trace && threadIdx.x == 64) trace[30] = clock64();
-    // ---- split-KV: park this CTA's un-normalised O row and (max, sum); the last CTA of the group to arrive merges all
-    // shares in share order (deterministic) and alone runs the epilogue
-    bool write_out = true;
-    float w_self[8];   // merge weights 2^(m_i - M) of the shares (nsplit <= 8)
-    float* part_o = nullptr;
-    float l_tot = l_run;
     if (nsplit > 1) {
+      // ---- split-KV: every share parks its un-normalised O slab and (max, sum) per row; the last CTA of the group to
+      // arrive merges all shares in share order (deterministic) and writes the output. Both directions move whole
+      // 128-byte lines: the O slab is transposed through the (dead) K/V stages so that a warp instruction stores one
+      // full fp32 row, and the merge reads rows the same way (thread-per-row 16-byte accesses ran at ~0.6 TB/s and
+      // made a split launch 2-4x slower than the unsplit kernel, profiles/r02_attn_split_kv.txt).
+      constexpr int ROWF = D * 4;     // bytes of one fp32 O row
+      constexpr int LPR = D / 4;      // lanes per row (one float4 each): 32 (D = 128) / 16 (D = 64)
+      constexpr int RPW = 32 / LPR;   // rows per warp instruction
       const size_t group = ((size_t)b * gridDim.y + h) * gridDim.x + blockIdx.x;
       int* counter = reinterpret_cast<int*>(d.split_ws) + group;
       float* ml = reinterpret_cast<float*>(static_cast<uint8_t*>(d.split_ws) + AT_COUNTER_BYTES);
       const size_t n_groups = (size_t)gridDim.x * gridDim.y * d.b;
-      part_o = ml + n_groups * nsplit * (TQ * 2);                        // [group][share][row][D] fp32
-      float* my_ml = ml + (group * nsplit + sp) * (TQ * 2) + row * 2;   // [group][share][row][2]
-      float* my_o = part_o + ((group * nsplit + sp) * TQ + row) * D;
-      __stcg(reinterpret_cast<float2*>(my_ml), make_float2(have ? m_used : -INFINITY, have ? l_run : 0.f));
+      float* part_o = ml + n_groups * nsplit * (TQ * 2);                          // [group][share][row][D] fp32
+      __stcg(reinterpret_cast<float2*>(ml + (group * nsplit + sp) * (TQ * 2) + row * 2),
+             make_float2(have ? m_used : -INFINITY, have ? l_run : 0.f));          // [group][share][row][2]
+      const uint32_t stgf = smem_u32(smem + Q_BYTES + (warp - 2) * (32 * ROWF));   // this warp's 32 x D fp32 slab
+      const int rsub = lane / LPR, c16 = lane % LPR;
       if (have) {
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
@@ -409,7 +414,16 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
           tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4*>(my_o + c * 32) + i, make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+          for (int j = 0; j < 8; ++j)
+            sts_v4(stgf + lane * ROWF + (((c * 8 + j) ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+        __syncwarp();
+        float* dst = part_o + ((group * nsplit + sp) * TQ + quarter * 32 + rsub) * D + c16 * 4;
+#pragma unroll 4
+        for (int it = 0; it < 32 / RPW; ++it) {
+          const int r = it * RPW + rsub;
+          const float4 t = lds_v4(stgf + r * ROWF + ((c16 ^ (r & 7)) << 4));
+          __stcg(reinterpret_cast<float4*>(dst + (size_t)it * RPW * D), t);
         }
       }
       __threadfence();
@@ -421,11 +435,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         ctl->is_last = last;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      write_out = lds_i32(&ctl->is_last) != 0;
-      if (write_out) {
+      if (lds_i32(&ctl->is_last) != 0) {
         __threadfence();
-        float mx = -INFINITY;
-        float mi[8], li[8];
+        // per-row merge weights 2^(m_i - M) and the total sum, in the thread that owns the row
+        float mx = -INFINITY, mi[8], li[8], wgt[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           mi[i] = -INFINITY; li[i] = 0.f;
@@ -435,40 +448,58 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
             if (t.y > 0.f) mx = fmaxf(mx, t.x);
           }
         }
-        l_tot = 0.f;
+        float l_tot = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          w_self[i] = (li[i] > 0.f) ? fast_exp2(mi[i] - mx) : 0.f;
-          l_tot += w_self[i] * li[i];
+          wgt[i] = (li[i] > 0.f) ? fast_exp2(mi[i] - mx) : 0.f;  // a share without valid keys for this row parked nothing usable
+          l_tot += wgt[i] * li[i];
         }
-        part_o += (group * nsplit * TQ + row) * D;  // share i of this row: + i * TQ * D
+        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        // rows of the slab, RPW at a time: lane (rsub, c16) owns 4 consecutive columns of row it * RPW + rsub
+        const float* src = part_o + (group * nsplit * TQ + quarter * 32 + rsub) * D + c16 * 4;
+        const size_t ooff = ((size_t)b * d.S + q0 + quarter * 32 + rsub) * HD + (size_t)h * D + c16 * 4;
+#pragma unroll 2
+        for (int it = 0; it < 32 / RPW; ++it) {
+          const int r = it * RPW + rsub;
+          // all shares of the row are requested before any is used (unconditionally: behind a branch on the weight the
+          // loads were serialised and the merge ran at one L2 round trip per share and row)
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nsplit) t[i] = __ldcg(reinterpret_cast<const float4*>(src + ((size_t)i * TQ + (size_t)it * RPW) * D));
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < nsplit) {
+              const float w = __shfl_sync(0xffffffffu, wgt[i], r);
+              const bool use = w > 0.f;  // a share that parked nothing for this row holds stale bytes: select, never multiply
+              acc.x = use ? fmaf(w, t[i].x, acc.x) : acc.x; acc.y = use ? fmaf(w, t[i].y, acc.y) : acc.y;
+              acc.z = use ? fmaf(w, t[i].z, acc.z) : acc.z; acc.w = use ? fmaf(w, t[i].w, acc.w) : acc.w;
+            }
+          }
+          const float iv = __shfl_sync(0xffffffffu, inv, r);
+          if (r < rows_ok) {
+            float2 g0 = make_float2(1.f, 1.f), g1 = g0;
+            if (d.gate) {
+              const uint2 gq = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(d.gate) + ooff + (size_t)it * RPW * HD);
+              g0 = unpack_bf16(gq.x); g1 = unpack_bf16(gq.y);
+            }
+            // two roundings like the unsplit path: O / l -> bf16, then (* gate) -> bf16
+            const float2 a0 = unpack_bf16(pack_bf16(acc.x * iv, acc.y * iv)), a1 = unpack_bf16(pack_bf16(acc.z * iv, acc.w * iv));
+            *reinterpret_cast<uint2*>(static_cast<bf16*>(d.out) + ooff + (size_t)it * RPW * HD) =
+                d.gate ? make_uint2(pack_bf16(a0.x * g0.x, a0.y * g0.y), pack_bf16(a1.x * g1.x, a1.y * g1.y))
+                       : make_uint2(pack_bf16(acc.x * iv, acc.y * iv), pack_bf16(acc.z * iv, acc.w * iv));
+          }
+        }
       }
-    }
-    if (write_out) {
-    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    } else {
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const uint32_t stg = smem_u32(smem + Q_BYTES + (warp - 2) * (32 * ROWB));  // 32 staged rows, private to this warp; all tiles are dead
     const uint32_t srow = stg + lane * ROWB;
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
       float o[32];
-      if (nsplit > 1) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
-#pragma unroll
-        for (int sidx = 0; sidx < 8; ++sidx) {
-          if (sidx >= nsplit) break;
-          const float wgt = w_self[sidx];
-          if (wgt > 0.f) {  // a share without keys (or fully masked for this row) parked no O
-            const float4* src = reinterpret_cast<const float4*>(part_o + (size_t)sidx * TQ * D + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 t = __ldcg(src + i);
-              o[4 * i] = fmaf(wgt, t.x, o[4 * i]); o[4 * i + 1] = fmaf(wgt, t.y, o[4 * i + 1]);
-              o[4 * i + 2] = fmaf(wgt, t.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(wgt, t.w, o[4 * i + 3]);
-            }
-          }
-        }
-      } else if (have) {
+      if (have) {
         tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
         tc_wait_ld();
       } else {
@@ -503,7 +534,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off0 + (size_t)(RPI * i) * HD) = val;
       }
     }
-    }  // write_out
+    }  // nsplit == 1
   }
 
   if (trace && threadIdx.x == 64) trace[31] = clock64();
@@ -535,8 +566,15 @@ static int attention_tile_bound(const echo_attn_desc& d) {
   return tiles;
 }
 
+// bytes of split-KV workspace for `groups` (query tile, head, batch row) groups and nsplit shares
+static size_t split_ws_need(size_t groups, int nsplit, int D) {
+  return (size_t)AT_COUNTER_BYTES + groups * nsplit * ((size_t)TQ * 2 * 4 + (size_t)TQ * D * 4);
+}
+
 template <int D>
-static cudaError_t attention_tc_launch_d(const echo_attn_desc& d, cudaStream_t s) {
+static cudaError_t attention_tc_launch_d(const echo_attn_desc& d_in, int nsplit, cudaStream_t s) {
+  echo_attn_desc d = d_in;
+  d.nsplit = nsplit;
   static std::atomic<uint64_t> configured{0};  // per device, see ensure_dyn_smem
   {
     cudaError_t e = ensure_dyn_smem(configured, attn_tc_kernel<D>, at_smem(D));
@@ -557,11 +595,11 @@ static cudaError_t attention_tc_launch_d(const echo_attn_desc& d, cudaStream_t s
       return cudaErrorInvalidValue;
   }
   for (int i = d.nseg; i < 4; ++i) { maps.k[i] = maps.k[0]; maps.v[i] = maps.v[0]; }
-  dim3 grid((d.S + TQ - 1) / TQ, d.H, d.b);
+  dim3 grid((d.S + TQ - 1) / TQ, d.H, d.b * nsplit);
   cudaError_t err;
   {
     char tag[64];
-    if (prof_enabled()) snprintf(tag, sizeof(tag), "attn_tc D=%d b=%d S=%d H=%d nseg=%d", D, d.b, d.S, d.H, d.nseg);
+    if (prof_enabled()) snprintf(tag, sizeof(tag), "attn_tc D=%d b=%d S=%d H=%d nseg=%d split=%d", D, d.b, d.S, d.H, d.nseg, nsplit);
     else tag[0] = 0;
     double keys = 0;  // keys a query can see (upper bound for masked segments)
     for (int i = 0; i < d.nseg; ++i) {
@@ -581,7 +619,30 @@ cudaError_t attention_launch(const echo_attn_desc& d, cudaStream_t s) {
   if (d.b <= 0 || d.S <= 0 || d.H <= 0) return cudaErrorInvalidValue;
   const int tiles = attention_tile_bound(d);
   if (tiles < 0 || tiles > AT_MAX_TILES) return cudaErrorInvalidValue;
-  return d.D == 128 ? attention_tc_launch_d<128>(d, s) : attention_tc_launch_d<64>(d, s);
+  // Split-KV: with few CTAs walking long key lists the kernel is bound by the per-tile latency chain of each CTA
+  // (~0.8 us per 64 keys) while most SMs idle. Divide the key tiles of every (query tile, head, batch row) over
+  // several CTAs until the 2 CTA / SM slots are filled, keeping >= 4 tiles per share.
+  int nsplit = 1;
+  const size_t groups = (size_t)((d.S + TQ - 1) / TQ) * d.H * d.b;
+  static const int env_split = [] { const char* e = std::getenv("ECHO_ATTN_SPLIT"); return e ? atoi(e) : 0; }();  // tuning: 1 = off
+  if (d.split_ws != nullptr && groups * 4 <= (size_t)AT_COUNTER_BYTES && d.nsplit != 1 && env_split != 1) {
+    if (d.nsplit > 1 || env_split > 1) {
+      nsplit = d.nsplit > 1 ? d.nsplit : env_split;
+    } else {
+      const size_t slots = 2 * (size_t)gemm_num_sms();
+      if (groups * 2 <= slots && tiles >= 8) {
+        nsplit = (int)(slots / groups);
+        if (nsplit > tiles / 4) nsplit = tiles / 4;
+      }
+    }
+    if (nsplit > 8) nsplit = 8;
+    if (nsplit > tiles) nsplit = tiles;
+    while (nsplit > 1 && split_ws_need(groups, nsplit, d.D) > (size_t)d.split_ws_bytes) --nsplit;
+    if (nsplit < 1) nsplit = 1;
+  } else if (d.nsplit > 1) {
+    return cudaErrorInvalidValue;  // a forced split needs a workspace
+  }
+  return d.D == 128 ? attention_tc_launch_d<128>(d, nsplit, s) : attention_tc_launch_d<64>(d, nsplit, s);
 }
 
 }  // namespace echo

@@ -126,7 +126,8 @@ __global__ void transpose_ct_kernel(const float* __restrict__ in, float* __restr
 __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ z, const float* __restrict__ w,
                                                         const float* __restrict__ wb, const float* __restrict__ lnw,
                                                         const float* __restrict__ lnb, bf16* __restrict__ out, int T,
-                                                        int C) {
+                                                        int C, int halo) {
+  // halo > 0 (streaming decode, one batch item): `halo` rows of the previous block sit in front of z's row 0
   pdl_wait();
   pdl_trigger();
   __shared__ float sh[32];
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int tt = t - 6 + j;
-      if (tt >= 0) acc = fmaf(w[c * 7 + j], z[((size_t)row - 6 + j) * C + c], acc);
+      if (tt >= -halo) acc = fmaf(w[c * 7 + j], z[((int64_t)row - 6 + j) * C + c], acc);
     }
     y[cnt] = acc;
     s1 += acc;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
 
 // final: audio[b, t] = tanh(bias + sum_j sum_c w[j][c] * sx[b, t - 6 + j, c])     (autoencoder.py:994)
 __global__ void __launch_bounds__(256) final_conv_tanh_kernel(const bf16* __restrict__ sx, const float* __restrict__ w,
-                                                              float bias, float* __restrict__ audio, int T, int C) {
+                                                              float bias, float* __restrict__ audio, int T, int C, int halo) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sw[];  // [7][C]
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(256) final_conv_tanh_kernel(const bf16* __rest
   float acc = bias;
   for (int j = 0; j < 7; ++j) {
     const int tt = t - 6 + j;
-    if (tt < 0) continue;
-    const uint4* rp = reinterpret_cast<const uint4*>(base + (size_t)tt * C);
+    if (tt < -halo) continue;  // halo rows of the previous block (streaming) sit in front of row 0
+    const uint4* rp = reinterpret_cast<const uint4*>(base + (int64_t)tt * C);
     const float* wj = sw + j * C;
     for (int c8 = 0; c8 < C / 8; ++c8) {
       const uint4 u = __ldg(rp + c8);
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(256) final_conv_tanh_kernel(const bf16* __rest
 // diagonal entries. Every activation byte is read once: the kernel is bound by the 252 MB it has to read.
 template <int CS>
 __global__ void __launch_bounds__(256) final_conv_tanh_rows_kernel(const bf16* __restrict__ sx, const float* __restrict__ w,
-                                                                   float bias, float* __restrict__ audio, int T) {
+                                                                   float bias, float* __restrict__ audio, int T, int halo) {
   pdl_wait();
   pdl_trigger();
   constexpr int C = 8 * CS, TB = 256, ROWS = TB + 6;
@@ -236,9 +237,9 @@ __global__ void __launch_bounds__(256) final_conv_tanh_rows_kernel(const bf16* _
     const int r = r0 + grp;          // row of this block's window
     const int tt = t0 - 6 + r;       // time index (negative: causal zero padding)
     float x[CS];
-    const bool live = r < ROWS && tt >= 0 && tt < T;
+    const bool live = r < ROWS && tt >= -halo && tt < T;
     if (live) {
-      const uint2* rp = reinterpret_cast<const uint2*>(base + (size_t)tt * C + slice * CS);
+      const uint2* rp = reinterpret_cast<const uint2*>(base + (int64_t)tt * C + slice * CS);
 #pragma unroll
       for (int q = 0; q < CS / 4; ++q) {
         const uint2 u = __ldg(rp + q);
@@ -894,12 +895,18 @@ struct TfBuffers { bf16 *XN, *Q, *K, *V, *AO, *Hh; };
 // place): pre-RMSNorm, fused QKV with RoPE on all heads, causal window attention, LayerScale residuals, SwiGLU.
 // Shared by quantizer.post_module / pre_module (window 128) and the last EncoderBlock (window 512). The final
 // RMSNorm (:607) is left to the caller (its output format differs per use).
+// Streaming (kcache != nullptr, B == 1): the T rows are positions pos .. pos + T - 1 of a longer sequence; layer i's
+// keys / values are appended to kcache[i] / vcache[i] ((max_T, C) bf16, rows < pos written by earlier blocks) and the
+// attention runs the T newest rows against the whole cache (causal + window with q_offset = pos).
 int run_window_transformer(echo_handle* h, const std::vector<DacPostLayerW>& layers, float* X, int B, int T, int C, int I,
-                           int H, int window, float eps, const TfBuffers& tb, cudaStream_t s) {
+                           int H, int window, float eps, const TfBuffers& tb, cudaStream_t s,
+                           bf16* const* kcache = nullptr, bf16* const* vcache = nullptr, int pos = 0) {
   const int rows = B * T;
-  bf16 *XN = tb.XN, *Q = tb.Q, *K = tb.K, *V = tb.V, *AO = tb.AO, *Hh = tb.Hh;
+  bf16 *XN = tb.XN, *Q = tb.Q, *AO = tb.AO, *Hh = tb.Hh;
   for (size_t i = 0; i < layers.size(); ++i) {
     const DacPostLayerW& w = layers[i];
+    bf16* K = kcache ? kcache[i] + (size_t)pos * C : tb.K;
+    bf16* V = vcache ? vcache[i] + (size_t)pos * C : tb.V;
     rmsnorm_affine(X, XN, w.attn_norm, nullptr, rows, C, 0, 0, eps, s);
     {
       GemmCall g = base_gemm(XN, C, w.wqkv, C, 1, rows, 3 * C, C, 1);
@@ -908,7 +915,7 @@ int run_window_transformer(echo_handle* h, const std::vector<DacPostLayerW>& lay
       g.p.sec[1] = {K, nullptr, 1 << 20, 0};
       g.p.sec[2] = {V, nullptr, 0, 0};
       g.p.sec_width = C; g.p.rope_cos = h->dac_rope_cos; g.p.rope_sin = h->dac_rope_sin; g.p.head_dim = 64;
-      g.p.pos_period = T; g.p.eps = eps;
+      g.p.pos_period = T; g.p.pos_offset = pos; g.p.eps = eps;
       DAC_GEMM(g);
     }
     {
@@ -916,8 +923,10 @@ int run_window_transformer(echo_handle* h, const std::vector<DacPostLayerW>& lay
       std::memset(&a, 0, sizeof(a));
       a.Q = Q; a.q_batch_stride = (int64_t)T * C; a.q_row_stride = C; a.out = AO;
       a.b = B; a.S = T; a.H = H; a.D = 64; a.scale = 0.125f; a.nseg = 1;
-      a.seg[0].K = K; a.seg[0].V = V; a.seg[0].batch_stride = (int64_t)T * C; a.seg[0].row_stride = C;
-      a.seg[0].len = T; a.seg[0].causal = 1; a.seg[0].window = window; a.seg[0].mask_stride = 1;
+      a.seg[0].K = kcache ? kcache[i] : K; a.seg[0].V = vcache ? vcache[i] : V;
+      a.seg[0].batch_stride = (int64_t)(pos + T) * C; a.seg[0].row_stride = C;
+      a.seg[0].len = pos + T; a.seg[0].q_offset = pos;
+      a.seg[0].causal = 1; a.seg[0].window = window; a.seg[0].mask_stride = 1;
       cudaError_t er = attention_launch(a, s);
       if (er != cudaSuccess) { set_error("dac attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
     }
@@ -943,10 +952,41 @@ int run_window_transformer(echo_handle* h, const std::vector<DacPostLayerW>& lay
   return ECHO_OK;
 }
 
-int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int B, int T, float* audio, cudaStream_t s) {
+}  // namespace
+
+// State of one streaming decode: what the causal decoder has to remember between blocks of latents.
+//   * quantizer.post_module: the keys / values of every layer for all latents so far (window-128 causal attention,
+//     autoencoder.py:762-773) -- (max_T, C) bf16 per layer, the attention reads the last 127 rows + the new block;
+//   * every causal conv with a receptive field into the past (autoencoder.py:285-289, left pad (k-1)*d): its last
+//     (k-1)*d input rows ("halo"): the ConvNeXt depthwise convs (6 rows fp32), decoder conv0 (6), each stage's transposed
+//     conv (1), the dilated conv7 of every ResidualUnit (6, 18, 54) and the final conv7 (6).
+// All halos start as zeros == the causal zero padding at the start of the sequence.
+struct echo_dac_stream {
+  int max_T = 0, pos = 0;
+  std::vector<bf16*> K, V;            // [post_layers]
+  std::vector<float*> dw_halo;        // [num_upsample]  6 x C fp32
+  bf16* conv0_halo = nullptr;         // 6 x C
+  std::vector<bf16*> convt_halo;      // [num_rates]     1 x cin
+  std::vector<bf16*> ru_halo;         // [num_rates * 3] 6 * dil x cout
+  bf16* final_halo = nullptr;         // 6 x C_last
+  std::vector<std::pair<void*, size_t>> bufs;  // every allocation (for reset / destroy)
+};
+
+namespace {
+
+constexpr int64_t DAC_HALO_ELEMS = 64 * 1536;  // headroom in front of every bf16 activation buffer: >= 54 rows x 768 ch
+
+// One decode. Offline (st == nullptr): B x T latents -> B x hop*T samples. Streaming (st != nullptr, B == 1): the next
+// T latents of the stream -> the next hop*T samples, bit-identical to the same samples of an offline decode of the
+// whole sequence: every kernel computes an output row from the same inputs in the same order, the rows a conv needs
+// from before the block come from the halos instead of the same buffer.
+int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int B, int T, float* audio, cudaStream_t s,
+            echo_dac_stream* st = nullptr) {
   const echo_dac_config& c = h->dcfg;
   const int C = c.latent_dim, I = c.post_intermediate, H = c.post_heads, rows = B * T;
   if (T > 4096) { set_error("dac: T=%d exceeds the post_module block size 4096", T); return ECHO_ERR_ARG; }
+  if (st && B != 1) { set_error("dac stream: one batch item per stream"); return ECHO_ERR_ARG; }
+  if (st && st->pos + T > st->max_T) { set_error("dac stream: %d + %d latents exceed the stream's capacity %d", st->pos, T, st->max_T); return ECHO_ERR_ARG; }
   // sizes of the largest activations
   int64_t max_elems = (int64_t)rows * C * 4;  // ConvNeXt hidden
   {
@@ -956,22 +996,48 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
     max_elems = std::max<int64_t>(max_elems, (int64_t)B * t * ch);
     for (int i = 0; i < c.num_rates; ++i) { t *= c.rates[i]; ch /= 2; max_elems = std::max<int64_t>(max_elems, (int64_t)B * t * ch); }
   }
+  const int64_t HR = DAC_HALO_ELEMS;  // halo headroom (elements) in front of row 0 of xa / sa / sb
   bf16* XN = (bf16*)h->wsget("dac.XN", (size_t)rows * C * 2, s);
   bf16* Q = (bf16*)h->wsget("dac.Q", (size_t)rows * C * 2, s);
   bf16* K = (bf16*)h->wsget("dac.K", (size_t)rows * C * 2, s);
   bf16* V = (bf16*)h->wsget("dac.V", (size_t)rows * C * 2, s);
   bf16* AO = (bf16*)h->wsget("dac.AO", (size_t)rows * C * 2, s);
   bf16* Hh = (bf16*)h->wsget("dac.Hh", (size_t)rows * I * 2, s);
-  float* xa = (float*)h->wsget("dac.xa", (size_t)max_elems * 4, s);
-  bf16* sa = (bf16*)h->wsget("dac.sa", (size_t)max_elems * 2, s);
-  bf16* sb = (bf16*)h->wsget("dac.sb", (size_t)max_elems * 2, s);
+  float* xa = (float*)h->wsget("dac.xa", (size_t)(max_elems + HR) * 4, s);
+  bf16* sa = (bf16*)h->wsget("dac.sa", (size_t)(max_elems + HR) * 2, s);
+  bf16* sb = (bf16*)h->wsget("dac.sb", (size_t)(max_elems + HR) * 2, s);
   bf16* hb = (bf16*)h->wsget("dac.hb", (size_t)max_elems * 2, s);
   if (!XN || !Q || !K || !V || !AO || !Hh || !xa || !sa || !sb || !hb) { set_error("dac: workspace allocation failed"); return ECHO_ERR_CUDA; }
+  xa += HR; sa += HR; sb += HR;
   const float eps = c.post_norm_eps;
+
+  // halo plumbing (streaming only): `rows0` is row 0 of the block in a buffer of row width W; the h rows in front of it
+  // are loaded from the stream state before the consumer runs and the last h rows of [halo | block] saved after it
+#define DAC_HALO_IN(rows0, store, hrows, W, esz)                                                                         \
+  do {                                                                                                                   \
+    if (st) ECHO_CUDA(cudaMemcpyAsync((char*)(rows0) - (size_t)(hrows) * (W) * (esz), (store), (size_t)(hrows) * (W) * (esz),   \
+                                      cudaMemcpyDeviceToDevice, s));                                                     \
+  } while (0)
+#define DAC_HALO_OUT(rows0, store, hrows, W, esz, nrows)                                                                 \
+  do {                                                                                                                   \
+    if (st) ECHO_CUDA(cudaMemcpyAsync((store), (char*)(rows0) + ((int64_t)(nrows) - (hrows)) * (W) * (esz),              \
+                                      (size_t)(hrows) * (W) * (esz), cudaMemcpyDeviceToDevice, s));                      \
+  } while (0)
+  // a conv / transposed-conv GEMM whose A rows start `hrows` rows before the block (tap shifts become >= 0)
+  auto with_halo = [&](GemmCall g, const bf16* rows0, int hrows, int n) {
+    if (st && hrows > 0) {
+      g.A = rows0 - (size_t)hrows * g.lda;
+      for (int j = 0; j < g.p.taps; ++j) g.p.tap_shift[j] += hrows;
+      g.a_rows = hrows + n;
+      g.a_batch_stride = (int64_t)(hrows + n) * g.lda;
+    }
+    return g;
+  };
 
   // ---- quantizer.post_module (autoencoder.py:786-802, 621-626)
   TfBuffers tb{XN, Q, K, V, AO, Hh};
-  ECHO_TRY(run_window_transformer(h, h->post, X, B, T, C, I, H, c.post_window, eps, tb, s));
+  ECHO_TRY(run_window_transformer(h, h->post, X, B, T, C, I, H, c.post_window, eps, tb, s, st ? st->K.data() : nullptr,
+                                  st ? st->V.data() : nullptr, st ? st->pos : 0));
   rmsnorm_affine(X, sa, h->post_final_norm, nullptr, rows, C, 0, 0, eps, s);  // sa = post_module output, bf16
 
   // ---- quantizer.upsample (autoencoder.py:427-435): [ConvTranspose k2 s2 ; ConvNeXt] per stage
@@ -987,8 +1053,10 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
     }
     Tc *= 2;
     const int r2 = B * Tc;
-    launch_k(dwconv_ln_kernel, dim3(r2), dim3(256), 0, s, 1, xa, u.dw_w, u.dw_b, u.ln_w, u.ln_b, nxt, Tc, C);
+    if (st) DAC_HALO_IN(xa, st->dw_halo[i], 6, C, 4);
+    launch_k(dwconv_ln_kernel, dim3(r2), dim3(256), 0, s, 1, xa, u.dw_w, u.dw_b, u.ln_w, u.ln_b, nxt, Tc, C, st ? 6 : 0);
     count_launch();
+    if (st) DAC_HALO_OUT(xa, st->dw_halo[i], 6, C, 4, Tc);  // before the ConvNeXt output overwrites xa below
     {
       GemmCall g = base_gemm(nxt, C, u.w1, C, 1, r2, 4 * C, C, 1);
       g.p.bias = u.b1; g.p.out_bf16 = hb; g.p.ld_bf16 = 4 * C; g.p.act = ACT_GELU;
@@ -1005,47 +1073,59 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
 
   // ---- decoder (autoencoder.py:984-998)
   {
-    GemmCall g = conv_gemm(h->dec_conv0, cur, B, Tc, 1);
+    if (st) DAC_HALO_IN(cur, st->conv0_halo, 6, C, 2);
+    GemmCall g = with_halo(conv_gemm(h->dec_conv0, cur, B, Tc, 1), cur, 6, Tc);
     g.p.out_bf16 = nxt; g.p.ld_bf16 = h->dec_conv0.n; g.p.act = ACT_SNAKE; g.p.alpha = h->stage[0].alpha_in; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
     DAC_GEMM(g);
+    if (st) DAC_HALO_OUT(cur, st->conv0_halo, 6, C, 2, Tc);
   }
   std::swap(cur, nxt);  // cur = snake(conv0 out), channels decoder_dim
   for (int b = 0; b < c.num_rates; ++b) {
-    const DacStageW& st = h->stage[b];
+    const DacStageW& stg = h->stage[b];
     {
-      GemmCall g = convt_gemm(st.convt, cur, B, Tc, st.cout);
-      g.p.out_f32 = xa; g.p.ld_f32 = st.stride * st.cout;
-      g.p.out_bf16 = nxt; g.p.ld_bf16 = st.stride * st.cout; g.p.act = ACT_SNAKE; g.p.alpha = st.ru[0].alpha1; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
+      if (st) DAC_HALO_IN(cur, st->convt_halo[b], 1, stg.cin, 2);
+      GemmCall g = with_halo(convt_gemm(stg.convt, cur, B, Tc, stg.cout), cur, 1, Tc);
+      g.p.out_f32 = xa; g.p.ld_f32 = stg.stride * stg.cout;
+      g.p.out_bf16 = nxt; g.p.ld_bf16 = stg.stride * stg.cout; g.p.act = ACT_SNAKE; g.p.alpha = stg.ru[0].alpha1; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
       DAC_GEMM(g);
+      if (st) DAC_HALO_OUT(cur, st->convt_halo[b], 1, stg.cin, 2, Tc);
     }
-    Tc *= st.stride;
+    Tc *= stg.stride;
     std::swap(cur, nxt);  // cur = snake1(x) for residual unit 0
     static const int dil[3] = {1, 3, 9};
     for (int u = 0; u < 3; ++u) {
-      const DacResUnitW& ru = st.ru[u];
+      const DacResUnitW& ru = stg.ru[u];
       {
-        GemmCall g = conv_gemm(ru.conv7, cur, B, Tc, dil[u]);
-        g.p.out_bf16 = hb; g.p.ld_bf16 = st.cout; g.p.act = ACT_SNAKE; g.p.alpha = ru.alpha2; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
+        const int hr = 6 * dil[u];
+        if (st) DAC_HALO_IN(cur, st->ru_halo[3 * b + u], hr, stg.cout, 2);
+        GemmCall g = with_halo(conv_gemm(ru.conv7, cur, B, Tc, dil[u]), cur, hr, Tc);
+        g.p.out_bf16 = hb; g.p.ld_bf16 = stg.cout; g.p.act = ACT_SNAKE; g.p.alpha = ru.alpha2; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
         DAC_GEMM(g);
+        if (st) DAC_HALO_OUT(cur, st->ru_halo[3 * b + u], hr, stg.cout, 2, Tc);
       }
       {
-        const float* next_alpha = (u < 2) ? st.ru[u + 1].alpha1
+        const float* next_alpha = (u < 2) ? stg.ru[u + 1].alpha1
                                   : (b + 1 < c.num_rates ? h->stage[b + 1].alpha_in : h->final_alpha);
         GemmCall g = conv_gemm(ru.conv1, hb, B, Tc, 1);
-        g.p.resid = xa; g.p.out_f32 = xa; g.p.ld_f32 = st.cout;
-        g.p.out_bf16 = cur; g.p.ld_bf16 = st.cout; g.p.act = ACT_SNAKE; g.p.alpha = next_alpha; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
+        g.p.resid = xa; g.p.out_f32 = xa; g.p.ld_f32 = stg.cout;
+        g.p.out_bf16 = cur; g.p.ld_bf16 = stg.cout; g.p.act = ACT_SNAKE; g.p.alpha = next_alpha; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
         DAC_GEMM(g);
       }
     }
   }
   const int Cl = h->stage.back().cout;
   dim3 grid((Tc + 255) / 256, B);
+  if (st) DAC_HALO_IN(cur, st->final_halo, 6, Cl, 2);
   if (Cl == 96)
-    launch_k(final_conv_tanh_rows_kernel<12>, dim3(grid), dim3(256), 0, s, 1, cur, h->final_w, h->final_b, audio, Tc);
+    launch_k(final_conv_tanh_rows_kernel<12>, dim3(grid), dim3(256), 0, s, 1, cur, h->final_w, h->final_b, audio, Tc, st ? 6 : 0);
   else
-    launch_k(final_conv_tanh_kernel, dim3(grid), dim3(256), 7 * Cl * sizeof(float), s, 1, cur, h->final_w, h->final_b, audio, Tc, Cl);
+    launch_k(final_conv_tanh_kernel, dim3(grid), dim3(256), 7 * Cl * sizeof(float), s, 1, cur, h->final_w, h->final_b, audio, Tc, Cl, st ? 6 : 0);
   count_launch();
+  if (st) DAC_HALO_OUT(cur, st->final_halo, 6, Cl, 2, Tc);
   ECHO_CUDA(cudaGetLastError());
+  if (st) st->pos += T;
+#undef DAC_HALO_IN
+#undef DAC_HALO_OUT
   return ECHO_OK;
 }
 
@@ -1070,6 +1150,89 @@ extern "C" int echo_dac_decode(echo_handle* h, const float* z, const float* pca_
   launch_k(pca_unproject_kernel, dim3(B * T), dim3(256), Kp * sizeof(float), s, 1, z, pca_components, pca_mean, latent_scale, X, Kp, C);
   count_launch();
   return dac_run(h, X, B, T, audio, s);
+}
+
+// ------------------------------------------------------------------------------------------------ streaming decode
+extern "C" int echo_dac_stream_reset(echo_handle* h, echo_dac_stream* st, void* stream) {
+  ECHO_TRY(dac_check(h, "echo_dac_stream_reset"));
+  if (!st) { set_error("echo_dac_stream_reset: null stream"); return ECHO_ERR_ARG; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
+  // halos = zeros (the causal left padding at the start of a sequence); the KV caches need no clearing: rows >= pos are
+  // never read
+  for (size_t i = 2 * st->K.size(); i < st->bufs.size(); ++i) ECHO_CUDA(cudaMemsetAsync(st->bufs[i].first, 0, st->bufs[i].second, s));
+  st->pos = 0;
+  return ECHO_OK;
+}
+
+extern "C" int echo_dac_stream_create(echo_handle* h, int max_latents, echo_dac_stream** out, void* stream) {
+  ECHO_TRY(dac_check(h, "echo_dac_stream_create"));
+  if (!out || max_latents <= 0 || max_latents > 4096) { set_error("echo_dac_stream_create: bad argument (max_latents 1..4096)"); return ECHO_ERR_ARG; }
+  const echo_dac_config& c = h->dcfg;
+  const int C = c.latent_dim;
+  echo_dac_stream* st = new echo_dac_stream();
+  st->max_T = max_latents;
+  bool ok = true;
+  auto alloc = [&](size_t bytes) -> void* {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { ok = false; return nullptr; }
+    st->bufs.push_back({p, bytes});
+    return p;
+  };
+  for (int i = 0; i < c.post_layers; ++i) st->K.push_back((bf16*)alloc((size_t)max_latents * C * 2));
+  for (int i = 0; i < c.post_layers; ++i) st->V.push_back((bf16*)alloc((size_t)max_latents * C * 2));
+  // (the first 2 * post_layers entries of bufs are the KV caches -- echo_dac_stream_reset skips them)
+  for (int i = 0; i < c.num_upsample; ++i) st->dw_halo.push_back((float*)alloc((size_t)6 * C * 4));
+  st->conv0_halo = (bf16*)alloc((size_t)6 * C * 2);
+  static const int dil[3] = {1, 3, 9};
+  for (int b = 0; b < c.num_rates; ++b) {
+    st->convt_halo.push_back((bf16*)alloc((size_t)h->stage[b].cin * 2));
+    for (int u = 0; u < 3; ++u) st->ru_halo.push_back((bf16*)alloc((size_t)6 * dil[u] * h->stage[b].cout * 2));
+  }
+  st->final_halo = (bf16*)alloc((size_t)6 * h->stage.back().cout * 2);
+  if (!ok) {
+    for (auto& b : st->bufs) cudaFree(b.first);
+    delete st;
+    set_error("echo_dac_stream_create: out of device memory");
+    return ECHO_ERR_CUDA;
+  }
+  h->dac_streams.insert(st);
+  int rc = echo_dac_stream_reset(h, st, stream);
+  if (rc != ECHO_OK) return rc;
+  *out = st;
+  return ECHO_OK;
+}
+
+extern "C" int echo_dac_stream_destroy(echo_handle* h, echo_dac_stream* st) {
+  if (!h || !st) return ECHO_OK;
+  std::lock_guard<std::recursive_mutex> g(h->mu);
+  if (!h->dac_streams.erase(st)) { set_error("echo_dac_stream_destroy: unknown stream"); return ECHO_ERR_ARG; }
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& b : st->bufs) cudaFree(b.first);
+  delete st;
+  return ECHO_OK;
+}
+
+extern "C" int echo_dac_stream_decode(echo_handle* h, echo_dac_stream* st, const float* z, const float* pca_components,
+                                      const float* pca_mean, float latent_scale, int T, float* audio, void* stream) {
+  ECHO_TRY(dac_check(h, "echo_dac_stream_decode"));
+  if (!st || !z || !pca_components || !pca_mean || !audio || T <= 0) { set_error("echo_dac_stream_decode: bad argument"); return ECHO_ERR_ARG; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HandleScope scope(h, s);
+  if (!h->dac_streams.count(st)) { set_error("echo_dac_stream_decode: unknown stream"); return ECHO_ERR_ARG; }
+  const int C = h->dcfg.latent_dim, Kp = h->dcfg.pca_dim;
+  float* X = (float*)h->wsget("dac.X", (size_t)T * C * 4, s);
+  if (!X) { set_error("dac: out of memory"); return ECHO_ERR_CUDA; }
+  launch_k(pca_unproject_kernel, dim3(T), dim3(256), Kp * sizeof(float), s, 1, z, pca_components, pca_mean, latent_scale, X, Kp, C);
+  count_launch();
+  return dac_run(h, X, 1, T, audio, s, st);
+}
+
+extern "C" int echo_dac_stream_position(echo_handle* h, echo_dac_stream* st, int* latents_decoded) {
+  if (!h || !st || !latents_decoded) { set_error("echo_dac_stream_position: bad argument"); return ECHO_ERR_ARG; }
+  *latents_decoded = st->pos;
+  return ECHO_OK;
 }
 
 extern "C" int echo_dac_decode_zq(echo_handle* h, const float* zq, int B, int T, float* audio, void* stream) {
@@ -1209,7 +1372,7 @@ int dac_encode_run(echo_handle* h, const float* audio, int B, int L, float* zq_r
       DAC_GEMM(g);
     }
     Tc = To;
-    launch_k(dwconv_ln_kernel, dim3(r2), dim3(256), 0, s, 1, xa, u.dw_w, u.dw_b, u.ln_w, u.ln_b, nxt, Tc, C);
+    launch_k(dwconv_ln_kernel, dim3(r2), dim3(256), 0, s, 1, xa, u.dw_w, u.dw_b, u.ln_w, u.ln_b, nxt, Tc, C, 0);
     count_launch();
     {
       GemmCall g = base_gemm(nxt, C, u.w1, C, 1, r2, 4 * C, C, 1);

@@ -268,7 +268,7 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   const int64_t a_bstride = c.a_batch_stride ? c.a_batch_stride : (int64_t)p.M * c.lda;
 
   CUtensorMap ma, mb;
-  if (!get_tensor_map(&ma, c.A, 3, (uint64_t)p.Kc, (uint64_t)p.M, (uint64_t)a_batches, (uint64_t)c.lda * 2,
+  if (!get_tensor_map(&ma, c.A, 3, (uint64_t)p.Kc, (uint64_t)(c.a_rows > 0 ? c.a_rows : p.M), (uint64_t)a_batches, (uint64_t)c.lda * 2,
                       (uint64_t)a_bstride * 2, bk, GEMM_BM, bk * 2))
     return cudaErrorInvalidValue;
   const uint64_t b_rows = c.b_rows ? (uint64_t)c.b_rows : (uint64_t)p.N * (p.b_batch_rows ? p.batches : 1);

@@ -74,6 +74,8 @@ struct GemmCall {
   const bf16* A;           // [a_batches][M][lda] bf16, K contiguous
   int64_t lda;             // elements
   int64_t a_batch_stride;  // elements; 0 -> M*lda
+  int64_t a_rows;          // rows of A per batch item the TMA map may touch; 0 -> M. Larger when A carries a halo of
+                           // earlier rows in front of the M output rows (streaming convs: tap_shift is then >= 0)
   const bf16* B;           // [b_rows][ldb] bf16, K contiguous (nn.Linear weight layout)
   int64_t ldb;
   int64_t b_rows;  // 0 -> N (or N*batches when b_batch_rows is set)

@@ -147,6 +147,7 @@ struct echo_handle {
   std::vector<echo::DacPostLayerW> pre;
   float* pre_final_norm = nullptr;
   std::vector<echo::DacVqW> vq;  // [0] semantic, [1 ..] residual
+  std::set<echo_dac_stream*> dac_streams;  // live streaming-decode states (freed by echo_destroy if the caller did not)
 
   // ---- serialisation of the public entry points (see echo::HandleScope)
   std::recursive_mutex mu;
@@ -156,6 +157,7 @@ struct echo_handle {
   cudaEvent_t order_ev = nullptr;
 
   void* wsget(const char* name, size_t bytes, cudaStream_t s);
+  void* wsget_zeroed(const char* name, size_t bytes, cudaStream_t s, size_t* got);
   void* dalloc(size_t bytes);
 };
 

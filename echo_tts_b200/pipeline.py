@@ -288,33 +288,41 @@ def stream_blockwise_audio(model, fish_ae, pca_state, sample_blockwise_fn: Calla
                            **sampler_kwargs):
     """Streaming synthesis: audio of block i is decoded while block i + 1 is being sampled.
     `sample_blockwise_fn` is the blockwise sampler (or a functools.partial of it, as handler._build_sample_fn would
-    build). The DAC is exactly causal, so decoding the finished prefix and keeping the new samples equals decoding
-    everything at the end. Returns (final_latents, [(audio_block (1, 1, n) fp32 on the device, ready_event), ...]);
-    `ready_event` completes when that block's audio is final -- for the first block long before the sampler has
-    finished. The call itself returns once everything is enqueued (the CUDA launch queue back-pressures the host), so
-    a consumer that wants the early blocks polls the events from another thread or from `on_audio`.
+    build). Every finished block of latents goes through a STATEFUL streaming decode (`B200DAC.new_stream`: the decoder
+    is exactly causal; the stream carries the window-128 attention keys / values and the conv halos), so a block costs
+    what its own latents cost and the samples are bit-identical to decoding everything at the end.
+    Returns (final_latents, [(audio_block (B, 1, n) fp32 on the device, ready_event), ...]); `ready_event` completes
+    when that block's audio is final -- for the first block long before the sampler has finished. The call itself
+    returns once everything is enqueued (the CUDA launch queue back-pressures the host), so a consumer that wants the
+    early blocks polls the events from another thread or from `on_audio`.
     `on_audio(index, audio_block, ready_event)` (optional) is invoked on the host right after block `index`'s decode
-    has been enqueued."""
-    from .autoencoder import ae_decode
-    hop = getattr(getattr(fish_ae, "cfg", None), "hop", AE_DOWNSAMPLE_FACTOR)
+    has been enqueued. A `continuation_latent` is decoded first (its audio is not returned: the caller already has it)
+    so that the stream state matches the prefix."""
     blocks = []
-    # size the decoder workspace for the longest prefix up front: growing it mid-stream would synchronise the stream
-    total = sum(block_sizes) + (sampler_kwargs["continuation_latent"].shape[1]
-                                if sampler_kwargs.get("continuation_latent") is not None else 0)
-    if getattr(fish_ae, "_reserved_latents", 0) < total * text_input_ids.shape[0]:
-        ae_decode(fish_ae, pca_state, torch.zeros(text_input_ids.shape[0], total, 80, device=model.device))
-        fish_ae._reserved_latents = total * text_input_ids.shape[0]
+    B = text_input_ids.shape[0]
+    cont = sampler_kwargs.get("continuation_latent")
+    total = sum(block_sizes) + (cont.shape[1] if cont is not None else 0)
+    streams = [fish_ae.new_stream(total) for _ in range(B)]
+    try:
+        if cont is not None and cont.shape[1] > 0:
+            for b, st in enumerate(streams):
+                st.decode(pca_state, cont[b:b + 1])
 
-    def on_block(index, start, length, prefix):
-        audio = ae_decode(fish_ae, pca_state, prefix[:, : start + length])  # enqueued behind the block's kernels
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        blocks.append((audio[..., start * hop:], ev))
-        if on_audio is not None:
-            on_audio(index, blocks[-1][0], ev)
+        def on_block(index, start, length, prefix):
+            # enqueued behind the block's kernels; one stream (= one sequence) per batch item
+            audio = torch.cat([st.decode(pca_state, prefix[b:b + 1, start:start + length]) for b, st in enumerate(streams)])
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            blocks.append((audio, ev))
+            if on_audio is not None:
+                on_audio(index, audio, ev)
 
-    latents = sample_blockwise_fn(model, speaker_latent, speaker_mask, text_input_ids, text_mask, rng_seed,
-                                  list(block_sizes), on_block=on_block, **sampler_kwargs)
+        latents = sample_blockwise_fn(model, speaker_latent, speaker_mask, text_input_ids, text_mask, rng_seed,
+                                      list(block_sizes), on_block=on_block, **sampler_kwargs)
+    finally:
+        torch.cuda.current_stream(model.device).synchronize()  # the states are freed below: nothing may still use them
+        for st in streams:
+            st.close()
     return latents, blocks
 
 

@@ -186,6 +186,20 @@ int echo_dac_decode(echo_handle* h, const float* z, const float* pca_components,
 /* == DAC.decode_zq: zq (B,1024,T) fp32 channels-first. */
 int echo_dac_decode_zq(echo_handle* h, const float* zq, int B, int T, float* audio, void* stream);
 
+/* ---- streaming DAC decode (reference gradio_app.py:43 "decode chunk-wise", the blockwise sampler writes
+ * its blocks back one by one, inference_blockwise.py:120-123). A stream carries what the causal decoder remembers
+ * between blocks -- the window-128 keys / values of the 8 post_module layers (autoencoder.py:762-773) and the (k-1)*d
+ * input rows in front of every causal conv (autoencoder.py:285-289) -- so decoding the latents block by block costs the
+ * same as decoding them once and produces BIT-IDENTICAL samples. One batch item per stream; max_latents <= 4096.
+ *   echo_dac_stream_decode : z (1, T, 80) fp32 = the next T latents; audio (1, 1, 2048*T) fp32 = the next samples. */
+typedef struct echo_dac_stream echo_dac_stream;
+int echo_dac_stream_create(echo_handle* h, int max_latents, echo_dac_stream** out, void* stream);
+int echo_dac_stream_reset(echo_handle* h, echo_dac_stream* st, void* stream);  /* start a new sequence */
+int echo_dac_stream_decode(echo_handle* h, echo_dac_stream* st, const float* z, const float* pca_components,
+                           const float* pca_mean, float latent_scale, int T, float* audio, void* stream);
+int echo_dac_stream_position(echo_handle* h, echo_dac_stream* st, int* latents_decoded);
+int echo_dac_stream_destroy(echo_handle* h, echo_dac_stream* st);
+
 /* ---- Fish S1-DAC encode: replaces inference.ae_encode (inference.py:219-224) / DAC.encode_zq (autoencoder.py:1080-1126)
  * audio: (B, 1, L) fp32 on the device, L a multiple of the frame length (enc hop * 2^num_upsample = 2048; the caller
  * right-pads with zeros as DAC.encode does). T = L / frame length.

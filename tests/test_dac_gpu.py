@@ -82,3 +82,54 @@ def test_dac_full_T640_vs_reference():
     print(f"dac T=640 whole-waveform rel-L2 {e:.3e}; per tenth max {max(tenths):.3e}")
     assert e < AUDIO_TOL, e
     assert max(tenths) < AUDIO_TOL, tenths
+
+
+@pytest.mark.parametrize("which,blocks", [("tiny", [5, 1, 7, 3]), ("tiny", [16]), ("full", [160, 160, 160, 160]), ("full", [3, 200, 77])])
+def test_dac_streaming_decode_is_bit_identical_to_offline(which, blocks):
+    """the stateful streaming decode (window-128 K/V carry of the post_module, conv halos of every causal
+    conv; autoencoder.py:285-289, 762-773) returns, block by block, exactly the samples of the offline decode of the
+    whole sequence -- including ragged block sizes smaller than a conv's receptive field -- and a stream can be
+    reset and reused."""
+    from echo_tts_b200.autoencoder import ae_decode
+    cfg = DacConfig.tiny() if which == "tiny" else DacConfig.base()
+    dac, pca = _build(cfg)
+    T = sum(blocks)
+    z = torch.randn(1, T, 80, generator=torch.Generator().manual_seed(21))
+    full = ae_decode(dac, pca, z)
+    st = dac.new_stream(T)
+    for attempt in range(2):
+        parts, pos = [], 0
+        for b in blocks:
+            parts.append(st.decode(pca, z[:, pos:pos + b]))
+            pos += b
+            assert st.position == pos
+        streamed = torch.cat(parts, dim=-1)
+        assert streamed.shape == full.shape
+        assert torch.equal(streamed, full), (which, blocks, attempt, rel_l2(streamed, full))
+        st.reset()
+    with pytest.raises(Exception):
+        for _ in range(2):
+            st.decode(pca, z)  # the second call exceeds the stream's capacity
+    st.close()
+
+
+def test_dac_streaming_block_cost_is_constant():
+    """Decoding the 4th block of 160 latents must launch exactly as many kernels as decoding the 1st (round 1 re-decoded
+    the whole prefix: 160 + 320 + 480 + 640 latents of work)."""
+    cfg = DacConfig.base()
+    dac, pca = _build(cfg)
+    z = torch.randn(1, 640, 80, generator=torch.Generator().manual_seed(22))
+    st = dac.new_stream(640)
+    counts, times = [], []
+    for i in range(4):
+        n0 = dac.h.num_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st.decode(pca, z[:, 160 * i:160 * (i + 1)])
+        e1.record()
+        torch.cuda.synchronize()
+        counts.append(dac.h.num_launches() - n0)
+        times.append(e0.elapsed_time(e1))
+    print("streaming decode of 4 x 160 latents: launches per block", counts, "ms per block", [round(t, 2) for t in times])
+    assert len(set(counts)) == 1
+    assert times[3] < 1.5 * times[1] + 0.2
