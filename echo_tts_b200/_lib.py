@@ -89,7 +89,7 @@ class AttnDesc(C.Structure):
         ("gate", C.c_void_p), ("out", C.c_void_p),
         ("b", C.c_int), ("S", C.c_int), ("H", C.c_int), ("D", C.c_int), ("scale", C.c_float),
         ("nseg", C.c_int), ("seg", AttnSegment * 4), ("trace", C.c_void_p),
-        ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_int64), ("nsplit", C.c_int),
+        ("nsplit", C.c_int),
     ]
 
 

@@ -50,7 +50,9 @@ constexpr int AT_MAX_TILES = 120;
 __host__ __device__ constexpr int at_q_bytes(int D) { return TQ * D * 2; }
 __host__ __device__ constexpr int at_slot(int D) { return TK * D * 2; }
 __host__ __device__ constexpr int at_tile_bytes(int D) { return at_q_bytes(D) + 4 * at_slot(D); }  // 96 KB (D = 128) / 48 KB
-__host__ __device__ constexpr int at_smem(int D) { return at_tile_bytes(D) + 1024 /*align slack*/ + 1024 /*barriers + tile list*/; }
+__host__ __device__ constexpr int at_smem(int D) {
+  return at_tile_bytes(D) + 1024 /*align slack*/ + 1024 /*barriers + tile list*/ + 1024 /*split-KV: (max, sum) per row*/;
+}
 constexpr float RESCALE_LOG2 = 8.f;  // O is rescaled only when a row max grows by more than 2^8
 
 struct AttnMaps {
@@ -62,13 +64,11 @@ struct AttnMaps {
 struct SmemCtl {
   uint64_t q_full, k_full[2], v_full[2], s_full[2], p_ready[2], pv_done[2];
   uint32_t tmem_slot;
-  int ntiles;   // tiles of THIS CTA (its share of the list when the keys are split over several CTAs)
+  int ntiles;   // tiles of THIS CTA (its share of the list when the keys are split over a cluster)
   int t_lo;     // first list entry of this CTA
-  int is_last;  // split-KV: this CTA arrived last and merges
   int seg_hi[4];
   int tiles[AT_MAX_TILES];
 };
-constexpr int AT_COUNTER_BYTES = 64 * 1024;  // arrival counters at the start of the split-KV workspace
 static_assert(sizeof(SmemCtl) <= 1024, "control block");
 
 template <int D>
@@ -86,8 +86,9 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   auto sV = [&](int st) { return smem + Q_BYTES + st * STAGE + KSLOT; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // split-KV: a cluster of nsplit CTAs (consecutive blockIdx.x) shares one (query tile, head, batch row)
   const int nsplit = d.nsplit > 1 ? d.nsplit : 1;
-  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = (int)blockIdx.z / nsplit, sp = (int)blockIdx.z % nsplit;
+  const int q0 = ((int)blockIdx.x / nsplit) * TQ, h = blockIdx.y, b = blockIdx.z, sp = (int)blockIdx.x % nsplit;
   // timeline (tuning): 0 entry, 1 setup done, 2 tile list done, 3 Q landed (MMA thread), 4+2j / 5+2j = softmax of
   // tile j starts (scores ready) / ends (P published), 30 O complete, 31 epilogue done   -- stamps of warp 2 lane 0
   long long* trace = d.trace ? d.trace + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -162,12 +163,12 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   pdl_wait();
   pdl_trigger();
   if (trace && threadIdx.x == 64) trace[1] = clock64();
-  if (warp == 0 && lane == 0) {  // Q first; the K / V tiles follow from the producer loop below without another barrier
-    mbar_expect_tx(&ctl->q_full, Q_BYTES);
+  const int ntiles = lds_i32(&ctl->ntiles);
+  if (warp == 0 && lane == 0 && ntiles > 0) {  // Q first; the K / V tiles follow from the producer loop below without another barrier
+    mbar_expect_tx(&ctl->q_full, Q_BYTES);       // (a share without tiles loads nothing: no TMA may be in flight when it exits)
 #pragma unroll
     for (int a = 0; a < NA; ++a) tma_load_3d(sQ + a * (Q_BYTES / NA), &maps.q, &ctl->q_full, h * D + a * 64, q0, b);
   }
-  const int ntiles = lds_i32(&ctl->ntiles);
   const int t_lo = lds_i32(&ctl->t_lo);
   const uint32_t tmem_base = (uint32_t)lds_i32(&ctl->tmem_slot);
   if (trace && threadIdx.x == 64) trace[2] = clock64();
@@ -390,23 +391,14 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     }
     if (trace && threadIdx.x == 64) trace[30] = clock64();
     if (nsplit > 1) {
-      // ---- split-KV: every share parks its un-normalised O slab and (max, sum) per row; the last CTA of the group to
-      // arrive merges all shares in share order (deterministic) and writes the output. Both directions move whole
-      // 128-byte lines: the O slab is transposed through the (dead) K/V stages so that a warp instruction stores one
-      // full fp32 row, and the merge reads rows the same way (thread-per-row 16-byte accesses ran at ~0.6 TB/s and
-      // made a split launch 2-4x slower than the unsplit kernel, profiles/r02_attn_split_kv.txt).
-      constexpr int ROWF = D * 4;     // bytes of one fp32 O row
-      constexpr int LPR = D / 4;      // lanes per row (one float4 each): 32 (D = 128) / 16 (D = 64)
-      constexpr int RPW = 32 / LPR;   // rows per warp instruction
-      const size_t group = ((size_t)b * gridDim.y + h) * gridDim.x + blockIdx.x;
-      int* counter = reinterpret_cast<int*>(d.split_ws) + group;
-      float* ml = reinterpret_cast<float*>(static_cast<uint8_t*>(d.split_ws) + AT_COUNTER_BYTES);
-      const size_t n_groups = (size_t)gridDim.x * gridDim.y * d.b;
-      float* part_o = ml + n_groups * nsplit * (TQ * 2);                          // [group][share][row][D] fp32
-      __stcg(reinterpret_cast<float2*>(ml + (group * nsplit + sp) * (TQ * 2) + row * 2),
-             make_float2(have ? m_used : -INFINITY, have ? l_run : 0.f));          // [group][share][row][2]
-      const uint32_t stgf = smem_u32(smem + Q_BYTES + (warp - 2) * (32 * ROWF));   // this warp's 32 x D fp32 slab
-      const int rsub = lane / LPR, c16 = lane % LPR;
+      // ---- split-KV, part 1: this share's un-normalised O slab goes into its own shared memory (over the dead K / V
+      // stages) as bf16 -- the merge reads it through distributed shared memory, which moves only ~20 B / clk / SM, so
+      // the slab is kept small (fp32 slabs made the merge of a 3-way split take 5 us) -- and the fp32 (max, sum) per row
+      // behind the control block. bf16 has fp32's exponent range: the lazily rescaled O (up to 2^8 x #keys) cannot overflow.
+      constexpr int ROWS = D * 2;  // bytes of one staged row
+      const uint32_t slab = smem_u32(smem + Q_BYTES);
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(smem_u32(smem + TILE_BYTES + 1024) + row * 8), "f"(have ? m_used : -INFINITY),
+                   "f"(have ? l_run : 0.f) : "memory");
       if (have) {
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
@@ -414,84 +406,13 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
           tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts_v4(stgf + lane * ROWF + (((c * 8 + j) ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        }
-        __syncwarp();
-        float* dst = part_o + ((group * nsplit + sp) * TQ + quarter * 32 + rsub) * D + c16 * 4;
-#pragma unroll 4
-        for (int it = 0; it < 32 / RPW; ++it) {
-          const int r = it * RPW + rsub;
-          const float4 t = lds_v4(stgf + r * ROWF + ((c16 ^ (r & 7)) << 4));
-          __stcg(reinterpret_cast<float4*>(dst + (size_t)it * RPW * D), t);
+          for (int j = 0; j < 4; ++j)
+            sts_u4(slab + row * ROWS + (((c * 4 + j) ^ (row & 7)) << 4),
+                   make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                              pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7])));
         }
       }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps
-      if (threadIdx.x == 64) {
-        const int prev = atomicAdd(counter, 1);
-        const int last = prev == nsplit - 1;
-        if (last) *counter = 0;  // every share has arrived: leave the counter ready for the next launch
-        ctl->is_last = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (lds_i32(&ctl->is_last) != 0) {
-        __threadfence();
-        // per-row merge weights 2^(m_i - M) and the total sum, in the thread that owns the row
-        float mx = -INFINITY, mi[8], li[8], wgt[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          mi[i] = -INFINITY; li[i] = 0.f;
-          if (i < nsplit) {
-            const float2 t = __ldcg(reinterpret_cast<const float2*>(ml + (group * nsplit + i) * (TQ * 2) + row * 2));
-            mi[i] = t.x; li[i] = t.y;
-            if (t.y > 0.f) mx = fmaxf(mx, t.x);
-          }
-        }
-        float l_tot = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          wgt[i] = (li[i] > 0.f) ? fast_exp2(mi[i] - mx) : 0.f;  // a share without valid keys for this row parked nothing usable
-          l_tot += wgt[i] * li[i];
-        }
-        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-        // rows of the slab, RPW at a time: lane (rsub, c16) owns 4 consecutive columns of row it * RPW + rsub
-        const float* src = part_o + (group * nsplit * TQ + quarter * 32 + rsub) * D + c16 * 4;
-        const size_t ooff = ((size_t)b * d.S + q0 + quarter * 32 + rsub) * HD + (size_t)h * D + c16 * 4;
-#pragma unroll 2
-        for (int it = 0; it < 32 / RPW; ++it) {
-          const int r = it * RPW + rsub;
-          // all shares of the row are requested before any is used (unconditionally: behind a branch on the weight the
-          // loads were serialised and the merge ran at one L2 round trip per share and row)
-          float4 t[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nsplit) t[i] = __ldcg(reinterpret_cast<const float4*>(src + ((size_t)i * TQ + (size_t)it * RPW) * D));
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < nsplit) {
-              const float w = __shfl_sync(0xffffffffu, wgt[i], r);
-              const bool use = w > 0.f;  // a share that parked nothing for this row holds stale bytes: select, never multiply
-              acc.x = use ? fmaf(w, t[i].x, acc.x) : acc.x; acc.y = use ? fmaf(w, t[i].y, acc.y) : acc.y;
-              acc.z = use ? fmaf(w, t[i].z, acc.z) : acc.z; acc.w = use ? fmaf(w, t[i].w, acc.w) : acc.w;
-            }
-          }
-          const float iv = __shfl_sync(0xffffffffu, inv, r);
-          if (r < rows_ok) {
-            float2 g0 = make_float2(1.f, 1.f), g1 = g0;
-            if (d.gate) {
-              const uint2 gq = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(d.gate) + ooff + (size_t)it * RPW * HD);
-              g0 = unpack_bf16(gq.x); g1 = unpack_bf16(gq.y);
-            }
-            // two roundings like the unsplit path: O / l -> bf16, then (* gate) -> bf16
-            const float2 a0 = unpack_bf16(pack_bf16(acc.x * iv, acc.y * iv)), a1 = unpack_bf16(pack_bf16(acc.z * iv, acc.w * iv));
-            *reinterpret_cast<uint2*>(static_cast<bf16*>(d.out) + ooff + (size_t)it * RPW * HD) =
-                d.gate ? make_uint2(pack_bf16(a0.x * g0.x, a0.y * g0.y), pack_bf16(a1.x * g1.x, a1.y * g1.y))
-                       : make_uint2(pack_bf16(acc.x * iv, acc.y * iv), pack_bf16(acc.z * iv, acc.w * iv));
-          }
-        }
-      }
+      if (trace && threadIdx.x == 64) trace[24] = clock64();
     } else {
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     const uint32_t stg = smem_u32(smem + Q_BYTES + (warp - 2) * (32 * ROWB));  // 32 staged rows, private to this warp; all tiles are dead
@@ -537,6 +458,122 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     }  // nsplit == 1
   }
 
+  if (nsplit > 1) {
+    // ---- split-KV, part 2. Every thread of the cluster arrives here once its share is staged. CTA `sp` then merges
+    // rows [128 sp / nsplit, 128 (sp + 1) / nsplit) of the query tile from the nsplit slabs (its own and its peers',
+    // read through DSMEM) in share order -- no global workspace, no atomics, bit-reproducible -- and writes them.
+    constexpr int ROWS = D * 2;    // bytes of one staged bf16 row
+    constexpr int LPR = D / 8;     // lanes per row, 8 columns (16 bytes) each: 16 (D = 128) / 8 (D = 64)
+    constexpr int RPW = 32 / LPR;  // rows per warp instruction
+    constexpr int MAXIT = (TQ / 2) / (4 * RPW);  // rows a lane handles at most (nsplit = 2: 64 rows over 4 warps)
+    const int r_lo = TQ * sp / nsplit, r_hi = TQ * (sp + 1) / nsplit;
+    const int rsub = lane / LPR, c16 = lane % LPR;
+    const size_t HDm = (size_t)d.H * D;
+    // the gate of this CTA's output rows does not depend on the peers: requested before the barrier (one exposed L2 round
+    // trip per row otherwise -- the first version of this merge took 10 us for 43 rows, profiles/r02_attn_split_kv.txt)
+    uint4 gq[MAXIT];
+    if (warp >= 2 && d.gate) {
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it) {
+        const int r = r_lo + (warp - 2) * RPW + rsub + it * 4 * RPW;
+        if (r < r_hi && q0 + r < d.S)
+          gq[it] = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + ((size_t)b * d.S + q0 + r) * HDm + (size_t)h * D + c16 * 8);
+      }
+    }
+    cluster_sync_all();
+    if (trace && threadIdx.x == 64) trace[25] = clock64();
+    if (warp >= 2) {
+      const uint32_t ml_local = smem_u32(smem + TILE_BYTES + 1024), slab_local = smem_u32(smem + Q_BYTES);
+      const uint32_t wtab = smem_u32(sQ);  // [row of the slice][8] normalised merge weights (Q is dead; empty shares never loaded it)
+      uint32_t slab_peer[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) slab_peer[i] = dsmem_addr(slab_local, i < nsplit ? i : 0);
+      // ---- phase A: one thread per row of the slice turns the shares' (max, sum) into normalised weights
+      {
+        const int rr = (warp - 2) * 32 + lane;
+        if (rr < r_hi - r_lo) {
+          float2 ml[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nsplit) ml[i] = ld_dsmem_v2(dsmem_addr(ml_local, i) + (r_lo + rr) * 8);
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nsplit && ml[i].y > 0.f) mx = fmaxf(mx, ml[i].x);
+          float w[8], l_tot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            w[i] = (i < nsplit && ml[i].y > 0.f) ? fast_exp2(ml[i].x - mx) : 0.f;  // a share without a valid key for this row: weight 0
+            l_tot = fmaf(w[i], i < nsplit ? ml[i].y : 0.f, l_tot);
+          }
+          const float iv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+          sts_v4(wtab + rr * 32, w[0] * iv, w[1] * iv, w[2] * iv, w[3] * iv);
+          sts_v4(wtab + rr * 32 + 16, w[4] * iv, w[5] * iv, w[6] * iv, w[7] * iv);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps
+      // ---- phase B: warp w takes rows r_lo + (w - 2) * RPW + rsub + it * 4 * RPW; two rows (x up to 8 shares) in flight
+#pragma unroll
+      for (int it0 = 0; it0 < MAXIT; it0 += 2) {
+        uint4 t[2][8];
+        int rws[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          rws[u] = r_lo + (warp - 2) * RPW + rsub + (it0 + u) * 4 * RPW;
+          if (rws[u] < r_hi) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < nsplit) {
+                const float4 f = ld_dsmem_v4(slab_peer[i] + rws[u] * ROWS + ((c16 ^ (rws[u] & 7)) << 4));
+                t[u][i] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = rws[u];
+          if (r < r_hi) {
+            const float4 w0 = lds_v4(wtab + (r - r_lo) * 32), w1 = lds_v4(wtab + (r - r_lo) * 32 + 16);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < nsplit && w[i] > 0.f) {  // a share that staged nothing usable for this row holds stale bytes: skip, never multiply
+                const uint32_t* tv = reinterpret_cast<const uint32_t*>(&t[u][i]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = unpack_bf16(tv[k]);
+                  acc[2 * k] = fmaf(w[i], f.x, acc[2 * k]);
+                  acc[2 * k + 1] = fmaf(w[i], f.y, acc[2 * k + 1]);
+                }
+              }
+            }
+            if (q0 + r < d.S) {
+              const size_t ooff = ((size_t)b * d.S + q0 + r) * HDm + (size_t)h * D + c16 * 8;
+              // two roundings like the unsplit path: O / l -> bf16, then (* gate) -> bf16
+              uint32_t val[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) val[k] = pack_bf16(acc[2 * k], acc[2 * k + 1]);
+              if (d.gate) {
+                const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gq[it0 + u]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 a = unpack_bf16(val[k]), g = unpack_bf16(gi[k]);
+                  val[k] = pack_bf16(a.x * g.x, a.y * g.y);
+                }
+              }
+              *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + ooff) = make_uint4(val[0], val[1], val[2], val[3]);
+            }
+          }
+        }
+      }
+    }
+    if (trace && threadIdx.x == 64) trace[26] = clock64();
+    cluster_sync_all();  // no CTA may exit (and free its shared memory) while a peer still reads it
+  }
   if (trace && threadIdx.x == 64) trace[31] = clock64();
   tc_fence_before();
   __syncthreads();
@@ -566,11 +603,6 @@ static int attention_tile_bound(const echo_attn_desc& d) {
   return tiles;
 }
 
-// bytes of split-KV workspace for `groups` (query tile, head, batch row) groups and nsplit shares
-static size_t split_ws_need(size_t groups, int nsplit, int D) {
-  return (size_t)AT_COUNTER_BYTES + groups * nsplit * ((size_t)TQ * 2 * 4 + (size_t)TQ * D * 4);
-}
-
 template <int D>
 static cudaError_t attention_tc_launch_d(const echo_attn_desc& d_in, int nsplit, cudaStream_t s) {
   echo_attn_desc d = d_in;
@@ -595,7 +627,7 @@ static cudaError_t attention_tc_launch_d(const echo_attn_desc& d_in, int nsplit,
       return cudaErrorInvalidValue;
   }
   for (int i = d.nseg; i < 4; ++i) { maps.k[i] = maps.k[0]; maps.v[i] = maps.v[0]; }
-  dim3 grid((d.S + TQ - 1) / TQ, d.H, d.b * nsplit);
+  dim3 grid(((d.S + TQ - 1) / TQ) * nsplit, d.H, d.b);  // the nsplit shares of a query tile are one cluster along x
   cudaError_t err;
   {
     char tag[64];
@@ -607,7 +639,7 @@ static cudaError_t attention_tc_launch_d(const echo_attn_desc& d_in, int nsplit,
       keys += g.causal ? (g.window > 0 && g.window < d.S ? (double)g.window : 0.5 * d.S) : (double)g.len;
     }
     ProfScope ps(PROF_ATTN, 4.0 * d.b * d.H * (double)d.S * keys * D, 0.0, s, tag);
-    err = launch_k(attn_tc_kernel<D>, grid, dim3(AT_THREADS), (size_t)at_smem(D), s, 1, maps, d);
+    err = launch_k(attn_tc_kernel<D>, grid, dim3(AT_THREADS), (size_t)at_smem(D), s, nsplit, maps, d);
   }
   count_launch();
   return err;
@@ -620,14 +652,17 @@ cudaError_t attention_launch(const echo_attn_desc& d, cudaStream_t s) {
   const int tiles = attention_tile_bound(d);
   if (tiles < 0 || tiles > AT_MAX_TILES) return cudaErrorInvalidValue;
   // Split-KV: with few CTAs walking long key lists the kernel is bound by the per-tile latency chain of each CTA
-  // (~0.8 us per 64 keys) while most SMs idle. Divide the key tiles of every (query tile, head, batch row) over
-  // several CTAs until the 2 CTA / SM slots are filled, keeping >= 4 tiles per share.
+  // (~0.7 us per 64 keys) while most SMs idle. The key tiles of every (query tile, head, batch row) are then divided
+  // over a thread-block cluster of nsplit CTAs (<= 8), which merge their partial (O, max, sum) through distributed
+  // shared memory. Auto: fill the 2 CTA / SM slots, keep >= 4 tiles per share; the merge costs ~2-3 us.
   int nsplit = 1;
   const size_t groups = (size_t)((d.S + TQ - 1) / TQ) * d.H * d.b;
   static const int env_split = [] { const char* e = std::getenv("ECHO_ATTN_SPLIT"); return e ? atoi(e) : 0; }();  // tuning: 1 = off
-  if (d.split_ws != nullptr && groups * 4 <= (size_t)AT_COUNTER_BYTES && d.nsplit != 1 && env_split != 1) {
-    if (d.nsplit > 1 || env_split > 1) {
-      nsplit = d.nsplit > 1 ? d.nsplit : env_split;
+  if (d.nsplit > 1) {
+    nsplit = d.nsplit;
+  } else if (d.nsplit == 0 && env_split != 1) {
+    if (env_split > 1) {
+      nsplit = env_split;
     } else {
       const size_t slots = 2 * (size_t)gemm_num_sms();
       if (groups * 2 <= slots && tiles >= 8) {
@@ -635,13 +670,10 @@ cudaError_t attention_launch(const echo_attn_desc& d, cudaStream_t s) {
         if (nsplit > tiles / 4) nsplit = tiles / 4;
       }
     }
-    if (nsplit > 8) nsplit = 8;
-    if (nsplit > tiles) nsplit = tiles;
-    while (nsplit > 1 && split_ws_need(groups, nsplit, d.D) > (size_t)d.split_ws_bytes) --nsplit;
-    if (nsplit < 1) nsplit = 1;
-  } else if (d.nsplit > 1) {
-    return cudaErrorInvalidValue;  // a forced split needs a workspace
   }
+  if (nsplit > 8) nsplit = 8;
+  if (nsplit > tiles) nsplit = tiles;
+  if (nsplit < 1) nsplit = 1;
   return d.D == 128 ? attention_tc_launch_d<128>(d, nsplit, s) : attention_tc_launch_d<64>(d, nsplit, s);
 }
 

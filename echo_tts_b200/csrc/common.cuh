@@ -132,6 +132,23 @@ ECHO_DEVICE void mbar_arrive_pair_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// ---- distributed shared memory: the same shared-space offset in another CTA of the cluster
+ECHO_DEVICE uint32_t dsmem_addr(uint32_t saddr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta_rank));
+  return r;
+}
+ECHO_DEVICE float4 ld_dsmem_v4(uint32_t caddr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(caddr) : "memory");
+  return v;
+}
+ECHO_DEVICE float2 ld_dsmem_v2(uint32_t caddr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(caddr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int NCOLS>
 ECHO_DEVICE void tmem_alloc(uint32_t* smem_dst) {

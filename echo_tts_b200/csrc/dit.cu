@@ -43,17 +43,6 @@ void* echo_handle::wsget(const char* name, size_t bytes, cudaStream_t s) {
   return b.p;
 }
 
-// A named workspace whose bytes are zero when it is (re)allocated; callers that keep it zero between uses (the split-KV
-// arrival counters) never pay for clearing it again. *got = the usable size (>= bytes), or 0 on failure.
-void* echo_handle::wsget_zeroed(const char* name, size_t bytes, cudaStream_t s, size_t* got) {
-  DevBuf& b = ws[name];
-  const bool fresh = b.bytes < bytes;
-  void* p = wsget(name, bytes, s);
-  if (p && fresh && cudaMemsetAsync(p, 0, ws[name].bytes, s) != cudaSuccess) p = nullptr;
-  if (got) *got = p ? ws[name].bytes : 0;
-  return p;
-}
-
 extern "C" int echo_create(echo_handle** out, int device) {
   if (!out) { set_error("echo_create: null out"); return ECHO_ERR_ARG; }
   int n = 0;
@@ -649,9 +638,6 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
   const bool planes_ok = f.layer_out == nullptr && f.layer_mid == nullptr && D % 128 == 0 && (nv == 2 || nv == 4 || nv == 8 || nv == 10 || nv == 16) &&
                          !(f.rows_per_group > 0 && f.rows_per_group % 32 != 0) && rows <= 1280;
   float* part = planes_ok ? (float*)h->wsget("dit.part", (size_t)4 * rows * D * 4, s) : nullptr;
-  // split-KV workspace of the joint attention (used when few query tiles face long key lists: blockwise / plain steps)
-  size_t split_bytes = 0;
-  void* split_ws = h->wsget_zeroed("attn.split", (size_t)48 << 20, s, &split_bytes);
   const int64_t part_stride = (int64_t)rows * D;
   int pending = 0;  // planes waiting to be folded into X by the next norm
   auto gated_accum = [&](const bf16* A, int lda, const bf16* W, int ldw, int K, const float* gate) -> int {
@@ -704,7 +690,6 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
         ++ns;
       }
       a.nseg = ns;
-      a.split_ws = split_ws; a.split_ws_bytes = (int64_t)split_bytes;
       cudaError_t er = attention_launch(a, s);
       if (er != cudaSuccess) { set_error("joint attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
     }

@@ -157,7 +157,6 @@ struct echo_handle {
   cudaEvent_t order_ev = nullptr;
 
   void* wsget(const char* name, size_t bytes, cudaStream_t s);
-  void* wsget_zeroed(const char* name, size_t bytes, cudaStream_t s, size_t* got);
   void* dalloc(size_t bytes);
 };
 

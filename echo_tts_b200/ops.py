@@ -88,11 +88,10 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoi
 
 
 def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch.Tensor] = None,
-              scale: Optional[float] = None, trace: Optional[torch.Tensor] = None,
-              split_ws: Optional[torch.Tensor] = None, nsplit: int = 0) -> None:
+              scale: Optional[float] = None, trace: Optional[torch.Tensor] = None, nsplit: int = 0) -> None:
     """q: (b, S, H, D) bf16. segments: list of dicts with keys k, v ((b, L, H, D) bf16) and optional mask (b, L) bool,
-    eff_len (b,) int32, pos_limit_mult, pos_limit, causal, window, q_offset. split_ws: optional ZEROED uint8 device
-    workspace enabling split-KV (nsplit 0 = auto, n = force)."""
+    eff_len (b,) int32, pos_limit_mult, pos_limit, causal, window, q_offset. nsplit: split-KV over a cluster of CTAs
+    (0 = auto, 1 = off, 2..8 = force)."""
     lib = _lib.load(strict=False)
     b, S, H, D = q.shape
     d = AttnDesc()
@@ -102,8 +101,6 @@ def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch
     d.scale = scale if scale is not None else D ** -0.5
     d.nseg = len(segments)
     d.trace = _ptr(trace)
-    if split_ws is not None:
-        d.split_ws, d.split_ws_bytes = split_ws.data_ptr(), split_ws.numel() * split_ws.element_size()
     d.nsplit = int(nsplit)
     keep = []
     for i, sg in enumerate(segments):

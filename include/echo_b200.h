@@ -275,14 +275,10 @@ typedef struct echo_attn_desc {
   float scale;       /* softmax scale, 1/sqrt(D) */
   int nseg; echo_attn_segment seg[4];
   long long* trace;  /* optional device buffer, 64 clock64 stamps per CTA (tcgen05 kernel timeline); NULL normally */
-  /* Split-KV (optional): when one CTA per (128 queries, head, batch row) leaves most SMs idle and every CTA walks a long
-     key list (blockwise S = 160 against ~2700 keys: 32 CTAs x 43 tiles), the key tiles of a CTA are divided over nsplit
-     CTAs; each parks its un-normalised fp32 O and (max, sum) per row in split_ws and the last one to arrive merges them in
-     a fixed order (deterministic) and runs the epilogue. split_ws: device buffer whose first 64 KB (arrival counters)
-     are ZERO before the first use (the kernel leaves them zero); split_ws_bytes its size. nsplit: 0 = auto (1 without a
-     workspace), 1 = off, n = force. */
-  void* split_ws;
-  int64_t split_ws_bytes;
+  /* Split-KV: when one CTA per (128 queries, head, batch row) leaves most SMs idle and every CTA walks a long key list
+     (blockwise S = 160 against ~2700 keys: 32 CTAs x 43 tiles), the key tiles are divided over a thread-block cluster
+     of nsplit CTAs that merge their partial (O, max, sum) through distributed shared memory in a fixed order
+     (deterministic; no workspace, no atomics). 0 = auto, 1 = off, 2..8 = force. */
   int nsplit;
 } echo_attn_desc;
 int echo_op_attention(const echo_attn_desc* d, void* stream);

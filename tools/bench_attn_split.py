@@ -23,17 +23,16 @@ def run(name, b, S, H, D, segs_len, eff=None, iters=200):
         segs.append(sg)
     gate = rnd((b, S, H * D), 4)
     out = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
-    ws = torch.zeros(48 << 20, dtype=torch.uint8, device="cuda")
     res = []
     for ns in (1, 2, 3, 4, 6, 8, 0):
         for _ in range(3):
-            ops.attention(q, segs, out, gate=gate, split_ws=ws, nsplit=ns)
+            ops.attention(q, segs, out, gate=gate, nsplit=ns)
         torch.cuda.synchronize()
         # a CUDA graph of 20 back-to-back launches: the Python / ctypes call costs more than the kernel
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for _ in range(20):
-                ops.attention(q, segs, out, gate=gate, split_ws=ws, nsplit=ns)
+                ops.attention(q, segs, out, gate=gate, nsplit=ns)
         g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from echo_tts_b200 import ops  # noqa: E402
 
 dev = "cuda"
+NS = int(sys.argv[1]) if len(sys.argv) > 1 else 1  # split-KV shares (1 = off)
 for b in (1, 3):
     S, H, Dh = 640, 16, 128
     q = torch.randn(b, S, H, Dh, device=dev).bfloat16()
@@ -20,19 +21,21 @@ for b in (1, 3):
     eff = torch.tensor([36, 0, 36][:b], dtype=torch.int32, device=dev)
     effs = torch.tensor([53, 53, 0][:b], dtype=torch.int32, device=dev)
     segs = [dict(k=k, v=v), dict(k=kt, v=kt, eff_len=eff, batch_mod=1), dict(k=ks, v=ks, eff_len=effs, batch_mod=1)]
-    ncta = 5 * H * b
+    ncta = 5 * H * b * NS
     trace = torch.zeros(ncta * 64, dtype=torch.int64, device=dev)
     for _ in range(3):
-        ops.attention(q, segs, out, gate=g, trace=trace)
+        ops.attention(q, segs, out, gate=g, trace=trace, nsplit=NS)
     torch.cuda.synchronize()
     trace.zero_()
-    ops.attention(q, segs, out, gate=g, trace=trace)
+    ops.attention(q, segs, out, gate=g, trace=trace, nsplit=NS)
     torch.cuda.synchronize()
     t = trace.view(ncta, 64).cpu()
     rel = (t - t[:, :1]).float() / 1.9e3  # stamps are taken by thread 64 (first softmax warp)
     rel[t == 0] = float("nan")
     med = rel.nanmedian(0).values
     print(f"b={b}: {ncta} CTAs; us @1.9GHz: setup={med[1]:.2f} tiles={med[2]:.2f} q_landed={med[3]:.2f} O_done={med[30]:.2f} end={med[31]:.2f}")
+    if NS > 1:
+        print(f"   split-KV x{NS}: slab staged={med[24]:.2f} cluster barrier passed={med[25]:.2f} merged={med[26]:.2f}")
     print("   softmax [start -> end] per tile: " + "  ".join(f"[{med[4+2*j]:.2f}->{med[5+2*j]:.2f}]" for j in range(13) if med[4+2*j] == med[4+2*j]))
     print("   MMA thread S_j issued: " + "  ".join(f"{med[32+j]:.2f}" for j in range(13) if med[32+j] == med[32+j]))
     print("   MMA thread PV_j issued: " + "  ".join(f"{med[48+j]:.2f}" for j in range(13) if med[48+j] == med[48+j]))
