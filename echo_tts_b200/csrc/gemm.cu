@@ -160,6 +160,16 @@ static TileCfg pick_cfg(const GemmCall& c) {
   if (p.epi != EPI_GENERIC && p.epi != EPI_ACCUM) {
     static const int env_cg = [] { const char* e = std::getenv("ECHO_GEMM_CG"); return e ? atoi(e) : 0; }();  // tuning only
     if (c.cg == 1 || env_cg == 1 || p.N % 256 != 0 || p.M <= 128) return {256, 1};
+    if (p.epi == EPI_QKV) {
+      // 384-column pair tiles (two MMAs per K step, one TMEM stage) when they save whole waves: the 640-row plain step
+      // is 96 tiles of 256 x 256 = two waves over the 74 CTA pairs, but 66 tiles of 256 x 384 = one (-25 % MMA time).
+      // ECHO_GEMM_BN384=0 switches it off, =1 forces it.
+      static const int env_384 = [] { const char* e = std::getenv("ECHO_GEMM_BN384"); return e ? atoi(e) : -1; }();
+      const long pm = (p.M + 255) / 256, slots = sms / 2;
+      const long w256 = (pm * p.batches * ((p.N + 255) / 256) + slots - 1) / slots;
+      const long w384 = (pm * p.batches * ((p.N + 383) / 384) + slots - 1) / slots;
+      if (c.bn == 384 || env_384 == 1 || (c.bn == 0 && env_384 != 0 && w384 * 384 < w256 * 256)) return {384, 2};
+    }
     return {256, 2};
   }
   if (c.bn) return {c.bn, (c.cg == 2 && (c.bn == 256 || c.bn == 128)) ? 2 : 1};
@@ -272,7 +282,8 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
                       (uint64_t)a_bstride * 2, bk, GEMM_BM, bk * 2))
     return cudaErrorInvalidValue;
   const uint64_t b_rows = c.b_rows ? (uint64_t)c.b_rows : (uint64_t)p.N * (p.b_batch_rows ? p.batches : 1);
-  if (!get_tensor_map(&mb, c.B, 2, (uint64_t)p.taps * p.Kc, b_rows, 1, (uint64_t)c.ldb * 2, 0, bk, bn / cg, bk * 2))
+  // B box rows = this CTA's share of the tile's rows; the 384-column tile stages its 192 rows as three 64-row boxes
+  if (!get_tensor_map(&mb, c.B, 2, (uint64_t)p.taps * p.Kc, b_rows, 1, (uint64_t)c.ldb * 2, 0, bk, bn == 384 ? 64 : bn / cg, bk * 2))
     return cudaErrorInvalidValue;
 
   switch (p.epi) {
@@ -285,6 +296,7 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
       return cg == 2 ? launch_inst<256, 64, 1, EPI_SWIGLU, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_SWIGLU, 1>(ma, mb, p, s);
     case EPI_QKV:
       if (p.sec_width % 128 != 0 || p.N % 128 != 0) return cudaErrorInvalidValue;
+      if (bn == 384) return launch_inst<384, 64, 1, EPI_QKV, 2>(ma, mb, p, s);
       return cg == 2 ? launch_inst<256, 64, 1, EPI_QKV, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_QKV, 1>(ma, mb, p, s);
     case EPI_GENERIC:
       if (small_k) return launch_inst<96, 32, 3, EPI_GENERIC, 1>(ma, mb, p, s);

@@ -40,7 +40,10 @@ constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
 constexpr int GEMM_EPI_WARPS = 8;
 
-__host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
+__host__ __device__ constexpr int gemm_acc_stride(int BN) { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512; }
+// TMEM has 512 columns: two accumulator stages (epilogue of tile i overlaps the MMAs of tile i + 1) up to BN = 256, one
+// for the 384-wide single-wave tiles
+__host__ __device__ constexpr int gemm_acc_stages(int BN) { return 2 * gemm_acc_stride(BN) <= 512 ? 2 : 1; }
 // per-CTA bytes of one pipeline stage; with a CTA pair (CG = 2) each CTA holds its 128 A rows and HALF of the B rows
 __host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS, int CG) {
   return (GEMM_BM + BN / CG) * BK * 2 * ATOMS;
@@ -86,7 +89,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int ACC_STRIDE = gemm_acc_stride(BN);
   constexpr int ROW_BYTES = BK * 2;
   static_assert(BK == 64 || BK == 32, "BK must match a swizzle span");
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(BN % 32 == 0 && BN >= 32 && (BN <= 256 || (BN == 384 && CG == 2 && EPI == EPI_QKV && ATOMS == 1)), "BN");
+  // BN = 384 (CTA pairs, QKV epilogue): a 256 x 384 tile is two MMAs per K step (N = 256 into TMEM columns [0, 256) and
+  // N = 128 into [256, 384)); each CTA stages 128 + 64 B rows. It exists to make the QKV GEMM of a 640-row plain step ONE
+  // wave (3 pair rows x 22 column tiles = 66 <= 74 CTA pairs) instead of two (96 tiles of 256 x 256).
+  constexpr int ACC_STAGES = gemm_acc_stages(BN);
   static_assert(A_ATOM % 1024 == 0 && B_ATOM % 1024 == 0, "atoms must keep 1024B alignment");
 
   extern __shared__ uint8_t smem_raw[];
@@ -134,8 +141,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) {
-    if constexpr (CG == 2) tmem_alloc_pair<2 * ACC_STRIDE>(tmem_slot);
-    else tmem_alloc<2 * ACC_STRIDE>(tmem_slot);
+    if constexpr (CG == 2) tmem_alloc_pair<ACC_STAGES * ACC_STRIDE>(tmem_slot);
+    else tmem_alloc<ACC_STAGES * ACC_STRIDE>(tmem_slot);
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
@@ -155,6 +162,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // dependency wait; the matching A tiles follow right after it, back to back, from values already in registers.
   // (In-kernel timeline: with the decode -- nine integer divisions and a dozen parameter loads -- behind the wait, the
   // first A load left 0.47 us after the predecessor had finished, on every one of the ~7 000 launches of a request.)
+  // B tile of one pipeline stage: rows [nrow, nrow + BNH) of this CTA -- except for BN = 384, where the CTA's 192 rows
+  // are the 128 rows its half of the N = 256 MMA needs and the 64 rows of the N = 128 MMA (three 64-row boxes)
+  auto load_b = [&](uint8_t* sb, uint64_t* bar, int kcoord, int ntile0 /* bt * b_batch_rows + nt * BN */) {
+    if constexpr (BN == 384) {
+      const int r0 = ntile0 + (int)cta_rank * 128, r1 = ntile0 + 256 + (int)cta_rank * 64;
+      tma_load_2d_pair_hint(sb, &tmB, bar, kcoord, r0, b_policy);
+      tma_load_2d_pair_hint(sb + 64 * ROW_BYTES, &tmB, bar, kcoord, r0 + 64, b_policy);
+      tma_load_2d_pair_hint(sb + 128 * ROW_BYTES, &tmB, bar, kcoord, r1, b_policy);
+    } else if constexpr (CG == 2) {
+      tma_load_2d_pair_hint(sb, &tmB, bar, kcoord, ntile0 + (int)cta_rank * BNH, b_policy);
+    } else {
+      tma_load_2d_hint(sb, &tmB, bar, kcoord, ntile0, b_policy);
+    }
+  };
   int pre = 0;                           // k-blocks of the first unit whose B tiles are in flight before the wait
   int f_m0 = 0, f_ab = 0, f_kb_lo = 0;   // first unit: A row origin, A batch coordinate, first K block
   if (warp == 0 && lane == 0 && tile0 < num_tiles) {
@@ -163,7 +184,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int rest = tile / tiles_m;
     const int bt = rest % p.batches;
     const int nt = rest / p.batches;
-    const int n0 = nt * BN + (int)cta_rank * BNH;
     const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
     f_m0 = (mt * CG + (int)cta_rank) * GEMM_BM;
     f_ab = bt / p.a_batch_div;
@@ -177,10 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader) mbar_expect_tx(&full_bar[i], STAGE_BYTES * CG);  // A's bytes are counted too; they are issued after the wait
         uint8_t* sb = smem + i * STAGE_BYTES + A_ATOM * ATOMS;
 #pragma unroll
-        for (int a = 0; a < ATOMS; ++a) {
-          if constexpr (CG == 2) tma_load_2d_pair_hint(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
-          else tma_load_2d_hint(sb + a * B_ATOM, &tmB, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
-        }
+        for (int a = 0; a < ATOMS; ++a) load_b(sb + a * B_ATOM, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + nt * BN);
       }
     }
   }
@@ -214,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rest = tile / tiles_m;
         const int bt = rest % p.batches;
         const int nt = rest / p.batches;
-        const int m0 = (mt * CG + (int)cta_rank) * GEMM_BM, n0 = nt * BN + (int)cta_rank * BNH;
+        const int m0 = (mt * CG + (int)cta_rank) * GEMM_BM;
         const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
         for (int kb = (unit == tile0 ? kb_lo + pre : kb_lo); kb < kb_hi; ++kb) {
           const int tap = kb / kb_per_tap;
@@ -225,13 +242,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + A_ATOM * ATOMS;
 #pragma unroll
           for (int a = 0; a < ATOMS; ++a) {
-            if constexpr (CG == 2) {
-              tma_load_3d_pair_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
-              tma_load_2d_pair_hint(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
-            } else {
-              tma_load_3d_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
-              tma_load_2d_hint(sb + a * B_ATOM, &tmB, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + n0, b_policy);
-            }
+            if constexpr (CG == 2) tma_load_3d_pair_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
+            else tma_load_3d_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
+            load_b(sb + a * B_ATOM, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + nt * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -240,13 +253,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN == 384 ? 256 : BN);
+      constexpr uint32_t idesc2 = make_idesc_bf16(GEMM_BM * CG, 128);  // BN = 384: the second MMA of a K step
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int unit = tile0; unit < num_tiles; unit += tile_step, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+        const int as = it % ACC_STAGES;
+        mbar_wait(&tempty_bar[as], ((it / ACC_STAGES) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
         const int sk = unit % splits;
@@ -266,6 +280,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // advance 16 bf16 (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
               if constexpr (CG == 2) tc_mma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
               else tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
+              if constexpr (BN == 384) {  // columns [256, 384): this CTA's 64 B rows sit behind its 128 rows of the first MMA
+                const uint64_t bdesc2 = make_smem_desc<ROW_BYTES>(sb + a * B_ATOM + 128 * ROW_BYTES);
+                tc_mma_f16_pair(d_tmem + 256, adesc + 2 * k, bdesc2 + 2 * k, idesc2, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
+              }
             }
           }
           // smem slot reusable (in both CTAs of a pair) once these MMAs retire
@@ -293,10 +311,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nt = rest / p.batches;
       const int mbase = (mt * CG + (int)cta_rank) * GEMM_BM + quarter * 32;  // first row of this warp's 32-row slab
       const int n0 = nt * BN;
-      const int as = it & 1;
+      const int as = it % ACC_STAGES;
+      const uint32_t acc_phase = (it / ACC_STAGES) & 1;
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
       if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM) {
-        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
           trace[5] = clock64();
@@ -360,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int o = half * 128; o < bytes; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
         }
         load_resid(half, rcur);
-        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
           trace[5] = clock64();
@@ -499,7 +518,7 @@ ECHO_CHUNK_UNROLL
             if (add_bias) bq[ci] = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c4));
           }
         }
-        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
           trace[5] = clock64();
@@ -550,9 +569,16 @@ ECHO_CHUNK_UNROLL
             __syncwarp();  // the patch is rewritten by the next chunk
           }
         }
-      } else {  // EPI_QKV: this warp owns 32 rows x one 128-column group (group `half` of the 256-wide tile)
-        static_assert(EPI != EPI_QKV || BN == 256, "QKV epilogue needs BN == 256");
-        const int g0 = n0 + half * 128;  // first global column of the group
+      } else {  // EPI_QKV: a warp owns 32 rows x one 128-column group per pass
+        static_assert(EPI != EPI_QKV || BN == 256 || BN == 384, "QKV epilogue needs BN == 256 or 384");
+        // BN = 256: warp half h takes group h. BN = 384: a second pass over group 2, whose four 32-column chunks are
+        // shared by the two halves (both read the whole group once more for the row statistics).
+        constexpr int PASSES = BN == 384 ? 2 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < PASSES; ++pass) {
+        const int grp_t = pass == 0 ? half : 2;                    // 128-column group inside the tile
+        const int ch_lo = pass == 0 ? 0 : 2 * half, ch_hi = pass == 0 ? 4 : 2 * half + 2;  // chunks this warp writes
+        const int g0 = n0 + grp_t * 128;  // first global column of the group
         if (g0 < p.N) {
           const int si = g0 / p.sec_width;
           const int cs = g0 - si * p.sec_width;  // column inside the section
@@ -570,7 +596,7 @@ ECHO_CHUNK_UNROLL
 ECHO_CHUNK_UNROLL
             for (int ch = 0; ch < 4; ++ch) {
               float v[32];
-              tc_ld_32x32(tbase + (half * 4 + ch) * 32, v);
+              tc_ld_32x32(tbase + (grp_t * 4 + ch) * 32, v);
               tc_wait_ld();
 #pragma unroll
               for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
@@ -598,9 +624,9 @@ ECHO_CHUNK_UNROLL
           const bool all_rows = rows_left >= 32;  // warp-uniform
           const size_t ostep = (size_t)4 * p.sec_width;
 ECHO_CHUNK_UNROLL
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = ch_lo; ch < ch_hi; ++ch) {
             float v[32];
-            tc_ld_32x32(tbase + (half * 4 + ch) * 32, v);
+            tc_ld_32x32(tbase + (grp_t * 4 + ch) * 32, v);
             const int cc = cs + ch * 32;
             float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (sec.norm_w) w4 = __ldg(reinterpret_cast<const float4*>(sec.norm_w + cc + 4 * c4));
@@ -640,6 +666,7 @@ ECHO_CHUNK_UNROLL
             __syncwarp();
           }
         }
+        }  // pass
       }
       if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
         trace[6] = clock64();
@@ -659,8 +686,8 @@ ECHO_CHUNK_UNROLL
   else __syncthreads();
   if (trace && threadIdx.x == 0) trace[7] = clock64();
   if (warp == 2) {
-    if constexpr (CG == 2) tmem_dealloc_pair<2 * ACC_STRIDE>(tmem_base);
-    else tmem_dealloc<2 * ACC_STRIDE>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<ACC_STAGES * ACC_STRIDE>(tmem_base);
+    else tmem_dealloc<ACC_STAGES * ACC_STRIDE>(tmem_base);
   }
 }
 

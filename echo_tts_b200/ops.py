@@ -67,7 +67,7 @@ def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor, cg: 
 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoids, sec_width: int, rope_cos=None,
              rope_sin=None, head_dim: int = 128, pos_period: int = 1, pos_offset: int = 0, pos_mult: int = 1,
-             eps: float = 1e-5, cg: int = 0, trace=None) -> None:
+             eps: float = 1e-5, cg: int = 0, trace=None, bn: int = 0) -> None:
     lib = _lib.load(strict=False)
     M, K = a.shape
     d = GemmDesc()
@@ -76,6 +76,7 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, outs, norm_ws, rope_heads, sigmoi
     d.M, d.N, d.Kc, d.batches, d.taps = M, w.shape[0], K, 1, 1
     d.epi = EPI_QKV
     d.cg = cg
+    d.bn = bn  # 0 = auto; 384 = the single-wave pair tile (two MMAs per K step)
     d.trace = _ptr(trace)
     for i, o in enumerate(outs):
         d.sec_out[i] = o.data_ptr()

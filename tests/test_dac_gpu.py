@@ -28,6 +28,7 @@ def test_dac_tiny_vs_reference():
     g = gold("dac_tiny.pt")
     audio = ae_decode(dac, pca, g["z"])
     assert audio.dtype == torch.float32 and tuple(audio.shape) == (2, 1, 6 * 2048)
+    print(f"dac tiny rel-L2 {rel_l2(audio, g['audio']):.3e}")
     assert rel_l2(audio, g["audio"]) < AUDIO_TOL, rel_l2(audio, g["audio"])
     # decode_zq entry point (channels-first input, reference autoencoder.py:1128-1132)
     zq = ((g["z"] / pca.latent_scale) @ pca.pca_components + pca.pca_mean).transpose(1, 2)
@@ -45,6 +46,7 @@ def test_dac_full_T64_vs_reference():
     g = gold("dac_full_T64.pt")
     audio = ae_decode(dac, pca, g["z"])
     assert tuple(audio.shape) == (1, 1, 64 * 2048)
+    print(f"dac T=64 rel-L2 {rel_l2(audio, g['audio']):.3e}")
     assert rel_l2(audio, g["audio"]) < AUDIO_TOL, rel_l2(audio, g["audio"])
 
 
@@ -79,7 +81,7 @@ def test_dac_full_T640_vs_reference():
     e = rel_l2(audio, ref)
     # the error must not grow along the sequence (window-128 transformer, conv stack): every tenth is within the bar
     tenths = [rel_l2(audio[..., i * 131072:(i + 1) * 131072], ref[..., i * 131072:(i + 1) * 131072]) for i in range(10)]
-    print(f"dac T=640 whole-waveform rel-L2 {e:.3e}; per tenth max {max(tenths):.3e}")
+    print(f"dac T=640 whole-waveform rel-L2 {e:.3e}; per tenth " + " ".join(f"{t:.2e}" for t in tenths))
     assert e < AUDIO_TOL, e
     assert max(tenths) < AUDIO_TOL, tenths
 

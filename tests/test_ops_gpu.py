@@ -104,11 +104,14 @@ def _rope_ref(x, cos, sin, pos):
     return o.reshape(x.shape)
 
 
-@pytest.mark.parametrize("cg", [1, 2])
-def test_gemm_qkv_norm_rope(ops, cg):
+@pytest.mark.parametrize("cg,bn,b,S,Dm", [(1, 0, 3, 160, 512), (2, 0, 3, 160, 512), (2, 384, 3, 160, 512), (2, 384, 1, 640, 1024),
+                                          (2, 384, 5, 100, 256), (0, 0, 1, 640, 2048)])
+def test_gemm_qkv_norm_rope(ops, cg, bn, b, S, Dm):
     """Fused wq|wk|wv|gate projection + per-head RMSNorm + RoPE on the first half of the heads
-    (reference model.py:217-232, 199-202)."""
-    b, S, Dm, H = 3, 160, 512, 4
+    (reference model.py:217-232, 199-202). bn = 384: the 256 x 384 pair tile (two MMAs per K step, one TMEM stage,
+    a partial last column tile) that makes the 640-row plain step a single wave; (0, 0, 1, 640, 2048) is that step's
+    real shape with the automatic choice."""
+    H = Dm // 128
     M = b * S
     a = _rand((M, Dm), 31)
     w = _rand((4 * Dm, Dm), 32, scale=Dm ** -0.5)
@@ -117,7 +120,7 @@ def test_gemm_qkv_norm_rope(ops, cg):
     cos, sin = _rope_tables(S + 7, 128)
     outs = [torch.empty(M, Dm, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
     ops.gemm_qkv(a, w, outs, [qn, kn, None, None], [H // 2, H // 2, 0, 0], [0, 0, 0, 1], Dm, cos, sin, 128,
-                 pos_period=S, pos_offset=7, eps=1e-5, cg=cg)
+                 pos_period=S, pos_offset=7, eps=1e-5, cg=cg, bn=bn)
     y = (a.float() @ w.float().T).view(M, 4, H, 128)
     pos = (torch.arange(M, device="cuda") % S) + 7
 
