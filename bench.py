@@ -108,7 +108,7 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic():
     """DRAM bytes per launch of the main kernels from the committed `ncu --set full` capture (profiles/), or {}."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     try:
         return json.load(open(p))["kernels"]
     except Exception:
@@ -523,7 +523,7 @@ def run_b200(args):
                         "dram_bytes_per_launch": w13["dram_bytes_read"] + w13["dram_bytes_write"],
                         "algorithmic_bytes_per_launch": 2 * (1920 * 2048 + 11776 * 2048 + 1920 * 5888),
                         "tensor_pipe_active_pct_ncu": w13["tensor_pipe_active_pct"],
-                        "source": "profiles/r01_ncu_traffic.json (ncu --set full, cold cache)"}
+                        "source": "profiles/r02_ncu_traffic.json (ncu --set full, cold cache)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
