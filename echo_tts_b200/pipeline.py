@@ -283,6 +283,50 @@ def sample_pipeline(model, fish_ae, pca_state, sample_fn: Callable, text_prompt:
 
 
 @torch.inference_mode()
+def sample_pipeline_batch(model, fish_ae, pca_state, sample_fn: Callable, text_prompts: Sequence[str],
+                          rng_seeds: Sequence[int], speaker_audio: Optional[torch.Tensor] = None,
+                          pad_to_max_speaker_latent_length: Optional[int] = None,
+                          pad_to_max_text_length: Optional[int] = None, normalize_text: bool = True, *,
+                          speaker_latent: Optional[torch.Tensor] = None, speaker_mask: Optional[torch.Tensor] = None,
+                          voice: Optional[Voice] = None) -> List[Tuple[torch.Tensor, str]]:
+    """`sample_pipeline` for several prompts that share ONE speaker reference -- the chunks of a long prompt
+    (handler.py:746-759 calls sample_pipeline once per chunk) -- in ONE sampler call and ONE DAC decode: the GEMMs then
+    run at M = B x 640 rows, where the tensor cores are 15-20 % better used than at batch 1. Item i draws its noise
+    exactly as a single call with `rng_seeds[i]` would (its own generator), so a chunk's latents differ from the
+    one-at-a-time result only by the bf16 noise floor (other tile shapes / summation orders), never by its inputs.
+    `sample_fn` must accept the keyword `noise=` (the samplers of this package do). Returns [(audio (1, 1, n), text)]."""
+    from .autoencoder import ae_decode
+    device = model.device
+    B = len(text_prompts)
+    assert B == len(rng_seeds) and B > 0
+    ids, mask, norm = get_text_input_ids_and_mask(
+        list(text_prompts), max_length=min(pad_to_max_text_length or MAX_TEXT_LENGTH, MAX_TEXT_LENGTH), device=device,
+        normalize=normalize_text, return_normalized_text=True, pad_to_max=(pad_to_max_text_length is not None))
+    kw = {}
+    if voice is not None:
+        speaker_latent, speaker_mask = voice.speaker_latent, voice.speaker_mask
+        kw["speaker_kv_cache"] = [(k.expand(B, *k.shape[1:]).contiguous(), v.expand(B, *v.shape[1:]).contiguous())
+                                  for k, v in voice.kv]
+    elif speaker_audio is not None and speaker_latent is None:
+        speaker_latent, speaker_mask = get_speaker_latent_and_mask(
+            fish_ae, pca_state, speaker_audio.to(device),
+            max_speaker_latent_length=pad_to_max_speaker_latent_length or MAX_SPEAKER_LATENT_LENGTH,
+            pad_to_max=(pad_to_max_speaker_latent_length is not None))
+    if speaker_latent is None:
+        n = pad_to_max_speaker_latent_length or 4
+        speaker_latent = torch.zeros((1, n, 80), device=device, dtype=model.dtype)
+        speaker_mask = torch.zeros((1, n), device=device, dtype=torch.bool)
+    S = getattr(sample_fn, "keywords", {}).get("sequence_length") or 640
+    noise = torch.cat([torch.randn((1, S, model.cfg.latent_size), device=device, dtype=torch.float32,
+                                   generator=torch.Generator(device=device).manual_seed(int(sd))) for sd in rng_seeds])
+    spk = speaker_latent.to(device).expand(B, *speaker_latent.shape[1:])
+    smk = speaker_mask.to(device).expand(B, *speaker_mask.shape[1:])
+    latent = sample_fn(model, spk, smk, ids, mask, int(rng_seeds[0]), noise=noise, **kw)
+    audio = ae_decode(fish_ae, pca_state, latent)
+    return [(crop_audio_to_flattening_point(audio[i:i + 1], latent[i]), norm[i]) for i in range(B)]
+
+
+@torch.inference_mode()
 def stream_blockwise_audio(model, fish_ae, pca_state, sample_blockwise_fn: Callable, speaker_latent, speaker_mask,
                            text_input_ids, text_mask, rng_seed: int, block_sizes: Sequence[int], on_audio=None,
                            **sampler_kwargs):
@@ -429,12 +473,16 @@ def gather_audio(local: Sequence[Tuple[int, torch.Tensor]], n_units: int, group=
     return out
 
 
-def synthesize(text: str, synth_chunk: Callable[[str, int], torch.Tensor], seed: int = 0,
+def synthesize(text: str, synth_chunk: Optional[Callable[[str, int], torch.Tensor]], seed: int = 0,
                max_chars_per_chunk: Optional[int] = 300, target_duration: float = 10.0,
-               normalize_boundaries: bool = True, enable_crossfade: bool = True, group=None):
+               normalize_boundaries: bool = True, enable_crossfade: bool = True, group=None, *,
+               synth_chunks: Optional[Callable[[List[str], List[int]], List[torch.Tensor]]] = None,
+               chunks_per_call: int = 4):
     """The chunk loop of handler._synthesize (handler.py:736-768), sharded over the ranks of `group` when
     torch.distributed is initialised. `synth_chunk(chunk_text, chunk_seed)` returns the chunk's audio (1, n);
-    chunk i uses seed + 1000 * i (handler.py:749). Rank 0 returns the stitched audio, other ranks None."""
+    chunk i uses seed + 1000 * i (handler.py:749). Rank 0 returns the stitched audio, other ranks None.
+    `synth_chunks(texts, seeds) -> [audio]` (optional, keyword-only extension): when given, a rank's chunks are
+    synthesised `chunks_per_call` at a time in one batched call (see `sample_pipeline_batch`) instead of one by one."""
     import torch.distributed as dist
     chunks = chunk_text_for_audio(text, max_chars_per_chunk, target_duration) if max_chars_per_chunk and \
         max_chars_per_chunk > 0 else [text]
@@ -444,9 +492,16 @@ def synthesize(text: str, synth_chunk: Callable[[str, int], torch.Tensor], seed:
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
     local = []
-    for i in shard_units(len(chunks), rank, world):
-        a = synth_chunk(chunks[i], seed + i * 1000)
-        local.append((i, a.reshape(1, -1) if a.dim() != 2 else a))
+    mine = shard_units(len(chunks), rank, world)
+    if synth_chunks is not None:
+        for j in range(0, len(mine), max(1, chunks_per_call)):
+            idx = mine[j:j + max(1, chunks_per_call)]
+            for i, a in zip(idx, synth_chunks([chunks[i] for i in idx], [seed + i * 1000 for i in idx])):
+                local.append((i, a.reshape(1, -1) if a.dim() != 2 else a))
+    else:
+        for i in mine:
+            a = synth_chunk(chunks[i], seed + i * 1000)
+            local.append((i, a.reshape(1, -1) if a.dim() != 2 else a))
     audio = gather_audio(local, len(chunks), group)
     if audio is None:
         return None

@@ -187,3 +187,22 @@ def test_voice_cache_lru_host_logic():
     assert calls["encode"] == 3 and calls["kv"] == 4
     cache.drop("d")
     assert "d" not in cache
+
+
+def test_synthesize_batched_callback_equals_per_chunk_callback():
+    """`synthesize(..., synth_chunks=...)` hands a rank's chunks to one batched callback `chunks_per_call` at a time: same
+    chunks, same seeds (seed + 1000 * idx, handler.py:749), same stitched result as the per-chunk callback."""
+    seen = []
+
+    def batched(texts, seeds):
+        seen.append(list(seeds))
+        return [fake_synth(t, s) for t, s in zip(texts, seeds)]
+
+    ref = P.synthesize(LONG_TEXT, fake_synth, seed=42)
+    for per_call in (1, 3, 100):
+        seen.clear()
+        got = P.synthesize(LONG_TEXT, None, seed=42, synth_chunks=batched, chunks_per_call=per_call)
+        assert torch.equal(got, ref)
+        n = len(P.chunk_text_for_audio(LONG_TEXT, 300, 10.0))
+        assert [s for call in seen for s in call] == [42 + 1000 * i for i in range(n)]
+        assert max(len(c) for c in seen) <= per_call
