@@ -505,7 +505,6 @@ inline int grid_for(int64_t n) {
   return (int)(g < 1 ? 1 : g);
 }
 
-bool starts_with(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
 
 }  // namespace
 
