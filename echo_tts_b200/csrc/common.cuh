@@ -334,5 +334,13 @@ ECHO_DEVICE float fast_exp2(float x) {  // single MUFU op; -inf -> 0, denormal r
 // element and made the SwiGLU / sigmoid(gate) epilogues instruction-bound.
 ECHO_DEVICE float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 ECHO_DEVICE float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// sigmoid(x) = 0.5 tanh(x / 2) + 0.5 with ONE MUFU op (tanh.approx.f32, abs error ~2^-11) instead of two (ex2 + rcp): the
+// gate section of the QKV epilogue is MUFU-bound (128 x 384 sigmoids per CTA = 3.2 us of a 25 us kernel at M = 640), and
+// its result is rounded to bf16 (quantum 2^-9 near 0.5 .. 1) anyway.
+ECHO_DEVICE float sigmoid_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 }  // namespace echo

@@ -658,7 +658,7 @@ ECHO_CHUNK_UNROLL
                 t.x = x0 * rc[i].x - y0 * rs[i].x; t.y = x0 * rs[i].x + y0 * rc[i].x;
                 t.z = x1 * rc[i].y - y1 * rs[i].y; t.w = x1 * rs[i].y + y1 * rc[i].y;
               }
-              if (sec.sigmoid) { t.x = sigmoid_f(t.x); t.y = sigmoid_f(t.y); t.z = sigmoid_f(t.z); t.w = sigmoid_f(t.w); }
+              if (sec.sigmoid) { t.x = sigmoid_fast(t.x); t.y = sigmoid_fast(t.y); t.z = sigmoid_fast(t.z); t.w = sigmoid_fast(t.w); }
               if (all_rows || sub + 4 * i < rows_left)
                 *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
               op += ostep;
