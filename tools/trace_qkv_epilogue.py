@@ -1,3 +1,5 @@
+"""Where the exposed epilogue of the QKV GEMM goes: per-CTA last-tile epilogue time (in-kernel clock64) with rope + norm +
+sigmoid (the real DiT call), without the sigmoid, without the rope, norm only, plain stores."""
 import os, sys, torch
 sys.path.insert(0, "/root/repo")
 from echo_tts_b200 import ops
