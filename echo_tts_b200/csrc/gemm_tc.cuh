@@ -474,8 +474,8 @@ ECHO_CHUNK_UNROLL
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), silu_f(a[4 * j]) * b[4 * j], silu_f(a[4 * j + 1]) * b[4 * j + 1],
-                   silu_f(a[4 * j + 2]) * b[4 * j + 2], silu_f(a[4 * j + 3]) * b[4 * j + 3]);
+            sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), silu_fast(a[4 * j]) * b[4 * j], silu_fast(a[4 * j + 1]) * b[4 * j + 1],
+                   silu_fast(a[4 * j + 2]) * b[4 * j + 2], silu_fast(a[4 * j + 3]) * b[4 * j + 3]);
           __syncwarp();
           bf16* op = p.out_bf16 + row0 * p.ld_bf16 + n0 / 2 + ch * 32 + 4 * c4;
 #pragma unroll
