@@ -289,6 +289,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       tc_ld_32x32(tmem_base + lane_base + st * TK, v);
       tc_ld_32x32(tmem_base + lane_base + st * TK + 32, v + 32);
       tc_wait_ld();
+      if (trace && threadIdx.x == 64 && j == 5) trace[27] = clock64();
       // causal / window segments: rows of this warp's slab see keys j with q - window < j <= q. Tiles entirely below the
       // diagonal and inside the window of all 32 rows take the row-uniform path; edge tiles are masked per row.
       int r_lo = 0, r_hi = TK;  // this row's valid key range inside the tile: [r_lo, r_hi)
@@ -320,6 +321,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
           tmax = fmaxf(tmax, v[i]);
         }
       }
+      if (trace && threadIdx.x == 64 && j == 5) trace[28] = clock64();
       const float m_new = fmaxf(m_used, tmax * sl2);
       if (j == 0) {
         m_used = m_new;
@@ -347,6 +349,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
           tc_wait_st();
         }
       }
+      if (trace && threadIdx.x == 64 && j == 5) trace[29] = clock64();
       const float muse = (m_used == -INFINITY) ? 0.f : m_used;
       // ---- P = exp2(s * scale*log2e - m) as bf16 pairs, stored over the first 32 columns of this row's S_j
       float lsum = 0.f;
@@ -359,8 +362,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         pk[c] = __uint_as_float(pack_bf16(p0, p1));
       }
       l_run += lsum;
+      if (trace && threadIdx.x == 64 && j == 5) trace[61] = clock64();
       tc_st_32x32(tmem_base + lane_base + st * TK, pk);
       tc_wait_st();
+      if (trace && threadIdx.x == 64 && j == 5) trace[62] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->p_ready[st]);

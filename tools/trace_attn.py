@@ -34,6 +34,8 @@ for b in (1, 3):
     rel[t == 0] = float("nan")
     med = rel.nanmedian(0).values
     print(f"b={b}: {ncta} CTAs; us @1.9GHz: setup={med[1]:.2f} tiles={med[2]:.2f} q_landed={med[3]:.2f} O_done={med[30]:.2f} end={med[31]:.2f}")
+    print(f"   tile 5 of the softmax warp: scores ready={med[14]:.3f} ld done={med[27]:.3f} max done={med[28]:.3f} rescale check done={med[29]:.3f} "
+          f"exp+pack done={med[61]:.3f} st done={med[62]:.3f} P published={med[15]:.3f}; tile 6 scores ready={med[16]:.3f}")
     if NS > 1:
         print(f"   split-KV x{NS}: slab staged={med[24]:.2f} cluster barrier passed={med[25]:.2f} merged={med[26]:.2f}")
     print("   softmax [start -> end] per tile: " + "  ".join(f"[{med[4+2*j]:.2f}->{med[5+2*j]:.2f}]" for j in range(13) if med[4+2*j] == med[4+2*j]))
