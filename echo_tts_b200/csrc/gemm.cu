@@ -8,12 +8,16 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "counters.h"
 #include "profiler.h"
 #include "gemm_tc.cuh"
 
 namespace echo {
+
+static inline bool b_batched_rows_check(const GemmParams& p) { return p.N % 128 != 0 || p.N / 128 > 250 || p.sec_width % 128 != 0; }
 
 // ------------------------------------------------------------------ driver entry point for tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -286,6 +290,33 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   if (!get_tensor_map(&mb, c.B, 2, (uint64_t)p.taps * p.Kc, b_rows, 1, (uint64_t)c.ldb * 2, 0, bk, bn == 384 ? 64 : bn / cg, bk * 2))
     return cudaErrorInvalidValue;
 
+  if (p.epi == EPI_QKV && bn == 384) {
+    // tile -> groups map (see GemmParams::tile_groups). Cost classes of a 128-column group in the epilogue: RoPE + norm (3),
+    // norm (2), sigmoid (1), plain (0). The most expensive groups go one per tile into the slot both warp halves share; the
+    // rest fill the per-half slots in pairs of equal class, so the two halves of a tile finish together.
+    const int ngroups = p.N / 128, ntile = (p.N + 383) / 384;
+    if (b_batched_rows_check(p) || 3 * ntile > (int)sizeof(p.tile_groups)) return cudaErrorInvalidValue;
+    std::vector<std::pair<int, int>> order;  // (-class, group)
+    for (int g = 0; g < ngroups; ++g) {
+      const int col = g * 128, si = col / p.sec_width;
+      const QkvSection& sc = p.sec[si];
+      const int grp = (col - si * p.sec_width) >> 7;
+      const int cls = grp < sc.rope_heads ? 3 : sc.norm_w ? 2 : sc.sigmoid ? 1 : 0;
+      order.push_back({-cls, g});
+    }
+    std::stable_sort(order.begin(), order.end());
+    const int empty = 255;
+    for (int i = 0; i < 3 * ntile; ++i) p.tile_groups[i] = (uint8_t)empty;
+    // shared slots: the ntile most expensive groups, heaviest first; per-half slots: the rest, CHEAPEST pairs to the tiles
+    // with the heaviest shared group
+    int next = 0;
+    for (int t = 0; t < ntile && next < ngroups; ++t) p.tile_groups[3 * t + 2] = (uint8_t)order[next++].second;
+    int last = ngroups - 1;
+    for (int t = 0; t < ntile && last >= next; ++t) {
+      p.tile_groups[3 * t] = (uint8_t)order[last--].second;
+      if (last >= next) p.tile_groups[3 * t + 1] = (uint8_t)order[last--].second;
+    }
+  }
   switch (p.epi) {
     case EPI_ACCUM:
       if (bn == 256) return cg == 2 ? launch_inst<256, 64, 1, EPI_ACCUM, 2>(ma, mb, p, s) : launch_inst<256, 64, 1, EPI_ACCUM, 1>(ma, mb, p, s);

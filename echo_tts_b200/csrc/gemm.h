@@ -66,6 +66,12 @@ struct GemmParams {
   int pos_offset;
   int pos_mult;
   float eps;
+  // ---- EPI_QKV with 384-column tiles only, set by gemm_launch: which three 128-column groups (heads) column tile t
+  // holds -- groups [3t], [3t+1] feed the N = 256 MMA (one per CTA of the pair, one per epilogue warp half), group [3t+2]
+  // the N = 128 MMA (its rows split across the pair, its chunks across the halves). A value >= N / 128 is an empty slot.
+  // The map spreads the expensive groups (RoPE + RMSNorm) one per tile into the shared slot instead of leaving them in
+  // three consecutive tiles whose epilogue is then the kernel's tail (single wave, one TMEM stage).
+  uint8_t tile_groups[96];
   // optional debug trace: 8 clock64 stamps per CTA (see gemm_tc.cuh); null in production
   long long* trace;
 };

@@ -164,9 +164,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // first A load left 0.47 us after the predecessor had finished, on every one of the ~7 000 launches of a request.)
   // B tile of one pipeline stage: rows [nrow, nrow + BNH) of this CTA -- except for BN = 384, where the CTA's 192 rows
   // are the 128 rows its half of the N = 256 MMA needs and the 64 rows of the N = 128 MMA (three 64-row boxes)
-  auto load_b = [&](uint8_t* sb, uint64_t* bar, int kcoord, int ntile0 /* bt * b_batch_rows + nt * BN */) {
+  auto load_b = [&](uint8_t* sb, uint64_t* bar, int kcoord, int bt_, int nt_) {
+    const int ntile0 = bt_ * p.b_batch_rows + nt_ * BN;
     if constexpr (BN == 384) {
-      const int r0 = ntile0 + (int)cta_rank * 128, r1 = ntile0 + 256 + (int)cta_rank * 64;
+      // the tile's three 128-row groups come from the map (any three heads)
+      const int boff = bt_ * p.b_batch_rows;
+      const int r0 = boff + (int)p.tile_groups[3 * nt_ + (int)cta_rank] * 128;
+      const int r1 = boff + (int)p.tile_groups[3 * nt_ + 2] * 128 + (int)cta_rank * 64;
       tma_load_2d_pair_hint(sb, &tmB, bar, kcoord, r0, b_policy);
       tma_load_2d_pair_hint(sb + 64 * ROW_BYTES, &tmB, bar, kcoord, r0 + 64, b_policy);
       tma_load_2d_pair_hint(sb + 128 * ROW_BYTES, &tmB, bar, kcoord, r1, b_policy);
@@ -197,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader) mbar_expect_tx(&full_bar[i], STAGE_BYTES * CG);  // A's bytes are counted too; they are issued after the wait
         uint8_t* sb = smem + i * STAGE_BYTES + A_ATOM * ATOMS;
 #pragma unroll
-        for (int a = 0; a < ATOMS; ++a) load_b(sb + a * B_ATOM, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + nt * BN);
+        for (int a = 0; a < ATOMS; ++a) load_b(sb + a * B_ATOM, &full_bar[i], tap * p.Kc + kc0 + a * BK, bt, nt);
       }
     }
   }
@@ -244,7 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int a = 0; a < ATOMS; ++a) {
             if constexpr (CG == 2) tma_load_3d_pair_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
             else tma_load_3d_hint(sa + a * A_ATOM, &tmA, &full_bar[stage], kc0 + a * BK, m0 + p.tap_shift[tap], bt / p.a_batch_div, a_policy);
-            load_b(sb + a * B_ATOM, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt * p.b_batch_rows + nt * BN);
+            load_b(sb + a * B_ATOM, &full_bar[stage], tap * p.Kc + kc0 + a * BK, bt, nt);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -578,7 +582,8 @@ ECHO_CHUNK_UNROLL
         for (int pass = 0; pass < PASSES; ++pass) {
         const int grp_t = pass == 0 ? half : 2;                    // 128-column group inside the tile
         const int ch_lo = pass == 0 ? 0 : 2 * half, ch_hi = pass == 0 ? 4 : 2 * half + 2;  // chunks this warp writes
-        const int g0 = n0 + grp_t * 128;  // first global column of the group
+        // first global column of the group: consecutive for 256-wide tiles, from the tile -> groups map for 384-wide ones
+        const int g0 = BN == 384 ? (int)p.tile_groups[3 * nt + grp_t] * 128 : n0 + grp_t * 128;
         if (g0 < p.N) {
           const int si = g0 / p.sec_width;
           const int cs = g0 - si * p.sec_width;  // column inside the section
