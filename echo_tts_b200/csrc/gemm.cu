@@ -121,8 +121,8 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
     cudaError_t e = ensure_dyn_smem(configured, kern, SMEM);
     if (e != cudaSuccess) return e;
   }
-  const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * p.batches * ((p.N + BN - 1) / BN) *
-                    (p.split_k > 1 ? p.split_k : 1);
+  const int tiles_n = (BN == 384 && p.qkv_tiles > 0) ? p.qkv_tiles : (p.N + BN - 1) / BN;
+  const int tiles = ((p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * p.batches * tiles_n * (p.split_k > 1 ? p.split_k : 1);
   const int slots = gemm_num_sms() / CG;
   const int grid = (tiles < slots ? tiles : slots) * CG;
   cudaError_t err;
@@ -294,8 +294,18 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
     // tile -> groups map (see GemmParams::tile_groups). Cost classes of a 128-column group in the epilogue: RoPE + norm (3),
     // norm (2), sigmoid (1), plain (0). The most expensive groups go one per tile into the slot both warp halves share; the
     // rest fill the per-half slots in pairs of equal class, so the two halves of a tile finish together.
-    const int ngroups = p.N / 128, ntile = (p.N + 383) / 384;
-    if (b_batched_rows_check(p) || 3 * ntile > (int)sizeof(p.tile_groups)) return cudaErrorInvalidValue;
+    const int ngroups = p.N / 128;
+    int ntile = (p.N + 383) / 384;
+    if (b_batched_rows_check(p)) return cudaErrorInvalidValue;
+    // single wave with CTA pairs to spare: more, narrower tiles -- x tiles of two groups (one MMA per K step, 1/3 less MMA
+    // time) take the most expensive groups, so that MMA + epilogue time is even across the tiles
+    {
+      const long pm = (long)((p.M + 255) / 256) * p.batches, slots = gemm_num_sms() / 2;
+      const int fit = (int)(slots / pm);
+      if (fit > ntile && pm * ntile <= slots) ntile = std::min(fit, (ngroups + 1) / 2);
+    }
+    if (3 * ntile > (int)sizeof(p.tile_groups)) return cudaErrorInvalidValue;
+    const int two = std::max(0, std::min(ntile, 3 * ntile - ngroups));  // tiles that hold two groups only
     std::vector<std::pair<int, int>> order;  // (-class, group)
     for (int g = 0; g < ngroups; ++g) {
       const int col = g * 128, si = col / p.sec_width;
@@ -305,16 +315,19 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
       order.push_back({-cls, g});
     }
     std::stable_sort(order.begin(), order.end());
-    const int empty = 255;
-    for (int i = 0; i < 3 * ntile; ++i) p.tile_groups[i] = (uint8_t)empty;
-    // shared slots: the ntile most expensive groups, heaviest first; per-half slots: the rest, CHEAPEST pairs to the tiles
-    // with the heaviest shared group
-    int next = 0;
-    for (int t = 0; t < ntile && next < ngroups; ++t) p.tile_groups[3 * t + 2] = (uint8_t)order[next++].second;
-    int last = ngroups - 1;
-    for (int t = 0; t < ntile && last >= next; ++t) {
+    for (int i = 0; i < (int)sizeof(p.tile_groups); ++i) p.tile_groups[i] = 255;  // empty slot: beyond N
+    p.qkv_tiles = ntile;
+    int next = 0, last = ngroups - 1;
+    // two-group tiles first: the heaviest groups, one per warp half
+    for (int t = 0; t < two && next <= last; ++t) {
+      p.tile_groups[3 * t] = (uint8_t)order[next++].second;
+      if (next <= last) p.tile_groups[3 * t + 1] = (uint8_t)order[next++].second;
+    }
+    // three-group tiles: shared slot = the heaviest remaining groups, per-half slots = the rest, cheapest pairs first
+    for (int t = two; t < ntile && next <= last; ++t) p.tile_groups[3 * t + 2] = (uint8_t)order[next++].second;
+    for (int t = two; t < ntile && next <= last; ++t) {
       p.tile_groups[3 * t] = (uint8_t)order[last--].second;
-      if (last >= next) p.tile_groups[3 * t + 1] = (uint8_t)order[last--].second;
+      if (next <= last) p.tile_groups[3 * t + 1] = (uint8_t)order[last--].second;
     }
   }
   switch (p.epi) {

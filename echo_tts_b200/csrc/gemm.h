@@ -72,6 +72,7 @@ struct GemmParams {
   // The map spreads the expensive groups (RoPE + RMSNorm) one per tile into the shared slot instead of leaving them in
   // three consecutive tiles whose epilogue is then the kernel's tail (single wave, one TMEM stage).
   uint8_t tile_groups[96];
+  int qkv_tiles;  // number of column tiles of the map (>= ceil(N / 384): tiles whose third slot is empty run one MMA per K step)
   // optional debug trace: 8 clock64 stamps per CTA (see gemm_tc.cuh); null in production
   long long* trace;
 };

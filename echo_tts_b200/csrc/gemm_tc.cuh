@@ -117,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool leader = cta_rank == 0;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   const int tiles_m = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
-  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_n = (BN == 384 && p.qkv_tiles > 0) ? p.qkv_tiles : (p.N + BN - 1) / BN;
   const int kb_per_tap = (p.Kc + BK * ATOMS - 1) / (BK * ATOMS);
   const int num_kb = kb_per_tap * p.taps;
   // split-K (EPI_GENERIC accumulate mode only): `splits` consecutive work units share one output tile and each
@@ -269,6 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
         const int sk = unit % splits;
         const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
+        bool third = true;  // BN = 384: does this tile hold a third group (else only the N = 256 MMA runs)
+        if constexpr (BN == 384) third = (int)p.tile_groups[3 * ((unit / splits) / tiles_m / p.batches) + 2] * 128 < p.N;
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -284,7 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // advance 16 bf16 (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
               if constexpr (CG == 2) tc_mma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
               else tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
-              if constexpr (BN == 384) {  // columns [256, 384): this CTA's 64 B rows sit behind its 128 rows of the first MMA
+              if (BN == 384 && third) {  // columns [256, 384): this CTA's 64 B rows sit behind its 128 rows of the first MMA
                 const uint64_t bdesc2 = make_smem_desc<ROW_BYTES>(sb + a * B_ATOM + 128 * ROW_BYTES);
                 tc_mma_f16_pair(d_tmem + 256, adesc + 2 * k, bdesc2 + 2 * k, idesc2, ((kb - kb_lo) | a | k) != 0 ? 1u : 0u);
               }
