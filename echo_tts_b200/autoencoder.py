@@ -148,6 +148,24 @@ class B200DAC:
         """A streaming-decode state for one sequence of up to `max_latents` latents (see `DacStream`)."""
         return DacStream(self, max_latents)
 
+    def borrow_stream(self, max_latents: int = 640) -> "DacStream":
+        """A reset stream from this decoder's pool (or a new one): a server that streams request after request does not
+        pay the ~26 device allocations of a stream state per request. Give it back with `return_stream`."""
+        pool = self.__dict__.setdefault("_stream_pool", [])
+        for i, st in enumerate(pool):
+            if st.max_latents >= max_latents:
+                pool.pop(i)
+                st.reset()
+                return st
+        return DacStream(self, max_latents)
+
+    def return_stream(self, st: "DacStream") -> None:
+        pool = self.__dict__.setdefault("_stream_pool", [])
+        if len(pool) < 16:
+            pool.append(st)
+        else:
+            st.close()
+
     @torch.inference_mode()
     def decode_latent(self, pca_state: PCAState, z: torch.Tensor) -> torch.Tensor:
         """Fused PCA un-projection + decode: z (B, T, 80) fp32 -> (B, 1, 2048 T) fp32."""

@@ -346,7 +346,7 @@ def stream_blockwise_audio(model, fish_ae, pca_state, sample_blockwise_fn: Calla
     B = text_input_ids.shape[0]
     cont = sampler_kwargs.get("continuation_latent")
     total = sum(block_sizes) + (cont.shape[1] if cont is not None else 0)
-    streams = [fish_ae.new_stream(total) for _ in range(B)]
+    streams = [fish_ae.borrow_stream(total) for _ in range(B)]  # pooled per decoder: no allocation after the first request
     try:
         if cont is not None and cont.shape[1] > 0:
             for b, st in enumerate(streams):
@@ -364,9 +364,10 @@ def stream_blockwise_audio(model, fish_ae, pca_state, sample_blockwise_fn: Calla
         latents = sample_blockwise_fn(model, speaker_latent, speaker_mask, text_input_ids, text_mask, rng_seed,
                                       list(block_sizes), on_block=on_block, **sampler_kwargs)
     finally:
-        torch.cuda.current_stream(model.device).synchronize()  # the states are freed below: nothing may still use them
+        # back to the pool without synchronising: the next user resets the state through the same handle, which orders the
+        # work on the device (HandleScope)
         for st in streams:
-            st.close()
+            fish_ae.return_stream(st)
     return latents, blocks
 
 
