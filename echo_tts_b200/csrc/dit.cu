@@ -1013,11 +1013,20 @@ extern "C" int echo_sample_blockwise_stream(echo_handle* h, const echo_sampler_a
   for (int bi = 0; bi < nblocks; ++bi) {
     const int bs = block_sizes[bi];
     if (a->has_kv_scale) scale_speaker_cache(h, a, &st, a->speaker_kv_scale, s);  // re-applied per block (:68-70)
-    // latent-prefix KV over the WHOLE prefix buffer (:72-74); one copy instead of the reference's three identical rows
-    cast_f32_to_bf16(prefix_out, prefix16, (int64_t)B * total * C, s);
-    ECHO_TRY(kv_patch_impl(h, 2, prefix16, B, total, st.kl.K.data(), st.kl.V.data(), s));
+    // latent-prefix KV (:72-74). The reference encodes the WHOLE prefix buffer for every block (three identical rows);
+    // the attention only ever sees the patches j with 4 j < start (model.py:243-244) and the latent encoder is causal, so
+    // only the first ceil(start / 4) patches are encoded here -- one copy, none at all for the first block without a
+    // continuation. Patch rows beyond `start` inside the last visible patch are the buffer's zeros, as in the reference.
+    const int ps = c.speaker_patch_size;
+    const int vis = (start + ps - 1) / ps;
+    if (vis > 0) {
+      for (int b = 0; b < B; ++b)  // rows [0, vis * ps) of every batch item, packed
+        cast_f32_to_bf16(prefix_out + (size_t)b * total * C, prefix16 + (size_t)b * vis * ps * C, (int64_t)vis * ps * C, s);
+      ECHO_TRY(kv_patch_impl(h, 2, prefix16, B, vis * ps, st.kl.K.data(), st.kl.V.data(), s));
+    }
+    st.kl.len = vis;
     scale_copy_f32(nz, xb, (int64_t)B * bs * C, a->has_truncation ? a->truncation_factor : 1.0f, s);
-    ECHO_TRY(euler_loop(h, a, &st, xb, bs, start, true, s));
+    ECHO_TRY(euler_loop(h, a, &st, xb, bs, start, vis > 0, s));
     ECHO_CUDA(cudaMemcpy2DAsync(prefix_out + (size_t)start * C, (size_t)total * C * 4, xb, (size_t)bs * C * 4,
                                 (size_t)bs * C * 4, B, cudaMemcpyDeviceToDevice, s));
     nz += (size_t)B * bs * C;
