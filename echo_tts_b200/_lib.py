@@ -79,7 +79,7 @@ class AttnSegment(C.Structure):
         ("len", C.c_int), ("eff_len", C.c_void_p),
         ("mask", C.c_void_p), ("mask_ld", C.c_int), ("mask_stride", C.c_int),
         ("pos_limit_mult", C.c_int), ("pos_limit", C.c_int), ("causal", C.c_int), ("window", C.c_int),
-        ("q_offset", C.c_int),
+        ("q_offset", C.c_int), ("kv_scale", C.c_float),
     ]
 
 

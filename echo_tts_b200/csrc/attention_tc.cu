@@ -322,7 +322,11 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         }
       }
       if (trace && threadIdx.x == 64 && j == 5) trace[28] = clock64();
-      const float m_new = fmaxf(m_used, tmax * sl2);
+      // speaker_kv_scale: a segment whose K and V count as multiplied by kv_scale -- the scores scale with it (folded into
+      // the softmax scale of this tile), and so does its share of P V (folded into P below; the row sum stays unscaled)
+      const float kvs = (sg.kv_scale != 0.f) ? sg.kv_scale : 1.f;
+      const float sl2t = sl2 * kvs;
+      const float m_new = fmaxf(m_used, tmax * sl2t);
       if (j == 0) {
         m_used = m_new;
       } else {
@@ -356,10 +360,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       float pk[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float p0 = fast_exp2(fmaf(v[2 * c], sl2, -muse));  // -inf -> 0
-        const float p1 = fast_exp2(fmaf(v[2 * c + 1], sl2, -muse));
+        const float p0 = fast_exp2(fmaf(v[2 * c], sl2t, -muse));  // -inf -> 0
+        const float p1 = fast_exp2(fmaf(v[2 * c + 1], sl2t, -muse));
         lsum += p0 + p1;
-        pk[c] = __uint_as_float(pack_bf16(p0, p1));
+        pk[c] = __uint_as_float(pack_bf16(p0 * kvs, p1 * kvs));
       }
       l_run += lsum;
       if (trace && threadIdx.x == 64 && j == 5) trace[61] = clock64();

@@ -606,6 +606,8 @@ struct KvSide {  // one cached key/value segment as the DiT layers see it
   const uint8_t* mask = nullptr;
   int mask_ld = 0, mask_stride = 1;
   const int32_t* eff = nullptr;
+  float kv_scale = 0.f;   // speaker_kv_scale currently in force (0 / 1: none) ...
+  int kv_scale_layers = 0;  // ... for the first kv_scale_layers blocks (inference.py:408-414)
 };
 
 struct FwdCtx {
@@ -686,6 +688,7 @@ int run_dit_layers(echo_handle* h, const FwdCtx& f, const Scratch& sc, float* v_
         echo_attn_segment& g = a.seg[ns];
         g.K = sd.K[i]; g.V = sd.V[i]; g.batch_stride = (int64_t)sd.len * D; g.row_stride = D; g.batch_mod = sd.batch_mod;
         g.len = sd.len; g.eff_len = sd.eff; g.mask = sd.mask; g.mask_ld = sd.mask_ld; g.mask_stride = sd.mask_stride;
+        if (i < sd.kv_scale_layers) g.kv_scale = sd.kv_scale;
         if (k == 0) { g.pos_limit_mult = c.speaker_patch_size; g.pos_limit = f.start_pos; }  // model.py:243-244
         ++ns;
       }
@@ -831,6 +834,7 @@ struct SamplerState {
   int B, Lt, Ls, Ps;
   KvStore kt, ks, kl;
   int32_t* eff3;  // [text x 3B | speaker x 3B]
+  float kv_factor = 1.f;  // running product of the speaker-KV scalings the reference would have applied to its cache so far
   float* mod;
   std::vector<float> t;
   const uint8_t *text_mask, *speaker_mask;
@@ -856,23 +860,14 @@ int sampler_prepare(echo_handle* h, const echo_sampler_args* a, const void* spea
   ECHO_TRY(alloc_kv(h, "smp.kt", B, Lt, &st->kt, s));
   ECHO_TRY(kv_text_impl(h, text_ids, text_mask, B, Lt, st->kt.K.data(), st->kt.V.data(), s));
   if (a->speaker_K != nullptr && a->speaker_V != nullptr) {
-    // per-voice persistence: the caller kept the cache echo_kv_speaker built for this speaker_latent. It is only
-    // read -- unless the sampler has to scale it (speaker_kv_scale), then it works on a copy.
+    // per-voice persistence: the caller kept the cache echo_kv_speaker built for this speaker_latent. It is only read
+    // (speaker_kv_scale is applied inside the attention kernel, never to the cache).
     const int L = c.num_layers;
     for (int i = 0; i < L; ++i)
       if (!a->speaker_K[i] || !a->speaker_V[i]) { set_error("sampler: null pointer in the cached speaker KV"); return ECHO_ERR_ARG; }
-    if (a->has_kv_scale) {
-      ECHO_TRY(alloc_kv(h, "smp.ks", B, st->Ps, &st->ks, s));
-      const size_t bytes = (size_t)B * st->Ps * c.model_size * 2;
-      for (int i = 0; i < L; ++i) {
-        ECHO_CUDA(cudaMemcpyAsync(st->ks.K[i], a->speaker_K[i], bytes, cudaMemcpyDeviceToDevice, s));
-        ECHO_CUDA(cudaMemcpyAsync(st->ks.V[i], a->speaker_V[i], bytes, cudaMemcpyDeviceToDevice, s));
-      }
-    } else {
-      st->ks.K.assign(a->speaker_K, a->speaker_K + L);
-      st->ks.V.assign(a->speaker_V, a->speaker_V + L);
-      st->ks.len = st->Ps;
-    }
+    st->ks.K.assign(a->speaker_K, a->speaker_K + L);
+    st->ks.V.assign(a->speaker_V, a->speaker_V + L);
+    st->ks.len = st->Ps;
   } else {
     ECHO_TRY(alloc_kv(h, "smp.ks", B, st->Ps, &st->ks, s));
     ECHO_TRY(kv_patch_impl(h, 1, static_cast<const bf16*>(speaker_latent), B, Ls, st->ks.K.data(), st->ks.V.data(), s));
@@ -888,15 +883,20 @@ int sampler_prepare(echo_handle* h, const echo_sampler_args* a, const void* spea
   return ECHO_OK;
 }
 
-void scale_speaker_cache(echo_handle* h, const echo_sampler_args* a, SamplerState* st, float factor, cudaStream_t s) {
+// speaker_kv_scale (inference.py:408-414, 467-468, 511-513; inference_blockwise.py:68-70). The reference multiplies the
+// first min(max_layers, L) layers of its speaker cache in place: by `scale` before the loop (before EVERY block in the
+// blockwise sampler, which compounds if a block never reaches speaker_kv_min_t) and by 1 / scale when t crosses
+// speaker_kv_min_t. Here the cache is never touched: the running product is kept in SamplerState::kv_factor and handed to
+// the attention kernel as a per-segment factor (scores and P V of the speaker keys scale with it), which saves eight
+// passes over a 315 MB cache per blockwise request with a 5-minute voice and the copy of a cached voice's KV.
+void scale_speaker_cache(echo_handle*, const echo_sampler_args*, SamplerState* st, float factor, cudaStream_t) {
+  st->kv_factor *= factor;
+}
+int kv_scale_layers(const echo_handle* h, const echo_sampler_args* a) {
   const int L = h->cfg.num_layers;
-  // inference.py:408-414: None -> every layer (here: a negative value), else min(max_layers, num_layers) -- 0 scales none
-  const int n = a->speaker_kv_max_layers < 0 ? L : (a->speaker_kv_max_layers < L ? a->speaker_kv_max_layers : L);
-  const int64_t numel = (int64_t)st->B * st->Ps * h->cfg.model_size;
-  for (int i = 0; i < n; ++i) {
-    scale_bf16((bf16*)st->ks.K[i], numel, factor, s);
-    scale_bf16((bf16*)st->ks.V[i], numel, factor, s);
-  }
+  if (!a->has_kv_scale) return 0;
+  // None -> every layer (here: a negative value), else min(max_layers, num_layers) -- 0 scales none
+  return a->speaker_kv_max_layers < 0 ? L : (a->speaker_kv_max_layers < L ? a->speaker_kv_max_layers : L);
 }
 
 // the num_steps loop shared by both samplers (inference.py:481-515 / inference_blockwise.py:80-118)
@@ -921,6 +921,7 @@ int euler_loop(echo_handle* h, const echo_sampler_args* a, SamplerState* st, flo
     f.spk.K = st->ks.K.data(); f.spk.V = st->ks.V.data(); f.spk.len = st->Ps; f.spk.batch_mod = B;
     f.spk.mask = st->speaker_mask; f.spk.mask_ld = st->Ls; f.spk.mask_stride = c.speaker_patch_size;
     f.spk.eff = st->eff3 + 3 * B;
+    f.spk.kv_scale = st->kv_factor; f.spk.kv_scale_layers = kv_scale_layers(h, a);
     if (use_latent) { f.lat.K = st->kl.K.data(); f.lat.V = st->kl.V.data(); f.lat.len = st->kl.len; f.lat.batch_mod = B; }
     ECHO_TRY(run_dit_layers(h, f, sc, v, s));
     float omt = 0.f, ratio = 1.f;

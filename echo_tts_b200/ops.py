@@ -121,6 +121,7 @@ def attention(q: torch.Tensor, segments, out: torch.Tensor, gate: Optional[torch
         s.pos_limit_mult, s.pos_limit = sg.get("pos_limit_mult", 0), sg.get("pos_limit", 0)
         s.causal, s.window = int(sg.get("causal", 0)), int(sg.get("window", 0))
         s.q_offset = int(sg.get("q_offset", 0))
+        s.kv_scale = float(sg.get("kv_scale", 0.0))
         s.batch_mod = int(sg.get("batch_mod", 0))
     _lib.check(lib.echo_op_attention(C.byref(d), _stream()), "echo_op_attention")
 

@@ -105,8 +105,8 @@ typedef struct echo_sampler_args {
   /* Optional per-voice persistence: HOST arrays of num_layers device pointers to a speaker KV cache built
      earlier by echo_kv_speaker for the SAME speaker_latent (each (B, Ls/4, 16, 128) bf16 contiguous). When both are
      non-NULL the samplers skip the speaker encoder + 24 K/V projections (the reference recomputes them on every call,
-     inference.py:465). The cache is never written: with speaker_kv_scale it is copied into the handle's workspace
-     first (the reference scales its per-call cache in place, inference.py:467-468, 511-513). */
+     inference.py:465). The cache is never written: speaker_kv_scale is applied inside the attention kernel
+     (the reference scales its per-call cache in place, inference.py:467-468, 511-513). */
   void* const* speaker_K;
   void* const* speaker_V;
 } echo_sampler_args;
@@ -266,6 +266,9 @@ typedef struct echo_attn_segment {
   int window;                     /* >0 with causal: also j > q - window */
   int q_offset;                   /* causal only: index of query row 0 on this segment's key axis (streaming decode: the
                                      keys are a growing cache, the queries its newest rows); 0 = plain self attention */
+  float kv_scale;                 /* 0 or 1: none. Otherwise the segment behaves as if its K and V were multiplied by this
+                                     factor (speaker_kv_scale, inference.py:408-414, 467-468): scores x factor, P V x factor --
+                                     applied in the kernel, the cache itself is never rewritten */
 } echo_attn_segment;
 typedef struct echo_attn_desc {
   const void* Q; int64_t q_batch_stride; int64_t q_row_stride; /* bf16 (b, S, H, D) */

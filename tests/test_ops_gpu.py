@@ -389,3 +389,21 @@ def test_gemm_gate_groups_must_be_multiples_of_32(ops):
     res = _rand((154, 256), 4, dtype=torch.float32)
     with pytest.raises(EchoError):
         ops.gemm(a, w, gate=gate, rows_per_gate=77, resid=res, out_f32=res)
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+def test_attention_segment_kv_scale(ops, nsplit):
+    """speaker_kv_scale applied inside the kernel (reference: the speaker K and V are multiplied in place,
+    inference.py:408-414): a segment with kv_scale = s must behave as if its keys AND values were scaled by s."""
+    b, S, H, D, L2, s = 2, 160, 2, 128, 300, 1.5
+    q = _rand((b, S, H, D), 141)
+    k, v = _rand((b, S, H, D), 142), _rand((b, S, H, D), 143)
+    k2, v2 = _rand((1, L2, H, D), 144), _rand((1, L2, H, D), 145)
+    out = torch.empty(b, S, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, [dict(k=k, v=v), dict(k=k2, v=v2, batch_mod=1, kv_scale=s)], out, nsplit=nsplit)
+    masks = [torch.ones(b, S, S, dtype=torch.bool, device="cuda"), torch.ones(b, S, L2, dtype=torch.bool, device="cuda")]
+    ref = _sdpa_ref(q, [k, (k2.float() * s).expand(b, -1, -1, -1)], [v, (v2.float() * s).expand(b, -1, -1, -1)], masks, D ** -0.5)
+    assert rel_l2(out, ref.reshape(b, S, H * D)) < 6e-3
+    plain = torch.empty_like(out)
+    ops.attention(q, [dict(k=k, v=v), dict(k=k2, v=v2, batch_mod=1)], plain, nsplit=nsplit)
+    assert rel_l2(plain, out.float()) > 5e-2  # the factor does something
