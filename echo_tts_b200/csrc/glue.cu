@@ -409,16 +409,6 @@ __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict_
   }
 }
 
-__global__ void scale_bf16_kernel(bf16* __restrict__ p, int64_t n, float sc) {
-  pdl_wait();
-  pdl_trigger();
-  const bf16 s16 = __float2bfloat16_rn(sc);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    // torch mul_ on a bf16 tensor by a python scalar: computed in fp32 (opmath), rounded once to bf16
-    p[i] = __float2bfloat16_rn(__bfloat162float(p[i]) * sc);
-  }
-  (void)s16;
-}
 
 __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, float sc) {
   pdl_wait();
@@ -534,11 +524,6 @@ void cfg_euler_update(float* x, const float* v, int64_t n, int has_cfg, float s_
                       float one_minus_t, float ratio, float dt, cudaStream_t s) {
   ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
   launch_k(cfg_euler_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, x, v, n, has_cfg, s_text, s_spk, has_rescale, one_minus_t, ratio, dt);
-  count_launch();
-}
-void scale_bf16(bf16* p, int64_t n, float sc, cudaStream_t s) {
-  ProfScope ps(PROF_GLUE, 0.0, 0.0, s, __func__);
-  launch_k(scale_bf16_kernel, dim3(grid_for(n)), dim3(256), 0, s, 1, p, n, sc);
   count_launch();
 }
 // ---- find_flattening_point (inference.py:288-296): first i whose `window` rows i .. i+window-1 of the zero-padded

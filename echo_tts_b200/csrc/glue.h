@@ -40,7 +40,6 @@ void adaln_finish(const float* up, const float* cond, float* mod, int n, int D, 
 void cfg_euler_update(float* x, const float* v, int64_t n_per_branch, int has_cfg, float s_text, float s_spk,
                       int has_rescale, float one_minus_t, float ratio, float dt, cudaStream_t s);
 
-void scale_bf16(bf16* p, int64_t n, float sc, cudaStream_t s);                 // _multiply_kv_cache, inference.py:408-414
 void scale_copy_f32(const float* src, float* dst, int64_t n, float sc, cudaStream_t s);
 void cast_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s);
 
