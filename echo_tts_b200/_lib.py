@@ -69,6 +69,7 @@ class GemmDesc(C.Structure):
         ("sec_width", C.c_int), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("head_dim", C.c_int),
         ("pos_period", C.c_int), ("pos_offset", C.c_int), ("pos_mult", C.c_int), ("eps", C.c_float),
         ("bn", C.c_int), ("cg", C.c_int), ("reserved0", C.c_int), ("trace", C.c_void_p), ("split_k", C.c_int),
+        ("B1", C.c_void_p), ("ldb1", C.c_int64), ("ru_bias1", C.c_void_p), ("ru_alpha_out", C.c_void_p),
     ]
 
 
@@ -98,7 +99,7 @@ class ProfileReport(C.Structure):
                 ("bytes", C.c_double * 3)]
 
 
-EPI_GENERIC, EPI_SWIGLU, EPI_QKV = 0, 1, 2
+EPI_GENERIC, EPI_SWIGLU, EPI_QKV, EPI_RU = 0, 1, 2, 4
 ACT_NONE, ACT_GELU, ACT_SNAKE, ACT_TANH, ACT_SIGMOID, ACT_SILU = 0, 1, 2, 3, 4, 5
 DTYPE_F32, DTYPE_BF16 = 0, 1
 

@@ -36,6 +36,8 @@ extern "C" int echo_op_gemm(const echo_gemm_desc* d, void* stream) {
   c.bn = d->bn;
   c.cg = d->cg;
   c.split_k = d->split_k;
+  c.B1 = static_cast<const bf16*>(d->B1);
+  c.ldb1 = d->ldb1;
   GemmParams& p = c.p;
   p.M = d->M; p.N = d->N; p.Kc = d->Kc; p.batches = d->batches; p.taps = d->taps;
   for (int i = 0; i < 8; ++i) p.tap_shift[i] = d->tap_shift[i];
@@ -52,6 +54,7 @@ extern "C" int echo_op_gemm(const echo_gemm_desc* d, void* stream) {
     p.sec[i].rope_heads = d->sec_rope_heads[i];
     p.sec[i].sigmoid = d->sec_sigmoid[i];
   }
+  p.ru_bias1 = d->ru_bias1; p.ru_alpha_out = d->ru_alpha_out; p.ru_alpha_out_inv = nullptr;
   p.sec_width = d->sec_width; p.rope_cos = d->rope_cos; p.rope_sin = d->rope_sin;
   p.head_dim = d->head_dim ? d->head_dim : 128;
   p.pos_period = d->pos_period; p.pos_offset = d->pos_offset; p.pos_mult = d->pos_mult ? d->pos_mult : 1;

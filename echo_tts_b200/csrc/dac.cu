@@ -10,6 +10,7 @@
 // row-major output IS the upsampled (T*s, Cout) signal. Bias, Snake, GELU, LayerScale, residual adds and the bf16
 // re-quantisation for the next layer all happen in the GEMM epilogue. Weight-norm is folded at load time.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "attention.h"
@@ -1092,10 +1093,33 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
     Tc *= stg.stride;
     std::swap(cur, nxt);  // cur = snake1(x) for residual unit 0
     static const int dil[3] = {1, 3, 9};
+    // ResidualUnit = Snake -> conv7 (dilated) -> Snake -> conv1 -> + x (autoencoder.py:884-900). For the two widest-in-time
+    // stages (C = 192 and 96 channels, where the activations -- not the weights -- are the traffic) it is ONE kernel:
+    // the conv7 accumulator goes Snake -> bf16 -> shared memory -> second MMA (EPI_RU, gemm_tc.cuh); the bf16
+    // intermediate never reaches HBM and the stream is read and written once per unit: 831 -> 655 us (C = 96) and
+    // 665 -> 528 us (C = 192) per unit, bit-identical to the two launches (tests/test_ops_gpu.py::test_fused_residual_unit).
+    static const int env_fuse = [] { const char* e = std::getenv("ECHO_DAC_FUSED_RU"); return e ? atoi(e) : 1; }();
+    const bool fuse = env_fuse != 0 && (stg.cout == 96 || stg.cout == 192);
     for (int u = 0; u < 3; ++u) {
       const DacResUnitW& ru = stg.ru[u];
+      const int hr = 6 * dil[u];
+      const float* next_alpha = (u < 2) ? stg.ru[u + 1].alpha1
+                                : (b + 1 < c.num_rates ? h->stage[b + 1].alpha_in : h->final_alpha);
+      if (fuse) {
+        if (st) DAC_HALO_IN(cur, st->ru_halo[3 * b + u], hr, stg.cout, 2);
+        GemmCall g = with_halo(conv_gemm(ru.conv7, cur, B, Tc, dil[u]), cur, hr, Tc);
+        g.p.epi = EPI_RU;
+        g.p.alpha = ru.alpha2; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
+        g.B1 = ru.conv1.w; g.ldb1 = ru.conv1.cin; g.p.ru_bias1 = ru.conv1.bias;
+        g.p.ru_alpha_out = next_alpha; g.p.ru_alpha_out_inv = h->dac_alpha_inv[next_alpha];
+        g.p.resid = xa; g.p.out_f32 = xa; g.p.ld_f32 = stg.cout;
+        g.p.out_bf16 = nxt; g.p.ld_bf16 = stg.cout;  // not `cur`: later tiles still read its rows (the conv's past)
+        DAC_GEMM(g);
+        if (st) DAC_HALO_OUT(cur, st->ru_halo[3 * b + u], hr, stg.cout, 2, Tc);
+        std::swap(cur, nxt);
+        continue;
+      }
       {
-        const int hr = 6 * dil[u];
         if (st) DAC_HALO_IN(cur, st->ru_halo[3 * b + u], hr, stg.cout, 2);
         GemmCall g = with_halo(conv_gemm(ru.conv7, cur, B, Tc, dil[u]), cur, hr, Tc);
         g.p.out_bf16 = hb; g.p.ld_bf16 = stg.cout; g.p.act = ACT_SNAKE; g.p.alpha = ru.alpha2; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];
@@ -1103,8 +1127,6 @@ int dac_run(echo_handle* h, float* X /* (B*T, C) fp32 latent, time-major */, int
         if (st) DAC_HALO_OUT(cur, st->ru_halo[3 * b + u], hr, stg.cout, 2, Tc);
       }
       {
-        const float* next_alpha = (u < 2) ? stg.ru[u + 1].alpha1
-                                  : (b + 1 < c.num_rates ? h->stage[b + 1].alpha_in : h->final_alpha);
         GemmCall g = conv_gemm(ru.conv1, hb, B, Tc, 1);
         g.p.resid = xa; g.p.out_f32 = xa; g.p.ld_f32 = stg.cout;
         g.p.out_bf16 = cur; g.p.ld_bf16 = stg.cout; g.p.act = ACT_SNAKE; g.p.alpha = next_alpha; g.p.alpha_inv = h->dac_alpha_inv[g.p.alpha];

@@ -113,7 +113,8 @@ int gemm_num_sms() {
 }
 
 template <int BN, int BK, int ATOMS, int EPI, int CG>
-static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s,
+                               const CUtensorMap* mb1 = nullptr) {
   static std::atomic<uint64_t> configured{0};  // per device, see ensure_dyn_smem
   constexpr int SMEM = gemm_smem_bytes(BN, BK, ATOMS, CG, EPI);
   auto kern = gemm_tc_kernel<BN, BK, ATOMS, EPI, CG>;
@@ -133,7 +134,7 @@ static cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, con
       snprintf(tag, sizeof(tag), "gemm epi=%d M=%d x%d N=%d K=%d taps=%d bn=%d cg=%d sk=%d", EPI, p.M, p.batches, p.N,
                p.Kc, p.taps, BN, CG, p.split_k > 1 ? p.split_k : 1);
     ProfScope ps(PROF_GEMM, 2.0 * p.M * p.batches * (double)p.N * (double)p.Kc * p.taps, 0.0, s, tag);
-    err = launch_k(kern, dim3(grid), dim3(GEMM_THREADS), SMEM, s, CG, ma, mb, p);
+    err = launch_k(kern, dim3(grid), dim3(GEMM_THREADS), SMEM, s, CG, ma, mb, mb1 ? *mb1 : mb, p);
   }
   count_launch();
   return err;
@@ -161,6 +162,7 @@ static TileCfg pick_cfg(const GemmCall& c) {
     const double per = std::max(bn / 2.0, (128.0 + bn / (double)cg) / 2.0);
     return waves * per + 12.0;  // small constant: prefer fewer, larger tiles on ties
   };
+  if (p.epi == EPI_RU) return {p.N, 1};
   if (p.epi != EPI_GENERIC && p.epi != EPI_ACCUM) {
     static const int env_cg = [] { const char* e = std::getenv("ECHO_GEMM_CG"); return e ? atoi(e) : 0; }();  // tuning only
     if (c.cg == 1 || env_cg == 1 || p.N % 256 != 0 || p.M <= 128) return {256, 1};
@@ -206,6 +208,16 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   if (p.pos_period < 1) p.pos_period = 1;
   if (p.M <= 0 || p.N <= 0 || p.Kc <= 0 || p.taps > 8) return cudaErrorInvalidValue;
   if (p.epi == EPI_ACCUM) return cudaErrorInvalidValue;  // internal mode, chosen below
+  if (p.epi == EPI_RU) {
+    // fused ResidualUnit: square channel counts the kernel is instantiated for, shared weights, bf16 output to a buffer
+    // other than A (tile t reads A rows that tile t - 1 has already replaced otherwise)
+    if ((p.N != 96 && p.N != 192) || p.Kc != p.N || p.b_batch_rows != 0 || c.B1 == nullptr || (c.ldb1 % 8) != 0 ||
+        (reinterpret_cast<uintptr_t>(c.B1) & 15) || p.out_bf16 == nullptr || (const void*)p.out_bf16 == (const void*)c.A ||
+        p.gate != nullptr || p.n_valid != 0)
+      return cudaErrorInvalidValue;
+    p.act = ACT_SNAKE;
+    p.col_mod = p.N;
+  }
   // one gate row per rows_per_gate rows: a warp's 32-row slab must not straddle two of them (callers with other
   // group sizes launch once per group, see run_dit_layers)
   if (p.gate != nullptr && p.rows_per_gate > 0 &&
@@ -329,6 +341,12 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
       p.tile_groups[3 * t] = (uint8_t)order[last--].second;
       if (next <= last) p.tile_groups[3 * t + 1] = (uint8_t)order[last--].second;
     }
+  }
+  if (p.epi == EPI_RU) {
+    CUtensorMap mb1;
+    if (!get_tensor_map(&mb1, c.B1, 2, (uint64_t)p.Kc, (uint64_t)p.N, 1, (uint64_t)c.ldb1 * 2, 0, bk, bn, bk * 2))
+      return cudaErrorInvalidValue;
+    return bn == 96 ? launch_inst<96, 32, 3, EPI_RU, 1>(ma, mb, p, s, &mb1) : launch_inst<192, 64, 1, EPI_RU, 1>(ma, mb, p, s, &mb1);
   }
   switch (p.epi) {
     case EPI_ACCUM:

@@ -9,7 +9,8 @@ namespace echo {
 typedef __nv_bfloat16 bf16;
 
 enum EpiMode : int { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV = 2,
-                     EPI_ACCUM = 3 /* internal: lean instantiation of the pure residual accumulate, chosen by gemm_launch */ };
+                     EPI_ACCUM = 3 /* internal: lean instantiation of the pure residual accumulate, chosen by gemm_launch */,
+                     EPI_RU = 4 /* fused DAC ResidualUnit: conv7 -> Snake -> conv1 -> + x, see GemmCall::B1 */ };
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SNAKE = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SILU = 5 };
 
 struct QkvSection {
@@ -66,6 +67,13 @@ struct GemmParams {
   int pos_offset;
   int pos_mult;
   float eps;
+  // ---- EPI_RU (N == Kc == channels C, 96 or 192): the main loop is the dilated conv7 (taps x C -> C); its accumulator
+  // gets bias + Snake(alpha) (the fields above), is re-quantised to bf16 INTO SHARED MEMORY as the A operand of a second
+  // MMA with the 1 x 1 conv's weights (GemmCall::B1); that accumulator gets ru_bias1 + resid -> out_f32 (the fp32 stream)
+  // and Snake(ru_alpha_out) -> out_bf16 (the next unit's conv input). One read + one write of the stream per unit.
+  const float* ru_bias1;
+  const float* ru_alpha_out;
+  const float* ru_alpha_out_inv;
   // ---- EPI_QKV with 384-column tiles only, set by gemm_launch: which three 128-column groups (heads) column tile t
   // holds -- groups [3t], [3t+1] feed the N = 256 MMA (one per CTA of the pair, one per epilogue warp half), group [3t+2]
   // the N = 128 MMA (its rows split across the pair, its chunks across the halves). A value >= N / 128 is an empty slot.
@@ -85,6 +93,8 @@ struct GemmCall {
                            // earlier rows in front of the M output rows (streaming convs: tap_shift is then >= 0)
   const bf16* B;           // [b_rows][ldb] bf16, K contiguous (nn.Linear weight layout)
   int64_t ldb;
+  const bf16* B1;          // EPI_RU: the 1 x 1 conv's weights [C][ldb1] bf16
+  int64_t ldb1;
   int64_t b_rows;  // 0 -> N (or N*batches when b_batch_rows is set)
   GemmParams p;
   int bn;  // tile N override (0 = auto)

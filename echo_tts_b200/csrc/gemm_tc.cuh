@@ -48,14 +48,18 @@ __host__ __device__ constexpr int gemm_acc_stages(int BN) { return 2 * gemm_acc_
 __host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS, int CG) {
   return (GEMM_BM + BN / CG) * BK * 2 * ATOMS;
 }
-// every epilogue transposes 32 x 32 fp32 chunks through 4 KB of smem per epilogue warp
-__host__ __device__ constexpr int gemm_epi_bytes(int /*EPI*/) { return GEMM_EPI_WARPS * 4096; }
+// every epilogue transposes 32 x 32 fp32 chunks through 4 KB of smem per epilogue warp; EPI_RU adds the bf16 A operand of
+// its second MMA (128 x C) and 4 KB of per-channel tables (bias, alpha, 1 / alpha of the first Snake)
+__host__ __device__ constexpr int gemm_ru_a2_bytes(int BN) { return GEMM_BM * BN * 2; }
+__host__ __device__ constexpr int gemm_epi_bytes(int EPI, int BN) {
+  return GEMM_EPI_WARPS * 4096 + (EPI == EPI_RU ? gemm_ru_a2_bytes(BN) + 4096 : 0);
+}
 __host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS, int CG, int EPI) {
-  int s = (227 * 1024 - 1024 - 256 - gemm_epi_bytes(EPI)) / gemm_stage_bytes(BN, BK, ATOMS, CG);
+  int s = (227 * 1024 - 1024 - 256 - gemm_epi_bytes(EPI, BN)) / gemm_stage_bytes(BN, BK, ATOMS, CG);
   return s > ECHO_MAX_STAGES ? ECHO_MAX_STAGES : s;
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int BN, int BK, int ATOMS, int CG, int EPI) {
-  return gemm_stages(BN, BK, ATOMS, CG, EPI) * gemm_stage_bytes(BN, BK, ATOMS, CG) + gemm_epi_bytes(EPI) +
+  return gemm_stages(BN, BK, ATOMS, CG, EPI) * gemm_stage_bytes(BN, BK, ATOMS, CG) + gemm_epi_bytes(EPI, BN) +
          1024 /*align slack*/ + 256 /*barriers*/;
 }
 
@@ -80,7 +84,8 @@ __device__ __noinline__ float apply_act(float v, int act, float alpha) {
 // shared memory and write both CTAs' TMEM, so the per-SM operand ingest drops from (128+BN) to (128+BN/2) rows per K.
 template <int BN, int BK, int ATOMS, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmB1 /* EPI_RU: the 1 x 1 conv's weights; else a copy of tmB */, const GemmParams p) {
   constexpr int STAGES = gemm_stages(BN, BK, ATOMS, CG, EPI);
   constexpr int A_ATOM = GEMM_BM * BK * 2;
   constexpr int BNH = BN / CG;  // B rows staged by this CTA
@@ -99,12 +104,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [8 warps][32 x 32] (generic epilogue)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + gemm_epi_bytes(EPI));
+  uint8_t* ru_a2 = smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096;      // EPI_RU: [atoms][128 rows][BK] bf16, swizzled like A
+  float* ru_tab = reinterpret_cast<float*>(ru_a2 + gemm_ru_a2_bytes(BN));    // EPI_RU: [3][BN] bias, alpha, 1 / alpha
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + gemm_epi_bytes(EPI, BN));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* a2_ready_bar = bars + 2 * STAGES + 5;  // EPI_RU: the epilogue warps have written the second MMA's A operand
+  uint64_t* t2full_bar = bars + 2 * STAGES + 7;    // EPI_RU: the second MMA's accumulator is ready
+  static_assert((2 * ECHO_MAX_STAGES + 9) * 8 <= 256, "barrier block");
+  // EPI_RU: K blocks of the 1 x 1 conv (its K = BN channels) and where they sit in the ring: after the first RU_J conv7
+  // blocks of the NEXT tile, so that the second MMA of tile i runs in the middle of tile i + 1's first MMA (its operand
+  // is written by the epilogue warps ~1.5 us after tile i's first accumulator is complete) and the second epilogue
+  // overlaps the rest of it
+  constexpr int RU_KB1 = (BN + BK * ATOMS - 1) / (BK * ATOMS);
+  constexpr int RU_J = 8;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,12 +153,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * CG);
+      if constexpr (EPI == EPI_RU) {
+        mbar_init(&a2_ready_bar[s], GEMM_EPI_WARPS);
+        mbar_init(&t2full_bar[s], 1);
+      }
     }
     fence_barrier_init();
   }
   if (warp == 2) {
     if constexpr (CG == 2) tmem_alloc_pair<ACC_STAGES * ACC_STRIDE>(tmem_slot);
     else tmem_alloc<ACC_STAGES * ACC_STRIDE>(tmem_slot);
+  }
+  if constexpr (EPI == EPI_RU) {
+    // per-channel constants of the first Snake (weights: never written by a kernel of the chain, safe before the wait)
+    if (warp >= GEMM_EPI_WARP0) {
+      for (int c = threadIdx.x - GEMM_EPI_WARP0 * 32; c < BN; c += GEMM_EPI_WARPS * 32) {
+        const float al = p.alpha ? p.alpha[c] : 1.f;
+        ru_tab[c] = p.bias ? p.bias[c] : 0.f;
+        ru_tab[BN + c] = al;
+        ru_tab[2 * BN + c] = p.alpha_inv ? p.alpha_inv[c] : 1.f / (al + 1e-9f);
+      }
+    }
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
@@ -237,7 +268,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nt = rest / p.batches;
         const int m0 = (mt * CG + (int)cta_rank) * GEMM_BM;
         const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
+        // EPI_RU: the 1 x 1 conv's weight blocks (B only) for the PREVIOUS tile's second MMA, RU_J blocks into this tile
+        auto load_w1 = [&]() {
+#pragma unroll 1
+          for (int b1 = 0; b1 < RU_KB1; ++b1) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], B_ATOM * ATOMS);
+            uint8_t* sb = smem + stage * STAGE_BYTES + A_ATOM * ATOMS;
+#pragma unroll
+            for (int a = 0; a < ATOMS; ++a)
+              tma_load_2d_hint(sb + a * B_ATOM, &tmB1, &full_bar[stage], (b1 * ATOMS + a) * BK, 0, kL2EvictNormal);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        };
+        const int ru_at = kb_lo + (kb_hi - kb_lo < RU_J ? kb_hi - kb_lo : RU_J);  // == kb_hi: after the tile's last block
         for (int kb = (unit == tile0 ? kb_lo + pre : kb_lo); kb < kb_hi; ++kb) {
+          if constexpr (EPI == EPI_RU) { if (unit != tile0 && kb == ru_at) load_w1(); }
           const int tap = kb / kb_per_tap;
           const int kc0 = (kb - tap * kb_per_tap) * (BK * ATOMS);
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -252,6 +298,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if constexpr (EPI == EPI_RU) {
+          if (unit != tile0 && ru_at == kb_hi) load_w1();                // a tile shorter than RU_J blocks
+          if (unit + tile_step >= num_tiles) load_w1();                   // the CTA's last tile: its own second MMA
+        }
       }
     }
   } else if (warp == 1) {
@@ -262,6 +312,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      // EPI_RU: second MMA of tile `j` (the 1 x 1 conv): A = the bf16 tile the epilogue warps wrote to shared memory,
+      // B = the RU_KB1 weight blocks next in the ring, D = the tile's own accumulator stage (its first accumulator has been
+      // read by then)
+      auto issue_mma2 = [&](int j) {
+        const int pas = j % ACC_STAGES;
+        mbar_wait(&a2_ready_bar[pas], (j / ACC_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t d2 = tmem_base + pas * ACC_STRIDE;
+#pragma unroll 1
+        for (int b1 = 0; b1 < RU_KB1; ++b1) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES) + A_ATOM * ATOMS;
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a) {
+            const uint64_t adesc = make_smem_desc<ROW_BYTES>(smem_u32(ru_a2) + (b1 * ATOMS + a) * A_ATOM);
+            const uint64_t bdesc = make_smem_desc<ROW_BYTES>(sb + a * B_ATOM);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) tc_mma_f16(d2, adesc + 2 * k, bdesc + 2 * k, idesc, (b1 | a | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&t2full_bar[pas]);
+      };
       for (int unit = tile0; unit < num_tiles; unit += tile_step, ++it) {
         const int as = it % ACC_STAGES;
         mbar_wait(&tempty_bar[as], ((it / ACC_STAGES) & 1) ^ 1);
@@ -269,9 +344,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
         const int sk = unit % splits;
         const int kb_lo = num_kb * sk / splits, kb_hi = num_kb * (sk + 1) / splits;
+        const int ru_at = kb_lo + (kb_hi - kb_lo < RU_J ? kb_hi - kb_lo : RU_J);
         bool third = true;  // BN = 384: does this tile hold a third group (else only the N = 256 MMA runs)
         if constexpr (BN == 384) third = (int)p.tile_groups[3 * ((unit / splits) / tiles_m / p.batches) + 2] * 128 < p.N;
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          if constexpr (EPI == EPI_RU) { if (it > 0 && kb == ru_at) issue_mma2(it - 1); }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (trace && kb == kb_lo && unit == tile0) trace[3] = clock64();
@@ -301,6 +378,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CG == 2) tc_commit_pair(&tfull_bar[as]);
         else tc_commit(&tfull_bar[as]);
         if (trace) trace[4] = clock64();
+        if constexpr (EPI == EPI_RU) {
+          if (it > 0 && ru_at == kb_hi) issue_mma2(it - 1);
+          if (unit + tile_step >= num_tiles) issue_mma2(it);  // the CTA's last tile
+        }
       }
     }
   } else if (warp >= GEMM_EPI_WARP0) {
@@ -320,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it % ACC_STAGES;
       const uint32_t acc_phase = (it / ACC_STAGES) & 1;
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-      if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM) {
+      if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM && EPI != EPI_RU) {
         mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
@@ -329,7 +410,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
-      if constexpr (EPI == EPI_GENERIC) {
+      if constexpr (EPI == EPI_RU) {
+        // ---- phase 1 of the fused ResidualUnit: conv7 accumulator -> + bias -> Snake -> bf16 -> the A operand of the
+        // second MMA, written straight into shared memory in the K-major swizzled layout a TMA load of the same tile would
+        // have produced (atoms of [128 rows][BK]; 16-byte chunk index XOR row bits: row & 7 for 128-byte rows, (row >> 1) & 3
+        // for 64-byte rows). The single A2 buffer is free: this warp only gets here after its second epilogue of the
+        // previous tile, i.e. after that tile's second MMA has completed.
+        mbar_wait(&tfull_bar[as], acc_phase);
+        tc_fence_after();
+        const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
+        const uint32_t a2 = smem_u32(ru_a2);
+#pragma unroll 1
+        for (int ch = half; ch < BN / 32; ch += 2) {
+          float v[32];
+          tc_ld_32x32(tbase + ch * 32, v);
+          tc_wait_ld();
+          const float* tb = ru_tab + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // four 16-byte chunks = 8 channels each
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c = 8 * j + 2 * q;
+              const float x0 = v[c] + tb[c], x1 = v[c + 1] + tb[c + 1];
+              const float s0 = __sinf(tb[BN + c] * x0), s1 = __sinf(tb[BN + c + 1] * x1);
+              w[q] = pack_bf16(fmaf(s0 * s0, tb[2 * BN + c], x0), fmaf(s1 * s1, tb[2 * BN + c + 1], x1));
+            }
+            const int k0 = ch * 32 + 8 * j;          // first channel of the chunk
+            const int atom = k0 / BK, c16 = (k0 % BK) / 8;
+            const int sw = ROW_BYTES == 128 ? (r & 7) : ROW_BYTES == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1);
+            sts_u4(a2 + atom * A_ATOM + r * ROW_BYTES + ((c16 ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a2_ready_bar[as]);
+      }
+      if constexpr (EPI == EPI_GENERIC || EPI == EPI_RU) {
+        // EPI_RU, phase 2: the generic epilogue on the SECOND accumulator with the 1 x 1 conv's bias and the next Snake
+        const float* const e_bias = EPI == EPI_RU ? p.ru_bias1 : p.bias;
+        const float* const e_alpha = EPI == EPI_RU ? p.ru_alpha_out : p.alpha;
+        const float* const e_alpha_inv = EPI == EPI_RU ? p.ru_alpha_out_inv : p.alpha_inv;
+        uint64_t* const acc_bar = EPI == EPI_RU ? &t2full_bar[as] : &tfull_bar[as];
         // tcgen05.ld hands every thread one ROW of the chunk (32 consecutive columns). Touching global memory in
         // that shape costs 32 L1 wavefronts per 128-bit access (32 lines, 16 B each) and made this epilogue -- an
         // fp32 read-modify-write of the residual stream -- longer than the K = 2048 mainloop (measured 14.8 us vs
@@ -358,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float* gate = p.gate;
         if (gate != nullptr && p.rows_per_gate > 0 && rows_left > 0)
           gate += (size_t)((uint32_t)row0 / (uint32_t)p.rows_per_gate) * (size_t)p.gate_ld;
-        const float* bias = (p.bias != nullptr && sk == 0) ? p.bias + (size_t)bt * p.bias_bstride : nullptr;
+        const float* bias = (e_bias != nullptr && sk == 0) ? e_bias + (size_t)bt * p.bias_bstride : nullptr;
         const int nstore = p.n_valid > 0 ? p.n_valid : p.N;
         const uint32_t rd_even = stg + sub * 128 + ((c4 ^ sub) << 4);  // rows sub + 4i: (sub + 4i) & 7 = sub | sub + 4
         const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);
@@ -385,7 +508,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int o = half * 128; o < bytes; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
         }
         load_resid(half, rcur);
-        mbar_wait(&tfull_bar[as], acc_phase);
+        mbar_wait(acc_bar, acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
           trace[5] = clock64();
@@ -415,8 +538,8 @@ ECHO_CHUNK_UNROLL
                 bs = make_float4(b.x * gs.x, b.y * gs.y, b.z * gs.z, b.w * gs.w);
               }
               if (snake && p.out_bf16) {
-                a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + cb));
-                if (p.alpha_inv) i4 = __ldg(reinterpret_cast<const float4*>(p.alpha_inv + cb));
+                a4 = __ldg(reinterpret_cast<const float4*>(e_alpha + cb));
+                if (e_alpha_inv) i4 = __ldg(reinterpret_cast<const float4*>(e_alpha_inv + cb));
                 else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
               }
             }

@@ -50,6 +50,29 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, taps: int = 1, tap_shift: Sequence
     _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm")
 
 
+def residual_unit(a: torch.Tensor, w7: torch.Tensor, bias7, alpha2, w1: torch.Tensor, bias1, stream_f32: torch.Tensor,
+                  alpha_out, out_bf16: torch.Tensor, dilation: int, trace=None) -> None:
+    """Fused DAC ResidualUnit (autoencoder.py:884-900) on time-major activations: a (T, C) bf16 = Snake(alpha1)(x) (the
+    conv7 input), w7 (C, 7 C) bf16 [cout][tap][cin], w1 (C, C) bf16; stream_f32 (T, C) fp32 is x and is UPDATED in place
+    (x + conv1(Snake(alpha2)(conv7(a)))); out_bf16 (T, C) = Snake(alpha_out)(new x), the next unit's conv input."""
+    from ._lib import EPI_RU
+    lib = _lib.load(strict=False)
+    T, Cc = a.shape
+    d = GemmDesc()
+    d.A, d.lda, d.a_batch_stride = a.data_ptr(), a.stride(0), 0
+    d.B, d.ldb, d.b_rows = w7.data_ptr(), w7.stride(0), Cc
+    d.M, d.N, d.Kc, d.batches, d.taps = T, Cc, Cc, 1, 7
+    for j in range(7):
+        d.tap_shift[j] = -(6 - j) * dilation
+    d.epi = EPI_RU
+    d.bias, d.scale, d.alpha = _ptr(bias7), 1.0, _ptr(alpha2)
+    d.B1, d.ldb1, d.ru_bias1, d.ru_alpha_out = w1.data_ptr(), w1.stride(0), _ptr(bias1), _ptr(alpha_out)
+    d.resid, d.out_f32, d.ld_f32 = stream_f32.data_ptr(), stream_f32.data_ptr(), stream_f32.stride(0)
+    d.out_bf16, d.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    d.trace = _ptr(trace)
+    _lib.check(lib.echo_op_gemm(C.byref(d), _stream()), "echo_op_gemm(residual unit)")
+
+
 def gemm_swiglu(a: torch.Tensor, w13: torch.Tensor, out_bf16: torch.Tensor, cg: int = 0, trace=None) -> None:
     """w13: (2*I, K) packed so that each 256-row tile is [128 rows of w1 | the matching 128 rows of w3]."""
     lib = _lib.load(strict=False)

@@ -234,7 +234,7 @@ typedef struct echo_gemm_desc {
   const void* B; int64_t ldb; int64_t b_rows;          /* bf16 [b_rows][ldb]; K extent = taps*Kc */
   int M, N, Kc, batches, taps;
   int tap_shift[8];
-  int epi; /* 0 generic, 1 swiglu, 2 qkv */
+  int epi; /* 0 generic, 1 swiglu, 2 qkv, 4 fused DAC ResidualUnit (see B1 below) */
   const float* bias; float scale;
   const float* gate; int rows_per_gate; int gate_ld;
   const float* resid; float* out_f32; int ld_f32;
@@ -249,6 +249,10 @@ typedef struct echo_gemm_desc {
   int reserved0;    /* must be 0 */
   long long* trace; /* optional device buffer, 16 clock64 stamps per CTA (kernel timeline for tuning); NULL normally */
   int split_k;      /* 0 = auto, 1 = off, n > 1 = n K-splits per tile (only when out_f32 == resid: atomic accumulate) */
+  /* epi == 4, fused ResidualUnit (autoencoder.py:884-900), N == Kc == C in {96, 192}: A / B / taps / tap_shift / bias / alpha
+     describe the dilated conv7 and the Snake behind it; B1 [C][ldb1] bf16 + ru_bias1 the 1 x 1 conv; resid / out_f32 the
+     fp32 stream (may alias); out_bf16 = Snake(ru_alpha_out) of the new stream (must not alias A). */
+  const void* B1; int64_t ldb1; const float* ru_bias1; const float* ru_alpha_out;
 } echo_gemm_desc;
 int echo_op_gemm(const echo_gemm_desc* d, void* stream);
 

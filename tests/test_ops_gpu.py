@@ -407,3 +407,38 @@ def test_attention_segment_kv_scale(ops, nsplit):
     plain = torch.empty_like(out)
     ops.attention(q, [dict(k=k, v=v), dict(k=k2, v=v2, batch_mod=1)], plain, nsplit=nsplit)
     assert rel_l2(plain, out.float()) > 5e-2  # the factor does something
+
+
+@pytest.mark.parametrize("C,T,dil", [(96, 1000, 1), (96, 4096 + 77, 9), (192, 700, 3), (192, 128 * 148 * 2 + 5, 1), (96, 50, 3)])
+def test_fused_residual_unit(ops, C, T, dil):
+    """Fused DAC ResidualUnit (autoencoder.py:884-900: Snake -> conv7 dilated -> Snake -> conv1 -> + x) as ONE kernel: conv7
+    accumulator -> Snake -> bf16 into shared memory -> second MMA with the 1 x 1 weights -> + x. Checked against fp32
+    torch on the same bf16 inputs (the intermediate is rounded to bf16 exactly as the two-kernel path rounds it) and,
+    bit for bit, against the two-GEMM path it replaces."""
+    from echo_tts_b200._lib import ACT_SNAKE
+    a = _rand((T, C), 151)                                   # Snake(alpha1)(x), the conv7 input
+    w7 = _rand((C, 7 * C), 152, scale=(7 * C) ** -0.5)
+    w1 = _rand((C, C), 153, scale=C ** -0.5)
+    b7, b1 = _rand((C,), 154, dtype=torch.float32) * 0.1, _rand((C,), 155, dtype=torch.float32) * 0.1
+    al2 = torch.exp(0.3 * _rand((C,), 156, dtype=torch.float32))
+    alo = torch.exp(0.3 * _rand((C,), 157, dtype=torch.float32))
+    x = _rand((T, C), 158, dtype=torch.float32)
+    shifts = [-(6 - j) * dil for j in range(7)]
+    # ---- two-GEMM path (what dac_run did): conv7 + Snake -> hb ; conv1 + resid -> stream, Snake -> next input
+    hb = torch.empty(T, C, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w7, taps=7, tap_shift=shifts, bias=b7, out_bf16=hb, act=ACT_SNAKE, alpha=al2, col_mod=C)
+    x2 = x.clone()
+    nxt2 = torch.empty(T, C, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(hb, w1, bias=b1, resid=x2, out_f32=x2, out_bf16=nxt2, act=ACT_SNAKE, alpha=alo, col_mod=C)
+    # ---- fused
+    x1 = x.clone()
+    nxt1 = torch.empty(T, C, device="cuda", dtype=torch.bfloat16)
+    ops.residual_unit(a, w7, b7, al2, w1, b1, x1, alo, nxt1, dil)
+    # ---- fp32 torch reference
+    af = torch.nn.functional.pad(a.float(), (0, 0, 6 * dil, 0))
+    y = b7 + sum(af[j * dil: j * dil + T] @ w7.float()[:, j * C:(j + 1) * C].T for j in range(7))
+    hs = (y + torch.sin(al2 * y) ** 2 / (al2 + 1e-9)).to(torch.bfloat16).float()
+    xr = x + hs @ w1.float().T + b1
+    nr = xr + torch.sin(alo * xr) ** 2 / (alo + 1e-9)
+    assert rel_l2(x1, xr) < 3e-3 and rel_l2(nxt1, nr) < 4e-3
+    assert torch.equal(x1, x2) and torch.equal(nxt1, nxt2)
