@@ -214,6 +214,18 @@ ECHO_DEVICE void tc_commit(uint64_t* bar) {
 }
 ECHO_DEVICE void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32 lanes x 16 columns of fp32: thread i of the warp receives row (lane_base + i), columns [c, c+16).
+ECHO_DEVICE void tc_ld_32x16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // 32 lanes x 32 columns of fp32: thread i of the warp receives row (lane_base + i), columns [c, c+32).
 ECHO_DEVICE void tc_ld_32x32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -315,6 +327,38 @@ ECHO_DEVICE float warp_sum(float v) {
 ECHO_DEVICE float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, IEEE round-to-nearest like the scalar forms): half the issue slots of an
+// epilogue that is bound by its instruction count (two epilogue warps per scheduler).
+ECHO_DEVICE float2 f2add(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+ECHO_DEVICE float2 f2mul(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+ECHO_DEVICE float2 f2fma(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; "
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+// snake(x) = x + sin^2(alpha x) / (alpha + 1e-9) on a pair, `inv` = 1 / (alpha + 1e-9)   (autoencoder.py:96-102)
+ECHO_DEVICE float2 snake2(float2 x, float2 alpha, float2 inv) {
+  const float2 ax = f2mul(alpha, x);
+  const float2 s = make_float2(__sinf(ax.x), __sinf(ax.y));
+  return f2fma(f2mul(s, s), inv, x);
+}
+ECHO_DEVICE float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
 ECHO_DEVICE uint32_t pack_bf16(float a, float b) {

@@ -293,9 +293,20 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   const int a_batches = (p.batches + p.a_batch_div - 1) / p.a_batch_div;
   const int64_t a_bstride = c.a_batch_stride ? c.a_batch_stride : (int64_t)p.M * c.lda;
 
+  // Fused ResidualUnit with 96 channels: the window form (EPI_RUW, gemm_tc.cuh) when the seven taps are evenly spaced and
+  // their rows fit one 192-row window (dilations 1, 3, 9). ECHO_DAC_RU_WINDOW=0 keeps the ring form.
+  bool ru_window = false;
+  if (p.epi == EPI_RU && bn == 96 && p.taps == RUW_TAPS) {
+    static const int env_w = [] { const char* e = std::getenv("ECHO_DAC_RU_WINDOW"); return e ? atoi(e) : 1; }();
+    static const int env_mode = [] { const char* e = std::getenv("ECHO_RUW_DESC_MODE"); return e ? atoi(e) : 0; }();
+    const int d = p.tap_shift[1] - p.tap_shift[0];
+    ru_window = env_w != 0 && d >= 0 && GEMM_BM + (RUW_TAPS - 1) * d <= RUW_WIN_ROWS;
+    for (int j = 1; j < RUW_TAPS; ++j) ru_window = ru_window && (p.tap_shift[j] - p.tap_shift[0] == j * d);
+    p.ruw_desc_mode = env_mode;
+  }
   CUtensorMap ma, mb;
   if (!get_tensor_map(&ma, c.A, 3, (uint64_t)p.Kc, (uint64_t)(c.a_rows > 0 ? c.a_rows : p.M), (uint64_t)a_batches, (uint64_t)c.lda * 2,
-                      (uint64_t)a_bstride * 2, bk, GEMM_BM, bk * 2))
+                      (uint64_t)a_bstride * 2, bk, ru_window ? RUW_WIN_ROWS : GEMM_BM, bk * 2))
     return cudaErrorInvalidValue;
   const uint64_t b_rows = c.b_rows ? (uint64_t)c.b_rows : (uint64_t)p.N * (p.b_batch_rows ? p.batches : 1);
   // B box rows = this CTA's share of the tile's rows; the 384-column tile stages its 192 rows as three 64-row boxes
@@ -346,6 +357,7 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
     CUtensorMap mb1;
     if (!get_tensor_map(&mb1, c.B1, 2, (uint64_t)p.Kc, (uint64_t)p.N, 1, (uint64_t)c.ldb1 * 2, 0, bk, bn, bk * 2))
       return cudaErrorInvalidValue;
+    if (ru_window) return launch_inst<96, 32, 3, EPI_RUW, 1>(ma, mb, p, s, &mb1);
     return bn == 96 ? launch_inst<96, 32, 3, EPI_RU, 1>(ma, mb, p, s, &mb1) : launch_inst<192, 64, 1, EPI_RU, 1>(ma, mb, p, s, &mb1);
   }
   switch (p.epi) {

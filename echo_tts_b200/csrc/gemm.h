@@ -10,7 +10,9 @@ typedef __nv_bfloat16 bf16;
 
 enum EpiMode : int { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV = 2,
                      EPI_ACCUM = 3 /* internal: lean instantiation of the pure residual accumulate, chosen by gemm_launch */,
-                     EPI_RU = 4 /* fused DAC ResidualUnit: conv7 -> Snake -> conv1 -> + x, see GemmCall::B1 */ };
+                     EPI_RU = 4 /* fused DAC ResidualUnit: conv7 -> Snake -> conv1 -> + x, see GemmCall::B1 */,
+                     EPI_RUW = 5 /* internal: EPI_RU with the conv weights resident in shared memory and the A rows of all
+                                    taps loaded once per tile as one window; chosen by gemm_launch for 96 channels */ };
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SNAKE = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SILU = 5 };
 
 struct QkvSection {
@@ -74,6 +76,7 @@ struct GemmParams {
   const float* ru_bias1;
   const float* ru_alpha_out;
   const float* ru_alpha_out_inv;
+  int ruw_desc_mode;  // EPI_RUW, debug only: how the row-shifted window descriptors encode their start (see gemm_tc.cuh)
   // ---- EPI_QKV with 384-column tiles only, set by gemm_launch: which three 128-column groups (heads) column tile t
   // holds -- groups [3t], [3t+1] feed the N = 256 MMA (one per CTA of the pair, one per epilogue warp half), group [3t+2]
   // the N = 128 MMA (its rows split across the pair, its chunks across the halves). A value >= N / 128 is an empty slot.

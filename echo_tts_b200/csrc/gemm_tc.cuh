@@ -49,18 +49,28 @@ __host__ __device__ constexpr int gemm_stage_bytes(int BN, int BK, int ATOMS, in
   return (GEMM_BM + BN / CG) * BK * 2 * ATOMS;
 }
 // every epilogue transposes 32 x 32 fp32 chunks through 4 KB of smem per epilogue warp; EPI_RU adds the bf16 A operand of
-// its second MMA (128 x C) and 4 KB of per-channel tables (bias, alpha, 1 / alpha of the first Snake)
+// its second MMA (128 x C) and 8 KB of per-channel tables (bias, alpha, 1 / alpha of both convs / Snakes)
 __host__ __device__ constexpr int gemm_ru_a2_bytes(int BN) { return GEMM_BM * BN * 2; }
+// EPI_RUW keeps that operand in the (then idle) transpose patches instead: 128 x 96 x 2 = 24 KB of the 32 KB
 __host__ __device__ constexpr int gemm_epi_bytes(int EPI, int BN) {
-  return GEMM_EPI_WARPS * 4096 + (EPI == EPI_RU ? gemm_ru_a2_bytes(BN) + 4096 : 0);
+  return GEMM_EPI_WARPS * 4096 + (EPI == EPI_RU ? gemm_ru_a2_bytes(BN) + 8192 : EPI == EPI_RUW ? 8192 : 0);
+}
+// EPI_RUW has no operand ring: [7 taps of conv7 weights | 1 x 1 weights | one A window of 128 + 64 rows], all K-major atoms
+constexpr int RUW_TAPS = 7;
+constexpr int RUW_WIN_ROWS = 192;
+__host__ __device__ constexpr int gemm_ruw_bytes(int BN, int BK, int ATOMS) {
+  return (RUW_TAPS + 1) * ATOMS * BN * BK * 2 + ATOMS * RUW_WIN_ROWS * BK * 2;
 }
 __host__ __device__ constexpr int gemm_stages(int BN, int BK, int ATOMS, int CG, int EPI) {
+  if (EPI == EPI_RUW) return 2;  // two barrier pairs: [0] weights resident, [1] window full / free
   int s = (227 * 1024 - 1024 - 256 - gemm_epi_bytes(EPI, BN)) / gemm_stage_bytes(BN, BK, ATOMS, CG);
   return s > ECHO_MAX_STAGES ? ECHO_MAX_STAGES : s;
 }
+__host__ __device__ constexpr int gemm_ring_bytes(int BN, int BK, int ATOMS, int CG, int EPI) {
+  return EPI == EPI_RUW ? gemm_ruw_bytes(BN, BK, ATOMS) : gemm_stages(BN, BK, ATOMS, CG, EPI) * gemm_stage_bytes(BN, BK, ATOMS, CG);
+}
 __host__ __device__ constexpr int gemm_smem_bytes(int BN, int BK, int ATOMS, int CG, int EPI) {
-  return gemm_stages(BN, BK, ATOMS, CG, EPI) * gemm_stage_bytes(BN, BK, ATOMS, CG) + gemm_epi_bytes(EPI, BN) +
-         1024 /*align slack*/ + 256 /*barriers*/;
+  return gemm_ring_bytes(BN, BK, ATOMS, CG, EPI) + gemm_epi_bytes(EPI, BN) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 // Rare activations (cond_module SiLU, ConvNeXt GELU, ...). Deliberately NOT inlined: inlining erff/tanhf 32x per
@@ -100,13 +110,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // wave (3 pair rows x 22 column tiles = 66 <= 74 CTA pairs) instead of two (96 tiles of 256 x 256).
   constexpr int ACC_STAGES = gemm_acc_stages(BN);
   static_assert(A_ATOM % 1024 == 0 && B_ATOM % 1024 == 0, "atoms must keep 1024B alignment");
+  constexpr bool RUW = EPI == EPI_RUW;       // fused ResidualUnit, weights resident + A window (see the producer branch)
+  constexpr bool RU = EPI == EPI_RU || RUW;  // fused ResidualUnit: second MMA + two-phase epilogue
+  constexpr int RING_BYTES = gemm_ring_bytes(BN, BK, ATOMS, CG, EPI);
+  constexpr int RU_W = (BN / 2) % 32 == 0 ? 32 : 16;  // fused ResidualUnit: columns per epilogue piece, pieces per warp
+  constexpr int RU_NPC = BN / 2 / RU_W;
+  constexpr int RUW_W7_BYTES = RUW_TAPS * ATOMS * B_ATOM, RUW_W1_BYTES = ATOMS * B_ATOM;
+  constexpr int WIN_ATOM = RUW_WIN_ROWS * BK * 2, RUW_WIN_BYTES = ATOMS * WIN_ATOM;
+  static_assert(!RUW || (CG == 1 && gemm_ru_a2_bytes(BN) <= GEMM_EPI_WARPS * 4096 && BN == BK * ATOMS), "EPI_RUW shape");
+  static_assert(gemm_smem_bytes(BN, BK, ATOMS, CG, EPI) <= 227 * 1024, "shared memory");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [8 warps][32 x 32] (generic epilogue)
-  uint8_t* ru_a2 = smem + STAGES * STAGE_BYTES + GEMM_EPI_WARPS * 4096;      // EPI_RU: [atoms][128 rows][BK] bf16, swizzled like A
-  float* ru_tab = reinterpret_cast<float*>(ru_a2 + gemm_ru_a2_bytes(BN));    // EPI_RU: [3][BN] bias, alpha, 1 / alpha
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + gemm_epi_bytes(EPI, BN));
+  float* epi_stage = reinterpret_cast<float*>(smem + RING_BYTES);  // [8 warps][32 x 32] (generic epilogue)
+  // EPI_RU: [atoms][128 rows][BK] bf16, swizzled like A; EPI_RUW: the same, aliasing the transpose patches
+  uint8_t* ru_a2 = smem + RING_BYTES + (RUW ? 0 : GEMM_EPI_WARPS * 4096);
+  // EPI_RU / EPI_RUW: [6][BN] bias, alpha, 1 / alpha of conv7 + first Snake, then of the 1 x 1 conv + the next unit's Snake
+  float* ru_tab = reinterpret_cast<float*>(smem + RING_BYTES + GEMM_EPI_WARPS * 4096 + (RUW ? 0 : gemm_ru_a2_bytes(BN)));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + gemm_epi_bytes(EPI, BN));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -153,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * CG);
-      if constexpr (EPI == EPI_RU) {
+      if constexpr (RU) {
         mbar_init(&a2_ready_bar[s], GEMM_EPI_WARPS);
         mbar_init(&t2full_bar[s], 1);
       }
@@ -164,7 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (CG == 2) tmem_alloc_pair<ACC_STAGES * ACC_STRIDE>(tmem_slot);
     else tmem_alloc<ACC_STAGES * ACC_STRIDE>(tmem_slot);
   }
-  if constexpr (EPI == EPI_RU) {
+  if constexpr (RU) {
     // per-channel constants of the first Snake (weights: never written by a kernel of the chain, safe before the wait)
     if (warp >= GEMM_EPI_WARP0) {
       for (int c = threadIdx.x - GEMM_EPI_WARP0 * 32; c < BN; c += GEMM_EPI_WARPS * 32) {
@@ -172,6 +193,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ru_tab[c] = p.bias ? p.bias[c] : 0.f;
         ru_tab[BN + c] = al;
         ru_tab[2 * BN + c] = p.alpha_inv ? p.alpha_inv[c] : 1.f / (al + 1e-9f);
+        const float ao = p.ru_alpha_out ? p.ru_alpha_out[c] : 1.f;
+        ru_tab[3 * BN + c] = p.ru_bias1 ? p.ru_bias1[c] : 0.f;
+        ru_tab[4 * BN + c] = ao;
+        ru_tab[5 * BN + c] = p.ru_alpha_out_inv ? p.ru_alpha_out_inv[c] : 1.f / (ao + 1e-9f);
       }
     }
   }
@@ -213,6 +238,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
   int pre = 0;                           // k-blocks of the first unit whose B tiles are in flight before the wait
   int f_m0 = 0, f_ab = 0, f_kb_lo = 0;   // first unit: A row origin, A batch coordinate, first K block
+  if constexpr (RUW) {
+    // the whole conv7 + 1 x 1 weight set (7 x C x C + C x C bf16 = 144 KB at C = 96) becomes resident: one barrier
+    if (warp == 0 && lane == 0 && tile0 < num_tiles) {
+      mbar_expect_tx(&full_bar[0], RUW_W7_BYTES + RUW_W1_BYTES);
+#pragma unroll 1
+      for (int j = 0; j < RUW_TAPS; ++j)
+#pragma unroll
+        for (int a = 0; a < ATOMS; ++a)
+          tma_load_2d_hint(smem + (j * ATOMS + a) * B_ATOM, &tmB, &full_bar[0], j * p.Kc + a * BK, 0, kL2EvictNormal);
+#pragma unroll
+      for (int a = 0; a < ATOMS; ++a)
+        tma_load_2d_hint(smem + RUW_W7_BYTES + a * B_ATOM, &tmB1, &full_bar[0], a * BK, 0, kL2EvictNormal);
+    }
+  } else
   if (warp == 0 && lane == 0 && tile0 < num_tiles) {
     const int sk = tile0 % splits, tile = tile0 / splits;
     const int mt = tile % tiles_m;
@@ -257,6 +296,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+    if constexpr (RUW) {
+      // One window per tile: the A rows [m0 + shift(tap 0), + 128 + 6 d) that the seven taps read -- each tap's operand is
+      // the same shared-memory tile addressed (tap * d) rows further down (row-shifted descriptors in the MMA thread),
+      // instead of seven separate 128-row loads of overlapping rows. The window is single-buffered: it is reloaded as soon
+      // as the tile's conv7 MMAs have retired, under the two epilogue phases of the tile.
+      if (lane == 0) {
+        int it = 0;
+        for (int unit = tile0; unit < num_tiles; unit += tile_step, ++it) {
+          const int mt = unit % tiles_m, bt = unit / tiles_m;
+          if (it > 0) mbar_wait(&empty_bar[1], (uint32_t)(it - 1) & 1);
+          mbar_expect_tx(&full_bar[1], RUW_WIN_BYTES);
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a)
+            tma_load_3d_hint(smem + RUW_W7_BYTES + RUW_W1_BYTES + a * WIN_ATOM, &tmA, &full_bar[1], a * BK,
+                             mt * GEMM_BM + p.tap_shift[0], bt / p.a_batch_div, a_policy);
+        }
+      }
+    } else
     if (lane == 0) {
       int stage = pre == STAGES ? 0 : pre;  // the first `pre` slots are already being filled
       uint32_t phase = pre == STAGES ? 1 : 0;
@@ -283,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         const int ru_at = kb_lo + (kb_hi - kb_lo < RU_J ? kb_hi - kb_lo : RU_J);  // == kb_hi: after the tile's last block
         for (int kb = (unit == tile0 ? kb_lo + pre : kb_lo); kb < kb_hi; ++kb) {
-          if constexpr (EPI == EPI_RU) { if (unit != tile0 && kb == ru_at) load_w1(); }
+          if constexpr (RU) { if (unit != tile0 && kb == ru_at) load_w1(); }
           const int tap = kb / kb_per_tap;
           const int kc0 = (kb - tap * kb_per_tap) * (BK * ATOMS);
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -298,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (EPI == EPI_RU) {
+        if constexpr (RU) {
           if (unit != tile0 && ru_at == kb_hi) load_w1();                // a tile shorter than RU_J blocks
           if (unit + tile_step >= num_tiles) load_w1();                   // the CTA's last tile: its own second MMA
         }
@@ -306,6 +363,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    if constexpr (RUW) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        const uint32_t w7 = smem_u32(smem), w1 = w7 + RUW_W7_BYTES, win = w1 + RUW_W1_BYTES, a2 = smem_u32(ru_a2);
+        // second MMA of tile j (the 1 x 1 conv): A = the bf16 tile the epilogue warps wrote, B = the resident weights
+        auto issue_mma2 = [&](int j) {
+          const int pas = j % ACC_STAGES;
+          mbar_wait(&a2_ready_bar[pas], (j / ACC_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t d2 = tmem_base + pas * ACC_STRIDE;
+#pragma unroll
+          for (int a = 0; a < ATOMS; ++a) {
+            const uint64_t adesc = make_smem_desc<ROW_BYTES>(a2 + a * A_ATOM);
+            const uint64_t bdesc = make_smem_desc<ROW_BYTES>(w1 + a * B_ATOM);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) tc_mma_f16(d2, adesc + 2 * k, bdesc + 2 * k, idesc, (a | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&t2full_bar[pas]);
+        };
+        if (tile0 < num_tiles) {
+          mbar_wait(&full_bar[0], 0);  // weights resident
+          tc_fence_after();
+        }
+        int it = 0;
+        for (int unit = tile0; unit < num_tiles; unit += tile_step, ++it) {
+          const int as = it % ACC_STAGES;
+          mbar_wait(&tempty_bar[as], ((it / ACC_STAGES) & 1) ^ 1);
+          mbar_wait(&full_bar[1], (uint32_t)it & 1);
+          tc_fence_after();
+          if (trace && unit == tile0) trace[3] = clock64();
+          const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+#pragma unroll 1
+          for (int j = 0; j < RUW_TAPS; ++j) {
+            // tap j reads window rows [shift(j) - shift(0), + 128): the descriptor's start address moves down by whole
+            // rows. The swizzle is a function of the shared-memory address bits, which the row shift changes -- the
+            // descriptor's base-offset field (bits 49-51) carries the start's phase inside the swizzle pattern.
+            const uint32_t roff = (uint32_t)(p.tap_shift[j] - p.tap_shift[0]) * ROW_BYTES;
+#pragma unroll
+            for (int a = 0; a < ATOMS; ++a) {
+              const uint32_t sa = win + a * WIN_ATOM + roff;
+              uint64_t adesc = make_smem_desc<ROW_BYTES>(sa);
+              if (p.ruw_desc_mode == 1) adesc |= (uint64_t)((sa >> 7) & 7) << 49;
+              const uint64_t bdesc = make_smem_desc<ROW_BYTES>(w7 + (j * ATOMS + a) * B_ATOM);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (j | a | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty_bar[1]);    // window reusable once these MMAs retire
+          tc_commit(&tfull_bar[as]);   // conv7 accumulator ready for epilogue phase 1
+          if (trace) trace[4] = clock64();
+          if (it > 0) issue_mma2(it - 1);
+          if (unit + tile_step >= num_tiles) issue_mma2(it);  // the CTA's last tile
+        }
+      }
+    } else
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN == 384 ? 256 : BN);
       constexpr uint32_t idesc2 = make_idesc_bf16(GEMM_BM * CG, 128);  // BN = 384: the second MMA of a K step
@@ -348,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bool third = true;  // BN = 384: does this tile hold a third group (else only the N = 256 MMA runs)
         if constexpr (BN == 384) third = (int)p.tile_groups[3 * ((unit / splits) / tiles_m / p.batches) + 2] * 128 < p.N;
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
-          if constexpr (EPI == EPI_RU) { if (it > 0 && kb == ru_at) issue_mma2(it - 1); }
+          if constexpr (RU) { if (it > 0 && kb == ru_at) issue_mma2(it - 1); }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (trace && kb == kb_lo && unit == tile0) trace[3] = clock64();
@@ -378,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CG == 2) tc_commit_pair(&tfull_bar[as]);
         else tc_commit(&tfull_bar[as]);
         if (trace) trace[4] = clock64();
-        if constexpr (EPI == EPI_RU) {
+        if constexpr (RU) {
           if (it > 0 && ru_at == kb_hi) issue_mma2(it - 1);
           if (unit + tile_step >= num_tiles) issue_mma2(it);  // the CTA's last tile
         }
@@ -401,7 +513,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it % ACC_STAGES;
       const uint32_t acc_phase = (it / ACC_STAGES) & 1;
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-      if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM && EPI != EPI_RU) {
+      if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM && !RU) {
         mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
@@ -410,49 +522,151 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
-      if constexpr (EPI == EPI_RU) {
+      if constexpr (RU) {
         // ---- phase 1 of the fused ResidualUnit: conv7 accumulator -> + bias -> Snake -> bf16 -> the A operand of the
         // second MMA, written straight into shared memory in the K-major swizzled layout a TMA load of the same tile would
         // have produced (atoms of [128 rows][BK]; 16-byte chunk index XOR row bits: row & 7 for 128-byte rows, (row >> 1) & 3
         // for 64-byte rows). The single A2 buffer is free: this warp only gets here after its second epilogue of the
         // previous tile, i.e. after that tile's second MMA has completed.
+        // EPI_RUW: the operand lives in the transpose patches -- every warp must be through the previous tile's phase 2
+        if constexpr (RUW) asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
+        const bool tr = trace && warp == GEMM_EPI_WARP0 && lane == 0 && it == 2;  // steady-state tile of the timeline
+        if (tr) trace[8] = clock64();
         mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
+        if (tr) trace[9] = clock64();
         const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
-        const uint32_t a2 = smem_u32(ru_a2);
+        const int sw = ROW_BYTES == 128 ? (r & 7) : ROW_BYTES == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1);
+        const uint32_t a2row = smem_u32(ru_a2) + r * ROW_BYTES;
+        const uint32_t tab = smem_u32(ru_tab);
+        // the two warps of a lane quarter split the columns in halves (BN / 2 each, RU_W columns at a time); per-channel
+        // constants come from the shared-memory table four at a time, the arithmetic runs on fp32 pairs
 #pragma unroll 1
-        for (int ch = half; ch < BN / 32; ch += 2) {
-          float v[32];
-          tc_ld_32x32(tbase + ch * 32, v);
+        for (int pc = 0; pc < RU_NPC; ++pc) {
+          const int c0 = half * (BN / 2) + pc * RU_W;
+          float v[RU_W];
+          if constexpr (RU_W == 32) tc_ld_32x32(tbase + c0, v);
+          else tc_ld_32x16(tbase + c0, v);
           tc_wait_ld();
-          const float* tb = ru_tab + ch * 32;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {  // four 16-byte chunks = 8 channels each
+          for (int g = 0; g < RU_W / 8; ++g) {  // 16-byte chunks of the operand row = 8 channels each
+            const int k0 = c0 + 8 * g;          // first channel of the chunk
             uint32_t w[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int c = 8 * j + 2 * q;
-              const float x0 = v[c] + tb[c], x1 = v[c + 1] + tb[c + 1];
-              const float s0 = __sinf(tb[BN + c] * x0), s1 = __sinf(tb[BN + c + 1] * x1);
-              w[q] = pack_bf16(fmaf(s0 * s0, tb[2 * BN + c], x0), fmaf(s1 * s1, tb[2 * BN + c + 1], x1));
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t ta = tab + (k0 + 4 * h) * 4;
+              const float4 b = lds_f4(ta), al = lds_f4(ta + BN * 4), iv = lds_f4(ta + 2 * BN * 4);
+              const float* vv = v + 8 * g + 4 * h;
+              const float2 y0 = snake2(f2add(make_float2(vv[0], vv[1]), make_float2(b.x, b.y)), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+              const float2 y1 = snake2(f2add(make_float2(vv[2], vv[3]), make_float2(b.z, b.w)), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+              w[2 * h] = pack_bf16(y0.x, y0.y);
+              w[2 * h + 1] = pack_bf16(y1.x, y1.y);
             }
-            const int k0 = ch * 32 + 8 * j;          // first channel of the chunk
             const int atom = k0 / BK, c16 = (k0 % BK) / 8;
-            const int sw = ROW_BYTES == 128 ? (r & 7) : ROW_BYTES == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1);
-            sts_u4(a2 + atom * A_ATOM + r * ROW_BYTES + ((c16 ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+            sts_u4(a2row + atom * A_ATOM + ((c16 ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
           }
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a2_ready_bar[as]);
+        if (tr) trace[10] = clock64();
       }
-      if constexpr (EPI == EPI_GENERIC || EPI == EPI_RU) {
-        // EPI_RU, phase 2: the generic epilogue on the SECOND accumulator with the 1 x 1 conv's bias and the next Snake
-        const float* const e_bias = EPI == EPI_RU ? p.ru_bias1 : p.bias;
-        const float* const e_alpha = EPI == EPI_RU ? p.ru_alpha_out : p.alpha;
-        const float* const e_alpha_inv = EPI == EPI_RU ? p.ru_alpha_out_inv : p.alpha_inv;
-        uint64_t* const acc_bar = EPI == EPI_RU ? &t2full_bar[as] : &tfull_bar[as];
+      if constexpr (RU) {
+        // ---- phase 2: second accumulator + bias + x -> the fp32 stream, Snake of the next unit -> bf16. Same arithmetic, in
+        // the same order, as the generic epilogue (the two-launch form is bit-identical), but nothing else: the generic
+        // code re-tests its options per row and was ~1 000 instructions per 32 x 32 chunk and warp -- with two epilogue warps
+        // per scheduler (one instruction per ~4.5 cycles) phase 2 alone took 5.5 us of an 8.2 us tile
+        // (profiles/r02_dac_ru_timeline.txt). Chunks of RU_W columns go through the warp's transpose patch as before.
+        constexpr int CPR = RU_W / 4, RPI = 32 / CPR, NIT = 32 / RPI;  // lanes per row, rows per pass, passes
+        const uint32_t stg = smem_u32(epi_stage + ew * 1024);
+        const uint32_t tab = smem_u32(ru_tab);
+        const int sub = lane / CPR, c4 = lane % CPR;
+        const size_t row0 = (size_t)bt * p.M + mbase;
+        const int rows_left = p.M - mbase;
+        const bool all_rows = rows_left >= 32;  // warp-uniform
+        const int colw = half * (BN / 2) + 4 * c4;  // this lane's first column of piece 0
+        const float* const rp = p.resid + (row0 + sub) * p.ld_f32 + colw;
+        float* const xp = p.out_f32 + (row0 + sub) * p.ld_f32 + colw;
+        bf16* const np = p.out_bf16 + (row0 + sub) * p.ld_bf16 + colw;
+        const size_t step32 = (size_t)RPI * p.ld_f32, step16 = (size_t)RPI * p.ld_bf16;
+        // rows sub + RPI i of the patch. 128-byte rows (RU_W = 32): chunk index XOR (row & 7) = sub | sub + 4;
+        // 64-byte rows (RU_W = 16): XOR ((row >> 1) & 3), the same for every pass
+        const uint32_t rd_even = RU_W == 32 ? stg + sub * 128 + ((c4 ^ sub) << 4) : stg + sub * 64 + ((c4 ^ ((sub >> 1) & 3)) << 4);
+        const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);  // RU_W = 32 only
+        float4 rcur[NIT], rnext[NIT];
+        auto load_resid = [&](int pc, float4* rr) {
+          if (pc < RU_NPC) {
+            const float* q = rp + pc * RU_W;
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+              if (all_rows || sub + RPI * i < rows_left) rr[i] = *reinterpret_cast<const float4*>(q);
+              q += step32;
+            }
+          }
+        };
+        // the rows of this CTA's NEXT tile go to L2 now, a whole tile period ahead of their use
+        {
+          const int u2 = unit + tile_step;
+          const int rown = (u2 % tiles_m) * GEMM_BM + quarter * 32 + lane;
+          if (u2 < num_tiles && rown < p.M) {
+            const char* q = reinterpret_cast<const char*>(p.resid + ((size_t)(u2 / tiles_m) * p.M + rown) * p.ld_f32 + half * (BN / 2));
+#pragma unroll
+            for (int o = 0; o < BN * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + BN * 2 - 4));
+          }
+        }
+        load_resid(0, rcur);
+        mbar_wait(&t2full_bar[as], acc_phase);
+        tc_fence_after();
+        if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
+          trace[5] = clock64();
+          if (it == 2) trace[11] = trace[5];
+        }
+#pragma unroll 1
+        for (int pc = 0; pc < RU_NPC; ++pc) {
+          float v[RU_W];
+          if constexpr (RU_W == 32) tc_ld_32x32(tbase + half * (BN / 2) + pc * RU_W, v);
+          else tc_ld_32x16(tbase + half * (BN / 2) + pc * RU_W, v);
+          load_resid(pc + 1, rnext);
+          const uint32_t ta = tab + (3 * BN + colw + pc * RU_W) * 4;
+          const float4 b4 = lds_f4(ta), a4 = lds_f4(ta + BN * 4), i4 = lds_f4(ta + 2 * BN * 4);
+          tc_wait_ld();
+          if constexpr (RU_W == 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts_v4(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          __syncwarp();
+          float* xo = xp + pc * RU_W;
+          bf16* no = np + pc * RU_W;
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const float4 t = lds_v4(RU_W == 32 ? ((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024 : rd_even + i * 512);
+            if (all_rows || sub + RPI * i < rows_left) {
+              float2 t0 = f2add(f2add(make_float2(t.x, t.y), make_float2(b4.x, b4.y)), make_float2(rcur[i].x, rcur[i].y));
+              float2 t1 = f2add(f2add(make_float2(t.z, t.w), make_float2(b4.z, b4.w)), make_float2(rcur[i].z, rcur[i].w));
+              *reinterpret_cast<float4*>(xo) = make_float4(t0.x, t0.y, t1.x, t1.y);
+              t0 = snake2(t0, make_float2(a4.x, a4.y), make_float2(i4.x, i4.y));
+              t1 = snake2(t1, make_float2(a4.z, a4.w), make_float2(i4.z, i4.w));
+              *reinterpret_cast<uint2*>(no) = make_uint2(pack_bf16(t0.x, t0.y), pack_bf16(t1.x, t1.y));
+            }
+            xo += step32;
+            no += step16;
+          }
+          __syncwarp();  // the patch is rewritten by the next chunk
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) rcur[i] = rnext[i];
+        }
+      } else if constexpr (EPI == EPI_GENERIC) {
+        const float* const e_bias = p.bias;
+        const float* const e_alpha = p.alpha;
+        const float* const e_alpha_inv = p.alpha_inv;
+        uint64_t* const acc_bar = &tfull_bar[as];
         // tcgen05.ld hands every thread one ROW of the chunk (32 consecutive columns). Touching global memory in
         // that shape costs 32 L1 wavefronts per 128-bit access (32 lines, 16 B each) and made this epilogue -- an
         // fp32 read-modify-write of the residual stream -- longer than the K = 2048 mainloop (measured 14.8 us vs
@@ -800,7 +1014,9 @@ ECHO_CHUNK_UNROLL
       }
       if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
         trace[6] = clock64();
-        if (it < 4) trace[9 + 2 * it] = trace[6];
+        if (!RU && it < 4) trace[9 + 2 * it] = trace[6];
+        if (RU && it == 2) trace[13] = trace[6];
+        if (RU && it == 1) trace[14] = trace[6];  // end of the previous tile
       }
       tc_fence_before();
       __syncwarp();

@@ -409,7 +409,8 @@ def test_attention_segment_kv_scale(ops, nsplit):
     assert rel_l2(plain, out.float()) > 5e-2  # the factor does something
 
 
-@pytest.mark.parametrize("C,T,dil", [(96, 1000, 1), (96, 4096 + 77, 9), (192, 700, 3), (192, 128 * 148 * 2 + 5, 1), (96, 50, 3)])
+@pytest.mark.parametrize("C,T,dil", [(96, 1000, 1), (96, 4096 + 77, 9), (192, 700, 3), (192, 128 * 148 * 2 + 5, 1), (96, 50, 3),
+                                     (96, 128 * 148 * 2 + 5, 3), (96, 128 * 148 * 5 + 17, 9), (96, 128 * 148 * 3, 1)])
 def test_fused_residual_unit(ops, C, T, dil):
     """Fused DAC ResidualUnit (autoencoder.py:884-900: Snake -> conv7 dilated -> Snake -> conv1 -> + x) as ONE kernel: conv7
     accumulator -> Snake -> bf16 into shared memory -> second MMA with the 1 x 1 weights -> + x. Checked against fp32
