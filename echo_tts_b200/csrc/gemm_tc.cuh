@@ -141,7 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // is written by the epilogue warps ~1.5 us after tile i's first accumulator is complete) and the second epilogue
   // overlaps the rest of it
   constexpr int RU_KB1 = (BN + BK * ATOMS - 1) / (BK * ATOMS);
-  constexpr int RU_J = 8;
+  constexpr int RU_J = BN >= 192 ? 4 : 8;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -413,8 +413,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_commit(&empty_bar[1]);    // window reusable once these MMAs retire
           tc_commit(&tfull_bar[as]);   // conv7 accumulator ready for epilogue phase 1
           if (trace) trace[4] = clock64();
-          if (it > 0) issue_mma2(it - 1);
-          if (unit + tile_step >= num_tiles) issue_mma2(it);  // the CTA's last tile
+          // the tile's own 1 x 1 conv next, BEFORE the next tile's conv7: that one waits for its window (requested when
+          // this tile's conv7 retired, an HBM round trip away), and queued behind it the second MMA left the epilogue
+          // warps idle for 1.65 us of every 5.5 us tile
+          issue_mma2(it);
         }
       }
     } else
@@ -503,11 +505,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;      // which half of the column chunks
     int it = 0;
     for (int unit = tile0; unit < num_tiles; unit += tile_step, ++it) {
-      const int sk = unit % splits, tile = unit / splits;
-      const int mt = tile % tiles_m;
+      // fused ResidualUnit: one column tile, no split-K -- one division instead of four
+      const int sk = RU ? 0 : unit % splits, tile = RU ? unit : unit / splits;
       const int rest = tile / tiles_m;
-      const int bt = rest % p.batches;
-      const int nt = rest / p.batches;
+      const int mt = tile - rest * tiles_m;
+      const int bt = RU ? rest : rest % p.batches;
+      const int nt = RU ? 0 : rest / p.batches;
       const int mbase = (mt * CG + (int)cta_rank) * GEMM_BM + quarter * 32;  // first row of this warp's 32-row slab
       const int n0 = nt * BN;
       const int as = it % ACC_STAGES;
@@ -528,6 +531,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // have produced (atoms of [128 rows][BK]; 16-byte chunk index XOR row bits: row & 7 for 128-byte rows, (row >> 1) & 3
         // for 64-byte rows). The single A2 buffer is free: this warp only gets here after its second epilogue of the
         // previous tile, i.e. after that tile's second MMA has completed.
+        // Set-up of phase 2 first: its pointers, the L2 prefetch of the NEXT tile's rows of the stream and the loads of this
+        // tile's first piece of the stream -- they are in flight during phase 1 instead of being waited for at its end.
+        constexpr int CPR = RU_W / 4, RPI = 32 / CPR, NIT = 32 / RPI;  // lanes per row, rows per pass, passes
+        const uint32_t stg = smem_u32(epi_stage + ew * 1024);
+        const uint32_t tab = smem_u32(ru_tab);
+        const int sub = lane / CPR, c4 = lane % CPR;
+        const size_t row0 = (size_t)bt * p.M + mbase;
+        const int rows_left = p.M - mbase;
+        const bool all_rows = rows_left >= 32;  // warp-uniform
+        const int colw = half * (BN / 2) + 4 * c4;  // this lane's first column of piece 0
+        const float* const rp = p.resid + (row0 + sub) * p.ld_f32 + colw;
+        float* const xp = p.out_f32 + (row0 + sub) * p.ld_f32 + colw;
+        bf16* const np = p.out_bf16 + (row0 + sub) * p.ld_bf16 + colw;
+        const size_t step32 = (size_t)RPI * p.ld_f32, step16 = (size_t)RPI * p.ld_bf16;
+        // rows sub + RPI i of the patch. 128-byte rows (RU_W = 32): chunk index XOR (row & 7) = sub | sub + 4;
+        // 64-byte rows (RU_W = 16): XOR ((row >> 1) & 3), the same for every pass
+        const uint32_t rd_even = RU_W == 32 ? stg + sub * 128 + ((c4 ^ sub) << 4) : stg + sub * 64 + ((c4 ^ ((sub >> 1) & 3)) << 4);
+        const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);  // RU_W = 32 only
+        float4 rcur[NIT], rnext[NIT];
+        auto load_resid = [&](int pc, float4* rr) {
+          if (pc < RU_NPC) {
+            const float* q = rp + pc * RU_W;
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+              if (all_rows || sub + RPI * i < rows_left) rr[i] = *reinterpret_cast<const float4*>(q);
+              q += step32;
+            }
+          }
+        };
+        // the rows of this CTA's NEXT tile go to L2 now, a whole tile period ahead of their use
+        {
+          const int u2 = unit + tile_step;
+          int mt2 = mt + tile_step, bt2 = bt;
+          if (mt2 >= tiles_m) {  // next batch item(s): rare, so the division is off the common path
+            const int q = mt2 / tiles_m;
+            mt2 -= q * tiles_m;
+            bt2 += q;
+          }
+          const int rown = mt2 * GEMM_BM + quarter * 32 + lane;
+          if (u2 < num_tiles && rown < p.M) {
+            const char* q = reinterpret_cast<const char*>(p.resid + ((size_t)bt2 * p.M + rown) * p.ld_f32 + half * (BN / 2));
+#pragma unroll
+            for (int o = 0; o < BN * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + BN * 2 - 4));
+          }
+        }
+        load_resid(0, rcur);
         // EPI_RUW: the operand lives in the transpose patches -- every warp must be through the previous tile's phase 2
         if constexpr (RUW) asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
         const bool tr = trace && warp == GEMM_EPI_WARP0 && lane == 0 && it == 2;  // steady-state tile of the timeline
@@ -538,7 +588,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
         const int sw = ROW_BYTES == 128 ? (r & 7) : ROW_BYTES == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1);
         const uint32_t a2row = smem_u32(ru_a2) + r * ROW_BYTES;
-        const uint32_t tab = smem_u32(ru_tab);
         // the two warps of a lane quarter split the columns in halves (BN / 2 each, RU_W columns at a time); per-channel
         // constants come from the shared-memory table four at a time, the arithmetic runs on fp32 pairs
 #pragma unroll 1
@@ -571,52 +620,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&a2_ready_bar[as]);
         if (tr) trace[10] = clock64();
-      }
-      if constexpr (RU) {
         // ---- phase 2: second accumulator + bias + x -> the fp32 stream, Snake of the next unit -> bf16. Same arithmetic, in
         // the same order, as the generic epilogue (the two-launch form is bit-identical), but nothing else: the generic
         // code re-tests its options per row and was ~1 000 instructions per 32 x 32 chunk and warp -- with two epilogue warps
         // per scheduler (one instruction per ~4.5 cycles) phase 2 alone took 5.5 us of an 8.2 us tile
         // (profiles/r02_dac_ru_timeline.txt). Chunks of RU_W columns go through the warp's transpose patch as before.
-        constexpr int CPR = RU_W / 4, RPI = 32 / CPR, NIT = 32 / RPI;  // lanes per row, rows per pass, passes
-        const uint32_t stg = smem_u32(epi_stage + ew * 1024);
-        const uint32_t tab = smem_u32(ru_tab);
-        const int sub = lane / CPR, c4 = lane % CPR;
-        const size_t row0 = (size_t)bt * p.M + mbase;
-        const int rows_left = p.M - mbase;
-        const bool all_rows = rows_left >= 32;  // warp-uniform
-        const int colw = half * (BN / 2) + 4 * c4;  // this lane's first column of piece 0
-        const float* const rp = p.resid + (row0 + sub) * p.ld_f32 + colw;
-        float* const xp = p.out_f32 + (row0 + sub) * p.ld_f32 + colw;
-        bf16* const np = p.out_bf16 + (row0 + sub) * p.ld_bf16 + colw;
-        const size_t step32 = (size_t)RPI * p.ld_f32, step16 = (size_t)RPI * p.ld_bf16;
-        // rows sub + RPI i of the patch. 128-byte rows (RU_W = 32): chunk index XOR (row & 7) = sub | sub + 4;
-        // 64-byte rows (RU_W = 16): XOR ((row >> 1) & 3), the same for every pass
-        const uint32_t rd_even = RU_W == 32 ? stg + sub * 128 + ((c4 ^ sub) << 4) : stg + sub * 64 + ((c4 ^ ((sub >> 1) & 3)) << 4);
-        const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);  // RU_W = 32 only
-        float4 rcur[NIT], rnext[NIT];
-        auto load_resid = [&](int pc, float4* rr) {
-          if (pc < RU_NPC) {
-            const float* q = rp + pc * RU_W;
-#pragma unroll
-            for (int i = 0; i < NIT; ++i) {
-              if (all_rows || sub + RPI * i < rows_left) rr[i] = *reinterpret_cast<const float4*>(q);
-              q += step32;
-            }
-          }
-        };
-        // the rows of this CTA's NEXT tile go to L2 now, a whole tile period ahead of their use
-        {
-          const int u2 = unit + tile_step;
-          const int rown = (u2 % tiles_m) * GEMM_BM + quarter * 32 + lane;
-          if (u2 < num_tiles && rown < p.M) {
-            const char* q = reinterpret_cast<const char*>(p.resid + ((size_t)(u2 / tiles_m) * p.M + rown) * p.ld_f32 + half * (BN / 2));
-#pragma unroll
-            for (int o = 0; o < BN * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + BN * 2 - 4));
-          }
-        }
-        load_resid(0, rcur);
         mbar_wait(&t2full_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
@@ -644,9 +652,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           float* xo = xp + pc * RU_W;
           bf16* no = np + pc * RU_W;
+          float4 tt[NIT];  // all rows of the piece first: the loads then overlap each other and the math of earlier rows
+#pragma unroll
+          for (int i = 0; i < NIT; ++i)
+            tt[i] = lds_v4(RU_W == 32 ? ((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024 : rd_even + i * 512);
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {
-            const float4 t = lds_v4(RU_W == 32 ? ((i & 1) ? rd_odd : rd_even) + (i >> 1) * 1024 : rd_even + i * 512);
+            const float4 t = tt[i];
             if (all_rows || sub + RPI * i < rows_left) {
               float2 t0 = f2add(f2add(make_float2(t.x, t.y), make_float2(b4.x, b4.y)), make_float2(rcur[i].x, rcur[i].y));
               float2 t1 = f2add(f2add(make_float2(t.z, t.w), make_float2(b4.z, b4.w)), make_float2(rcur[i].z, rcur[i].w));
