@@ -353,6 +353,20 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
       if (next <= last) p.tile_groups[3 * t + 1] = (uint8_t)order[last--].second;
     }
   }
+  // DAC convs (bias, optional fp32 stream in / out, Snake -> bf16, nothing else): the lean epilogue -- same arithmetic in the
+  // same order as the generic one (bit-identical), a third of its instructions. ECHO_CONV_EPILOGUE=0 keeps the generic path.
+  if (p.epi == EPI_GENERIC) {
+    static const int env_conv = [] { const char* e = std::getenv("ECHO_CONV_EPILOGUE"); return e ? atoi(e) : 1; }();
+    const int cmod = p.col_mod > 0 ? p.col_mod : p.N;
+    const bool lean = env_conv != 0 && p.act == ACT_SNAKE && p.out_bf16 != nullptr && p.alpha != nullptr && p.gate == nullptr &&
+                      p.scale == 1.f && p.n_valid == 0 && p.split_k <= 1 && p.atomic_out == 0 && p.bias_bstride == 0 &&
+                      cmod % 32 == 0 && p.N % bn == 0 && (p.resid == nullptr || p.out_f32 != nullptr);
+    if (lean) {
+      if (small_k) return launch_inst<96, 32, 3, EPI_CONV, 1>(ma, mb, p, s);
+      if (bn == 192 && cg == 1) return launch_inst<192, 64, 1, EPI_CONV, 1>(ma, mb, p, s);
+      if (bn == 256 && cg == 2) return launch_inst<256, 64, 1, EPI_CONV, 2>(ma, mb, p, s);
+    }
+  }
   if (p.epi == EPI_RU) {
     CUtensorMap mb1;
     if (!get_tensor_map(&mb1, c.B1, 2, (uint64_t)p.Kc, (uint64_t)p.N, 1, (uint64_t)c.ldb1 * 2, 0, bk, bn, bk * 2))

@@ -12,7 +12,9 @@ enum EpiMode : int { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV = 2,
                      EPI_ACCUM = 3 /* internal: lean instantiation of the pure residual accumulate, chosen by gemm_launch */,
                      EPI_RU = 4 /* fused DAC ResidualUnit: conv7 -> Snake -> conv1 -> + x, see GemmCall::B1 */,
                      EPI_RUW = 5 /* internal: EPI_RU with the conv weights resident in shared memory and the A rows of all
-                                    taps loaded once per tile as one window; chosen by gemm_launch for 96 channels */ };
+                                    taps loaded once per tile as one window; chosen by gemm_launch for 96 channels */,
+                     EPI_CONV = 6 /* internal: lean form of the generic epilogue for the DAC convs -- bias (+ fp32 stream) ->
+                                     fp32, Snake -> bf16 -- chosen by gemm_launch when nothing else is asked for */ };
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SNAKE = 2, ACT_TANH = 3, ACT_SIGMOID = 4, ACT_SILU = 5 };
 
 struct QkvSection {

@@ -112,6 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(A_ATOM % 1024 == 0 && B_ATOM % 1024 == 0, "atoms must keep 1024B alignment");
   constexpr bool RUW = EPI == EPI_RUW;       // fused ResidualUnit, weights resident + A window (see the producer branch)
   constexpr bool RU = EPI == EPI_RU || RUW;  // fused ResidualUnit: second MMA + two-phase epilogue
+  constexpr bool CONV = EPI == EPI_CONV;     // lean conv epilogue: bias (+ stream) -> fp32, Snake -> bf16 (the RU's phase 2)
   constexpr int RING_BYTES = gemm_ring_bytes(BN, BK, ATOMS, CG, EPI);
   constexpr int RU_W = (BN / 2) % 32 == 0 ? 32 : 16;  // fused ResidualUnit: columns per epilogue piece, pieces per warp
   constexpr int RU_NPC = BN / 2 / RU_W;
@@ -516,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it % ACC_STAGES;
       const uint32_t acc_phase = (it / ACC_STAGES) & 1;
       const uint32_t tbase = tmem_base + as * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-      if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM && !RU) {
+      if constexpr (EPI != EPI_GENERIC && EPI != EPI_ACCUM && !RU && !CONV) {
         mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
@@ -525,7 +526,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
-      if constexpr (RU) {
+      if constexpr (RU || CONV) {
         // ---- phase 1 of the fused ResidualUnit: conv7 accumulator -> + bias -> Snake -> bf16 -> the A operand of the
         // second MMA, written straight into shared memory in the K-major swizzled layout a TMA load of the same tile would
         // have produced (atoms of [128 rows][BK]; 16-byte chunk index XOR row bits: row & 7 for 128-byte rows, (row >> 1) & 3
@@ -540,10 +541,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const size_t row0 = (size_t)bt * p.M + mbase;
         const int rows_left = p.M - mbase;
         const bool all_rows = rows_left >= 32;  // warp-uniform
-        const int colw = half * (BN / 2) + 4 * c4;  // this lane's first column of piece 0
-        const float* const rp = p.resid + (row0 + sub) * p.ld_f32 + colw;
-        float* const xp = p.out_f32 + (row0 + sub) * p.ld_f32 + colw;
-        bf16* const np = p.out_bf16 + (row0 + sub) * p.ld_bf16 + colw;
+        const int colw = half * (BN / 2) + 4 * c4;  // this lane's first column of piece 0 (inside the tile)
+        // EPI_CONV: the stream input and / or the fp32 output may be absent (warp-uniform)
+        const bool has_resid = RU || p.resid != nullptr, has_f32 = RU || p.out_f32 != nullptr;
+        const float* const rp = p.resid + (row0 + sub) * p.ld_f32 + n0 + colw;
+        float* const xp = p.out_f32 + (row0 + sub) * p.ld_f32 + n0 + colw;
+        bf16* const np = p.out_bf16 + (row0 + sub) * p.ld_bf16 + n0 + colw;
         const size_t step32 = (size_t)RPI * p.ld_f32, step16 = (size_t)RPI * p.ld_bf16;
         // rows sub + RPI i of the patch. 128-byte rows (RU_W = 32): chunk index XOR (row & 7) = sub | sub + 4;
         // 64-byte rows (RU_W = 16): XOR ((row >> 1) & 3), the same for every pass
@@ -551,7 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t rd_odd = stg + (sub + 4) * 128 + ((c4 ^ (sub + 4)) << 4);  // RU_W = 32 only
         float4 rcur[NIT], rnext[NIT];
         auto load_resid = [&](int pc, float4* rr) {
-          if (pc < RU_NPC) {
+          if (pc < RU_NPC && has_resid) {
             const float* q = rp + pc * RU_W;
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
@@ -570,7 +573,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bt2 += q;
           }
           const int rown = mt2 * GEMM_BM + quarter * 32 + lane;
-          if (u2 < num_tiles && rown < p.M) {
+          if (RU && u2 < num_tiles && rown < p.M) {
             const char* q = reinterpret_cast<const char*>(p.resid + ((size_t)bt2 * p.M + rown) * p.ld_f32 + half * (BN / 2));
 #pragma unroll
             for (int o = 0; o < BN * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
@@ -578,9 +581,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         load_resid(0, rcur);
+        const bool tr = trace && warp == GEMM_EPI_WARP0 && lane == 0 && it == 2;  // steady-state tile of the timeline
+        if constexpr (RU) {
         // EPI_RUW: the operand lives in the transpose patches -- every warp must be through the previous tile's phase 2
         if constexpr (RUW) asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
-        const bool tr = trace && warp == GEMM_EPI_WARP0 && lane == 0 && it == 2;  // steady-state tile of the timeline
         if (tr) trace[8] = clock64();
         mbar_wait(&tfull_bar[as], acc_phase);
         tc_fence_after();
@@ -620,25 +624,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&a2_ready_bar[as]);
         if (tr) trace[10] = clock64();
+        }  // RU: phase 1
         // ---- phase 2: second accumulator + bias + x -> the fp32 stream, Snake of the next unit -> bf16. Same arithmetic, in
         // the same order, as the generic epilogue (the two-launch form is bit-identical), but nothing else: the generic
         // code re-tests its options per row and was ~1 000 instructions per 32 x 32 chunk and warp -- with two epilogue warps
         // per scheduler (one instruction per ~4.5 cycles) phase 2 alone took 5.5 us of an 8.2 us tile
         // (profiles/r02_dac_ru_timeline.txt). Chunks of RU_W columns go through the warp's transpose patch as before.
-        mbar_wait(&t2full_bar[as], acc_phase);
+        mbar_wait(RU ? &t2full_bar[as] : &tfull_bar[as], acc_phase);
         tc_fence_after();
         if (trace && warp == GEMM_EPI_WARP0 && lane == 0) {
           trace[5] = clock64();
           if (it == 2) trace[11] = trace[5];
         }
+        const int cmod = p.col_mod > 0 ? p.col_mod : p.N;  // EPI_CONV: multiple of 32, so a piece never wraps
 #pragma unroll 1
         for (int pc = 0; pc < RU_NPC; ++pc) {
           float v[RU_W];
           if constexpr (RU_W == 32) tc_ld_32x32(tbase + half * (BN / 2) + pc * RU_W, v);
           else tc_ld_32x16(tbase + half * (BN / 2) + pc * RU_W, v);
           load_resid(pc + 1, rnext);
-          const uint32_t ta = tab + (3 * BN + colw + pc * RU_W) * 4;
-          const float4 b4 = lds_f4(ta), a4 = lds_f4(ta + BN * 4), i4 = lds_f4(ta + 2 * BN * 4);
+          float4 b4, a4, i4;
+          if constexpr (RU) {
+            const uint32_t ta = tab + (3 * BN + colw + pc * RU_W) * 4;
+            b4 = lds_f4(ta), a4 = lds_f4(ta + BN * 4), i4 = lds_f4(ta + 2 * BN * 4);
+          } else {
+            const int cb = (n0 + half * (BN / 2) + pc * RU_W) % cmod + 4 * c4;  // one modulo per piece
+            b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + cb));
+            if (p.alpha_inv) i4 = __ldg(reinterpret_cast<const float4*>(p.alpha_inv + cb));
+            else i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
+          }
           tc_wait_ld();
           if constexpr (RU_W == 32) {
 #pragma unroll
@@ -660,9 +675,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < NIT; ++i) {
             const float4 t = tt[i];
             if (all_rows || sub + RPI * i < rows_left) {
-              float2 t0 = f2add(f2add(make_float2(t.x, t.y), make_float2(b4.x, b4.y)), make_float2(rcur[i].x, rcur[i].y));
-              float2 t1 = f2add(f2add(make_float2(t.z, t.w), make_float2(b4.z, b4.w)), make_float2(rcur[i].z, rcur[i].w));
-              *reinterpret_cast<float4*>(xo) = make_float4(t0.x, t0.y, t1.x, t1.y);
+              float2 t0 = f2add(make_float2(t.x, t.y), make_float2(b4.x, b4.y));
+              float2 t1 = f2add(make_float2(t.z, t.w), make_float2(b4.z, b4.w));
+              if (has_resid) {
+                t0 = f2add(t0, make_float2(rcur[i].x, rcur[i].y));
+                t1 = f2add(t1, make_float2(rcur[i].z, rcur[i].w));
+              }
+              if (has_f32) *reinterpret_cast<float4*>(xo) = make_float4(t0.x, t0.y, t1.x, t1.y);
               t0 = snake2(t0, make_float2(a4.x, a4.y), make_float2(i4.x, i4.y));
               t1 = snake2(t1, make_float2(a4.z, a4.w), make_float2(i4.z, i4.w));
               *reinterpret_cast<uint2*>(no) = make_uint2(pack_bf16(t0.x, t0.y), pack_bf16(t1.x, t1.y));

@@ -443,3 +443,44 @@ def test_fused_residual_unit(ops, C, T, dil):
     nr = xr + torch.sin(alo * xr) ** 2 / (alo + 1e-9)
     assert rel_l2(x1, xr) < 3e-3 and rel_l2(nxt1, nr) < 4e-3
     assert torch.equal(x1, x2) and torch.equal(nxt1, nxt2)
+
+
+@pytest.mark.parametrize("T,K,N,taps,cmod,resid,f32", [
+    (1000, 96, 96, 7, 0, False, False),        # RU conv7 form, 96 channels (16-column pieces, BK = 32 atoms)
+    (128 * 148 + 70, 96, 96, 1, 0, True, True),  # RU conv1 form: + stream -> fp32, Snake -> bf16; two tiles on some CTAs
+    (3000, 192, 192, 2, 96, False, True),      # polyphase transposed conv: N = stride x C_out, constants indexed col % C_out
+    (700, 384, 768, 2, 192, False, True),      # 256-wide CTA-pair tiles
+    (2100, 384, 384, 1, 0, True, True),        # 192-wide tiles, two column tiles
+    (5, 192, 192, 7, 0, False, False),         # a single ragged tile
+])
+def test_lean_conv_epilogue_equals_generic(ops, T, K, N, taps, cmod, resid, f32):
+    """gemm_launch routes the DAC convs (bias, optional fp32 stream in / out, Snake -> bf16) to a lean epilogue
+    (EPI_CONV, csrc/gemm_tc.cuh). Same arithmetic in the same order as the generic epilogue: bit-identical. The generic
+    path is forced here with a LayerScale gate of ones (t * 1.0 changes nothing), and both are checked against fp32 torch
+    (Snake: autoencoder.py:96-102, causal conv: autoencoder.py:285-289)."""
+    from echo_tts_b200._lib import ACT_SNAKE
+    a = _rand((T, K), 171)
+    w = _rand((N, taps * K), 172, scale=(taps * K) ** -0.5)
+    cm = cmod or N
+    bias = _rand((cm,), 173, dtype=torch.float32) * 0.1
+    alpha = torch.exp(0.3 * _rand((cm,), 174, dtype=torch.float32))
+    x = _rand((T, N), 175, dtype=torch.float32)
+    shifts = [-(taps - 1 - j) * 3 for j in range(taps)]
+    outs = []
+    for gate in (None, torch.ones(cm, device="cuda")):
+        xs = x.clone() if (resid or f32) else None
+        o16 = torch.empty(T, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, w, taps=taps, tap_shift=shifts, bias=bias, gate=gate, resid=xs if resid else None,
+                 out_f32=xs if f32 else None, out_bf16=o16, act=ACT_SNAKE, alpha=alpha, col_mod=cmod)
+        outs.append((xs, o16))
+    af = torch.nn.functional.pad(a.float(), (0, 0, 3 * (taps - 1), 0))
+    y = sum(af[3 * j: 3 * j + T] @ w.float()[:, j * K:(j + 1) * K].T for j in range(taps)) + bias.repeat(N // cm)
+    if resid:
+        y = y + x
+    al = alpha.repeat(N // cm)
+    ref16 = y + torch.sin(al * y) ** 2 / (al + 1e-9)
+    assert rel_l2(outs[0][1], ref16) < 4e-3
+    if f32:
+        assert rel_l2(outs[0][0], y) < 3e-3
+        assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])

@@ -1,3 +1,5 @@
 set -u
-timeout 900 python -m pytest tests/test_dac_gpu.py tests/test_dac_encode_gpu.py -m gpu -q -x 2>&1 | tail -3
-timeout 600 python tools/phase_times.py 2>&1 | tail -12
+for i in 1 2; do
+timeout 600 python tools/phase_times.py 2>&1 | grep ae_decode
+ECHO_CONV_EPILOGUE=0 timeout 600 python tools/phase_times.py 2>&1 | grep ae_decode
+done
