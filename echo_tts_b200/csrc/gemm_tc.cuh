@@ -573,7 +573,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bt2 += q;
           }
           const int rown = mt2 * GEMM_BM + quarter * 32 + lane;
-          if (RU && u2 < num_tiles && rown < p.M) {
+          if (RU && u2 < num_tiles && p.ld_f32 == BN && (mt2 + 1) * GEMM_BM <= p.M) {
+            // contiguous rows: ONE bulk prefetch of the warp's 32 x BN slab (a per-lane prefetch.global.L2 is a wavefront of
+            // the L1 data pipe per lane and line -- 768 per tile, on the pipe that bounds this epilogue)
+            if (half == 0 && lane == 0) {
+              const float* q = p.resid + ((size_t)bt2 * p.M + mt2 * GEMM_BM + quarter * 32) * BN;
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "n"(32 * BN * 4) : "memory");
+            }
+          } else if (RU && u2 < num_tiles && rown < p.M) {
             const char* q = reinterpret_cast<const char*>(p.resid + ((size_t)bt2 * p.M + rown) * p.ld_f32 + half * (BN / 2));
 #pragma unroll
             for (int o = 0; o < BN * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));

@@ -1,5 +1,8 @@
 set -u
-for i in 1 2; do
-timeout 600 python tools/phase_times.py 2>&1 | grep ae_decode
-ECHO_CONV_EPILOGUE=0 timeout 600 python tools/phase_times.py 2>&1 | grep ae_decode
+for rep in 1 2; do
+for lib in echo_tts_b200/libecho_b200_base.so echo_tts_b200/libecho_b200.so; do
+echo "== $lib"
+ECHO_B200_LIB=$PWD/$lib timeout 600 python tools/bench_dac_ru.py 2>&1 | grep -E "dilation 3"
 done
+done
+timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q -x -k "fused_residual" 2>&1 | tail -2
