@@ -356,16 +356,34 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       if (trace && threadIdx.x == 64 && j == 5) trace[29] = clock64();
       const float muse = (m_used == -INFINITY) ? 0.f : m_used;
       // ---- P = exp2(s * scale*log2e - m) as bf16 pairs, stored over the first 32 columns of this row's S_j
-      float lsum = 0.f;
+      // The softmax warps run one per scheduler, so this loop is bound by its instruction count: the scale / subtract and
+      // the row sum run on fp32 PAIRS (FFMA2 / FADD2: 32 + 32 instead of 64 + 64 issue slots per tile), and the kv_scale
+      // multiply only exists for a scaled segment (warp-uniform).
       float pk[32];
+      {
+        const float2 s2 = make_float2(sl2t, sl2t), nm2 = make_float2(-muse, -muse);
+        float2 ls2 = make_float2(0.f, 0.f);
+        if (kvs == 1.f) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float p0 = fast_exp2(fmaf(v[2 * c], sl2t, -muse));  // -inf -> 0
-        const float p1 = fast_exp2(fmaf(v[2 * c + 1], sl2t, -muse));
-        lsum += p0 + p1;
-        pk[c] = __uint_as_float(pack_bf16(p0 * kvs, p1 * kvs));
+          for (int c = 0; c < 32; ++c) {
+            const float2 a = f2fma(make_float2(v[2 * c], v[2 * c + 1]), s2, nm2);
+            const float2 pp = make_float2(fast_exp2(a.x), fast_exp2(a.y));  // -inf -> 0
+            ls2 = f2add(ls2, pp);
+            pk[c] = __uint_as_float(pack_bf16(pp.x, pp.y));
+          }
+        } else {
+          const float2 k2 = make_float2(kvs, kvs);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float2 a = f2fma(make_float2(v[2 * c], v[2 * c + 1]), s2, nm2);
+            float2 pp = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+            ls2 = f2add(ls2, pp);
+            pp = f2mul(pp, k2);
+            pk[c] = __uint_as_float(pack_bf16(pp.x, pp.y));
+          }
+        }
+        l_run += ls2.x + ls2.y;
       }
-      l_run += lsum;
       if (trace && threadIdx.x == 64 && j == 5) trace[61] = clock64();
       tc_st_32x32(tmem_base + lane_base + st * TK, pk);
       tc_wait_st();
