@@ -53,6 +53,16 @@ def tokens(prompt, max_length=768):
     return ids, mask
 
 
+def mask_to(mask_h, device):
+    """Text mask -> device, with the length of its longest unmasked prefix (host metadata of the prompt) left on the tensor:
+    the samplers then skip the text rows behind it (echo_sampler_args::text_valid_len), which are masked out of every
+    attention. A mask built by pipeline.get_text_input_ids_and_mask carries the same number."""
+    m = mask_h.to(device)
+    cols = mask_h.reshape(-1, mask_h.shape[-1]).any(0).nonzero()
+    m._echo_valid_len = int(cols.max()) + 1 if cols.numel() else 1
+    return m
+
+
 def request_flops(n_text_valid: int, n_spk_patches: int):
     """Algorithmic FLOPs of one request: 2MNK for the DiT linears, 4*S*keys*D per layer for attention
     over UNMASKED keys, DAC decode 4.34 TFLOP measured by the survey."""
@@ -300,7 +310,7 @@ def run_extras(args, model, dac, pca, device, rank, world, barrier):
             b = len(c)
             nz = torch.randn(b, 640, 80, device=device, generator=torch.Generator(device).manual_seed(c[0]))
             lat = sample(model, spk1.repeat(b, 1, 1), smask1.repeat(b, 1), ids_h.repeat(b, 1).to(device),
-                         mask_h.repeat(b, 1).to(device), 0, sequence_length=640, noise=nz, **KNOBS)
+                         mask_to(mask_h.repeat(b, 1), device), 0, sequence_length=640, noise=nz, **KNOBS)
             ae_decode(dac, pca, lat)
 
     run_calls()  # warm-up (workspaces grow to the batch-4 sizes)
@@ -365,7 +375,7 @@ def run_extras(args, model, dac, pca, device, rank, world, barrier):
         def batch4():
             nz = torch.randn(4, 640, 80, device=device, generator=torch.Generator(device).manual_seed(7))
             lat = sample(model, spk1.repeat(4, 1, 1), smask1.repeat(4, 1), ids_h.repeat(4, 1).to(device),
-                         mask_h.repeat(4, 1).to(device), 0, sequence_length=640, noise=nz, **KNOBS)
+                         mask_to(mask_h.repeat(4, 1), device), 0, sequence_length=640, noise=nz, **KNOBS)
             return ae_decode(dac, pca, lat)
 
         batch4()
@@ -382,7 +392,7 @@ def run_extras(args, model, dac, pca, device, rank, world, barrier):
         spk5 = torch.randn(1, 6400, 80, generator=torch.Generator().manual_seed(1)).to(device)
         smask5 = torch.ones(1, 6400, dtype=torch.bool, device=device)
         knobs5 = dict(KNOBS, speaker_kv_scale=1.5, speaker_kv_min_t=0.9, speaker_kv_max_layers=24)
-        ids, mask = ids_h.to(device), mask_h.to(device)
+        ids, mask = ids_h.to(device), mask_to(mask_h, device)
         runs = []
         for it in range(4):
             torch.cuda.synchronize(device)
@@ -436,7 +446,8 @@ def run_b200(args):
     smask_h = torch.ones(Bq, 212, dtype=torch.bool)
     n_req = args.warmup + args.steps + 1
     noise_h = torch.randn(n_req, Bq, 640, 80, generator=torch.Generator().manual_seed(1000 + rank))
-    ids, mask, spk, smask, noise = (t.to(device) for t in (ids_h, mask_h, spk_h, smask_h, noise_h))
+    ids, spk, smask, noise = (t.to(device) for t in (ids_h, spk_h, smask_h, noise_h))
+    mask = mask_to(mask_h, device)
 
     def request(i):
         lat = sample(model, spk, smask, ids, mask, 0, sequence_length=640, noise=noise[i], **KNOBS)

@@ -49,6 +49,7 @@ class SamplerArgs(C.Structure):
         ("sequence_length", C.c_int), ("round_t_to_bf16", C.c_int),
         ("t_schedule", C.POINTER(C.c_float)),
         ("speaker_K", C.POINTER(C.c_void_p)), ("speaker_V", C.POINTER(C.c_void_p)),
+        ("text_valid_len", C.c_int),
     ]
 
 

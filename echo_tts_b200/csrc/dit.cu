@@ -73,6 +73,9 @@ extern "C" int echo_destroy(echo_handle* h) {
   for (auto& kv : h->ws) if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->dac_raw) if (kv.second.p) cudaFree(kv.second.p);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   while (!h->dac_streams.empty()) echo_dac_stream_destroy(h, *h->dac_streams.begin());
   delete h;
   return ECHO_OK;
@@ -412,7 +415,7 @@ int get_scratch(echo_handle* h, const char* tag, int64_t rows, int64_t W, int64_
 
 // One pre-norm encoder stack (model.py:311-339) over X (B*L rows of width E, fp32, in place).
 int run_encoder(echo_handle* h, const EncoderW& e, const Scratch& sc, int B, int L, const uint8_t* key_mask,
-                const int32_t* eff_len, bool causal, cudaStream_t s) {
+                const int32_t* eff_len, bool causal, cudaStream_t s, int mask_ld = 0 /* row stride of key_mask; 0 = L */) {
   const int rows = B * L, E = e.E;
   const float eps = h->cfg.norm_eps;
   for (int li = 0; li < e.layers; ++li) {
@@ -436,7 +439,7 @@ int run_encoder(echo_handle* h, const EncoderW& e, const Scratch& sc, int B, int
       a.gate = sc.G; a.out = sc.AO; a.b = B; a.S = L; a.H = e.heads; a.D = 128; a.scale = 1.0f / sqrtf(128.f);
       a.nseg = 1;
       a.seg[0].K = sc.K; a.seg[0].V = sc.V; a.seg[0].batch_stride = (int64_t)L * E; a.seg[0].row_stride = E;
-      a.seg[0].len = L; a.seg[0].eff_len = eff_len; a.seg[0].mask = key_mask; a.seg[0].mask_ld = L;
+      a.seg[0].len = L; a.seg[0].eff_len = eff_len; a.seg[0].mask = key_mask; a.seg[0].mask_ld = mask_ld > 0 ? mask_ld : L;
       a.seg[0].mask_stride = 1; a.seg[0].causal = causal ? 1 : 0;
       cudaError_t er = attention_launch(a, s);
       if (er != cudaSuccess) { set_error("encoder attention: %s", cudaGetErrorString(er)); return ECHO_ERR_CUDA; }
@@ -480,10 +483,14 @@ int project_kv(echo_handle* h, const bf16* state, int rows, int E, int which /*0
   return ECHO_OK;
 }
 
-int kv_text_impl(echo_handle* h, const int32_t* ids, const uint8_t* mask, int B, int Lt, void* const* K, void* const* V,
-                 cudaStream_t s) {
+// `Lrun` <= Lt: rows per batch item that are computed and written -- K[i], V[i] are then (B, Lrun, heads, 128). The public
+// entry passes Lt; the samplers pass the length of the longest unmasked prefix when the caller told them
+// (echo_sampler_args::text_valid_len): rows behind it are masked out of every attention that follows.
+int kv_text_impl(echo_handle* h, const int32_t* ids, const uint8_t* mask, int B, int Lt, int Lrun, void* const* K,
+                 void* const* V, cudaStream_t s) {
   const EncoderW& e = h->enc[0];
-  const int rows = B * Lt;
+  if (Lrun <= 0 || Lrun > Lt) Lrun = Lt;
+  const int rows = B * Lrun;
   if (Lt > h->rope_positions) { set_error("text length %d exceeds the RoPE table (%d positions)", Lt, h->rope_positions); return ECHO_ERR_ARG; }
   Scratch sc;
   ECHO_TRY(get_scratch(h, "enc", rows, e.E, e.inter, &sc, s));
@@ -492,14 +499,17 @@ int kv_text_impl(echo_handle* h, const int32_t* ids, const uint8_t* mask, int B,
     eff = (int32_t*)h->wsget("enc.eff", (size_t)B * 4, s);
     mask_eff_len(mask, eff, B, Lt, Lt, 1, s);
   }
-  embed_rows(ids, e.embed, sc.X, rows, e.E, h->cfg.text_vocab_size, s);
-  ECHO_TRY(run_encoder(h, e, sc, B, Lt, mask, eff, false, s));
+  if (Lrun == Lt) embed_rows(ids, e.embed, sc.X, rows, e.E, h->cfg.text_vocab_size, s);
+  else
+    for (int b = 0; b < B; ++b)
+      embed_rows(ids + (size_t)b * Lt, e.embed, sc.X + (size_t)b * Lrun * e.E, Lrun, e.E, h->cfg.text_vocab_size, s);
+  ECHO_TRY(run_encoder(h, e, sc, B, Lrun, mask, eff, false, s, Lt));
   rmsnorm_affine(sc.X, sc.XN, e.final_norm, nullptr, rows, e.E, 0, 0, h->cfg.norm_eps, s);
-  return project_kv(h, sc.XN, rows, e.E, 0, Lt, K, V, s);
+  return project_kv(h, sc.XN, rows, e.E, 0, Lrun, K, V, s);
 }
 
 int kv_patch_impl(echo_handle* h, int which, const bf16* latent, int B, int L, void* const* K, void* const* V,
-                  cudaStream_t s) {
+                  cudaStream_t s, const char* scratch_tag = "enc") {
   const EncoderW& e = h->enc[which];
   const int ps = h->cfg.speaker_patch_size;
   if (L % ps != 0 || L <= 0) { set_error("latent length %d must be a positive multiple of %d", L, ps); return ECHO_ERR_ARG; }
@@ -509,7 +519,7 @@ int kv_patch_impl(echo_handle* h, int which, const bf16* latent, int B, int L, v
     set_error("latent length %d exceeds the RoPE table (%d positions)", L, h->rope_positions); return ECHO_ERR_ARG;
   }
   Scratch sc;
-  ECHO_TRY(get_scratch(h, "enc", rows, e.E, e.inter, &sc, s));
+  ECHO_TRY(get_scratch(h, scratch_tag, rows, e.E, e.inter, &sc, s));
   {  // x = (in_proj(patches) + b) / 6   (model.py:459-462)
     GemmCall c = plain_gemm(latent, kin, e.in_proj_w, kin, rows, e.E, kin);
     c.p.bias = e.in_proj_b; c.p.scale = 1.0f / 6.0f; c.p.out_f32 = sc.X; c.p.ld_f32 = e.E;
@@ -729,7 +739,7 @@ extern "C" int echo_kv_text(echo_handle* h, const int32_t* ids, const uint8_t* m
   ECHO_TRY(check_ready(h, "echo_kv_text"));
   if (!ids || B <= 0 || Lt <= 0 || !K || !V) { set_error("echo_kv_text: bad argument"); return ECHO_ERR_ARG; }
   HandleScope scope(h, static_cast<cudaStream_t>(stream));
-  return kv_text_impl(h, ids, mask, B, Lt, K, V, static_cast<cudaStream_t>(stream));
+  return kv_text_impl(h, ids, mask, B, Lt, Lt, K, V, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int echo_kv_speaker(echo_handle* h, const void* latent, int B, int Ls, void* const* K, void* const* V,
@@ -857,8 +867,46 @@ int sampler_prepare(echo_handle* h, const echo_sampler_args* a, const void* spea
   ECHO_CUDA(cudaMemcpyAsync(t_dev, st->t.data(), (size_t)a->num_steps * 4, cudaMemcpyHostToDevice, s));
   ECHO_TRY(build_mod_tables(h, t_dev, a->num_steps, a->round_t_to_bf16, &st->mod, s));
   // caches, computed once and shared by the CFG branches
-  ECHO_TRY(alloc_kv(h, "smp.kt", B, Lt, &st->kt, s));
-  ECHO_TRY(kv_text_impl(h, text_ids, text_mask, B, Lt, st->kt.K.data(), st->kt.V.data(), s));
+  // text rows behind the longest unmasked prefix are neither encoded nor projected when the caller vouches for it
+  const int Lrun = (a->text_valid_len > 0 && a->text_valid_len < Lt) ? a->text_valid_len : Lt;
+  ECHO_TRY(alloc_kv(h, "smp.kt", B, Lrun, &st->kt, s));
+  // The two caches are independent chains of ~120 small launches each (14 encoder layers + 24 projections): the speaker
+  // cache is built on a side stream forked from `s` here and joined below (events; also valid under stream capture).
+  // ECHO_KV_SIDE_STREAM=0 keeps everything on the caller's stream.
+  static const int env_side = [] { const char* e = std::getenv("ECHO_KV_SIDE_STREAM"); return e ? atoi(e) : 1; }();
+  const bool own_speaker = !(a->speaker_K != nullptr && a->speaker_V != nullptr);
+  cudaStream_t ss = s;
+  if (own_speaker && env_side != 0) {
+    if (!h->side_stream) {
+      if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        h->side_stream = nullptr;
+      }
+    }
+    if (h->side_stream && cudaEventRecord(h->fork_ev, s) == cudaSuccess &&
+        cudaStreamWaitEvent(h->side_stream, h->fork_ev, 0) == cudaSuccess)
+      ss = h->side_stream;
+    else
+      cudaGetLastError();
+  }
+  if (own_speaker) {
+    ECHO_TRY(alloc_kv(h, "smp.ks", B, st->Ps, &st->ks, ss));
+    const int rc = kv_patch_impl(h, 1, static_cast<const bf16*>(speaker_latent), B, Ls, st->ks.K.data(), st->ks.V.data(), ss,
+                                 ss != s ? "encs" : "enc");
+    // the text cache goes onto the caller's stream next to it; the join comes before any error return, so that the
+    // caller's stream never outruns the side stream
+    const int rt = kv_text_impl(h, text_ids, text_mask, B, Lt, Lrun, st->kt.K.data(), st->kt.V.data(), s);
+    if (ss != s) {
+      cudaEventRecord(h->join_ev, ss);
+      cudaStreamWaitEvent(s, h->join_ev, 0);
+    }
+    ECHO_TRY(rc);
+    ECHO_TRY(rt);
+  } else {
+    ECHO_TRY(kv_text_impl(h, text_ids, text_mask, B, Lt, Lrun, st->kt.K.data(), st->kt.V.data(), s));
+  }
   if (a->speaker_K != nullptr && a->speaker_V != nullptr) {
     // per-voice persistence: the caller kept the cache echo_kv_speaker built for this speaker_latent. It is only read
     // (speaker_kv_scale is applied inside the attention kernel, never to the cache).
@@ -868,9 +916,6 @@ int sampler_prepare(echo_handle* h, const echo_sampler_args* a, const void* spea
     st->ks.K.assign(a->speaker_K, a->speaker_K + L);
     st->ks.V.assign(a->speaker_V, a->speaker_V + L);
     st->ks.len = st->Ps;
-  } else {
-    ECHO_TRY(alloc_kv(h, "smp.ks", B, st->Ps, &st->ks, s));
-    ECHO_TRY(kv_patch_impl(h, 1, static_cast<const bf16*>(speaker_latent), B, Ls, st->ks.K.data(), st->ks.V.data(), s));
   }
   // eff_len per row-batch: text [m, 0, m], speaker [m, m, 0]   (inference.py:474-475)
   st->eff3 = (int32_t*)h->wsget("smp.eff", (size_t)6 * B * 4, s);
@@ -916,7 +961,7 @@ int euler_loop(echo_handle* h, const echo_sampler_args* a, SamplerState* st, flo
     FwdCtx f;
     f.nb = nbr * B; f.S = S; f.start_pos = start_pos; f.mod = st->mod; f.mod_n = a->num_steps; f.mod_j = i;
     f.rows_per_group = 0;
-    f.text.K = st->kt.K.data(); f.text.V = st->kt.V.data(); f.text.len = st->Lt; f.text.batch_mod = B;
+    f.text.K = st->kt.K.data(); f.text.V = st->kt.V.data(); f.text.len = st->kt.len; f.text.batch_mod = B;
     f.text.mask = st->text_mask; f.text.mask_ld = st->Lt; f.text.mask_stride = 1; f.text.eff = st->eff3;
     f.spk.K = st->ks.K.data(); f.spk.V = st->ks.V.data(); f.spk.len = st->Ps; f.spk.batch_mod = B;
     f.spk.mask = st->speaker_mask; f.spk.mask_ld = st->Ls; f.spk.mask_stride = c.speaker_patch_size;
@@ -1063,7 +1108,16 @@ extern "C" int echo_sample_euler_host(echo_handle* h, const echo_sampler_args* a
   ECHO_CUDA(cudaMemcpyAsync(d_tm, tmask_host, (size_t)B * Lt, cudaMemcpyHostToDevice, s));
   ECHO_CUDA(cudaMemcpyAsync(d_noise, noise_host, n_x * 4, cudaMemcpyHostToDevice, s));
   cast_f32_to_bf16(d_spk, d_spk16, (int64_t)n_spk, s);
-  ECHO_TRY(echo_sample_euler(h, a, d_spk16, d_sm, Ls, d_ids, d_tm, Lt, B, d_noise, d_x, s));
+  // the mask is in host memory here: the length of the longest unmasked prefix costs a scan of B x Lt bytes
+  echo_sampler_args aa = *a;
+  if (aa.text_valid_len <= 0) {
+    int last = 0;
+    for (int b = 0; b < B; ++b)
+      for (int j = Lt - 1; j >= last; --j)
+        if (tmask_host[(size_t)b * Lt + j]) { last = j + 1; break; }
+    aa.text_valid_len = last > 0 ? last : 1;
+  }
+  ECHO_TRY(echo_sample_euler(h, &aa, d_spk16, d_sm, Ls, d_ids, d_tm, Lt, B, d_noise, d_x, s));
   ECHO_CUDA(cudaMemcpyAsync(x_out_host, d_x, n_x * 4, cudaMemcpyDeviceToHost, s));
   ECHO_CUDA(cudaStreamSynchronize(s));
   return ECHO_OK;

@@ -155,6 +155,10 @@ struct echo_handle {
   bool used = false;
   cudaStream_t last_stream = nullptr;
   cudaEvent_t order_ev = nullptr;
+  // side stream of the samplers: the speaker KV cache is built next to the text KV cache (both are a hundred small,
+  // latency-bound launches), forked from and joined back into the caller's stream with events
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 
   void* wsget(const char* name, size_t bytes, cudaStream_t s);
   void* dalloc(size_t bytes);

@@ -58,8 +58,12 @@ def get_text_input_ids_and_mask(text_arr: List[str], max_length: Optional[int], 
         n = min(len(e), max_length)
         tokens[i, :n] = e[:n]
         mask[i, :n] = True
+    valid = max((min(len(e), max_length) for e, _ in enc), default=0)
     if device is not None:
         tokens, mask = tokens.to(device), mask.to(device)
+    # the samplers of this package skip the text rows behind the longest unmasked prefix when they know it without a
+    # device round trip (sampler._text_valid_len); a copy / slice of the tensor loses the attribute, which is the safe side
+    mask._echo_valid_len = valid
     if return_normalized_text:
         return tokens, mask, [t for _, t in enc]
     return tokens, mask

@@ -20,6 +20,9 @@ from . import _lib
 from .model import B200EchoDiT, _stream, _u8
 
 
+_SCHEDULES: dict = {}
+
+
 def _args(model: B200EchoDiT, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor,
           rescale_k, rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, sequence_length):
     a = _lib.SamplerArgs()
@@ -41,8 +44,12 @@ def _args(model: B200EchoDiT, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_
     a.sequence_length = int(sequence_length)
     a.round_t_to_bf16 = int(model.round_t_to_model_dtype)
     # the schedule is computed by torch on the model's device, exactly as the reference does (inference.py:459)
-    INIT_SCALE = 0.999
-    sched = (torch.linspace(1., 0., a.num_steps + 1, device=model.device) * INIT_SCALE).cpu().contiguous()
+    key = (a.num_steps, str(model.device))
+    sched = _SCHEDULES.get(key)
+    if sched is None:  # one device round trip per (num_steps, device), not per request
+        INIT_SCALE = 0.999
+        sched = (torch.linspace(1., 0., a.num_steps + 1, device=model.device) * INIT_SCALE).cpu().contiguous()
+        _SCHEDULES[key] = sched
     a._sched_keepalive = sched
     a.t_schedule = C.cast(sched.data_ptr(), C.POINTER(C.c_float))
     return a
@@ -65,6 +72,20 @@ def _attach_speaker_kv(a, model: B200EchoDiT, speaker_kv_cache, B: int, Ls: int)
         Ks[i], Vs[i] = k.data_ptr(), v.data_ptr()
     a._kv_keepalive = (Ks, Vs, speaker_kv_cache)
     a.speaker_K, a.speaker_V = C.cast(Ks, C.POINTER(C.c_void_p)), C.cast(Vs, C.POINTER(C.c_void_p))
+
+
+def _text_valid_len(text_mask: torch.Tensor) -> int:
+    """Length of the longest unmasked text prefix over the batch, when it is known WITHOUT a device round trip: the mask is
+    still in host memory, or `pipeline.get_text_input_ids_and_mask` built it and left the number on the tensor. 0 = not
+    known (the text encoder then runs over all padded rows, as the reference does). The samplers skip the text rows behind
+    it: they are masked out of every attention (echo_sampler_args::text_valid_len)."""
+    n = getattr(text_mask, "_echo_valid_len", None)
+    if n is not None:
+        return max(int(n), 1)
+    if text_mask.device.type == "cpu" and text_mask.numel() > 0:
+        cols = text_mask.reshape(-1, text_mask.shape[-1]).any(0).nonzero()
+        return int(cols.max()) + 1 if cols.numel() else 1
+    return 0
 
 
 def _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask):
@@ -114,6 +135,7 @@ def sample_euler_cfg_independent_guidances(
     assert noise.shape == (B, sequence_length, C_lat)
     a = _args(model, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor, rescale_k,
               rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, sequence_length)
+    a.text_valid_len = _text_valid_len(text_mask)
     spk, sm, ids, tm = _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask)
     if speaker_kv_cache is not None:
         _attach_speaker_kv(a, model, speaker_kv_cache, B, sm.shape[1])
@@ -169,6 +191,7 @@ def sample_blockwise_euler_cfg_independent_guidances(
     total = Lc + sum(block_sizes)
     a = _args(model, num_steps, cfg_scale_text, cfg_scale_speaker, cfg_min_t, cfg_max_t, truncation_factor, rescale_k,
               rescale_sigma, speaker_kv_scale, speaker_kv_max_layers, speaker_kv_min_t, max(block_sizes))
+    a.text_valid_len = _text_valid_len(text_mask)
     spk, sm, ids, tm = _inputs(model, speaker_latent, speaker_mask, text_input_ids, text_mask)
     if speaker_kv_cache is not None:  # same extension as in sample_euler_cfg_independent_guidances
         _attach_speaker_kv(a, model, speaker_kv_cache, B, sm.shape[1])

@@ -109,6 +109,12 @@ typedef struct echo_sampler_args {
      (the reference scales its per-call cache in place, inference.py:467-468, 511-513). */
   void* const* speaker_K;
   void* const* speaker_V;
+  /* Optional hint, 0 = unknown: every text_mask entry at index >= text_valid_len is 0 in every batch row (the masks
+     get_text_input_ids_and_mask builds are such prefixes, inference.py:192-215). The samplers then run the text encoder
+     and the 24 K/V projections over the first text_valid_len rows only -- the rows behind it are masked out of every
+     attention, in the reference too (model.py:606-613 computes them and never uses them). The host entry derives it
+     from the mask it is given. */
+  int text_valid_len;
 } echo_sampler_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

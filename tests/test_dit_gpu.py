@@ -192,6 +192,34 @@ def test_sample_euler_host_entry_is_bit_equal_to_the_device_entry(tiny):
     assert rel_l2(out_h, g["eu_latent"]) < LATENT_TOL
 
 
+def test_sampler_skips_masked_text_rows_without_changing_the_result(tiny):
+    """When the sampler knows the longest unmasked text prefix without a device round trip (mask still on the host, or
+    built by pipeline.get_text_input_ids_and_mask), it encodes and projects only those text rows
+    (echo_sampler_args::text_valid_len); with a device mask it runs all padded rows like the reference
+    (model.py:606-613). The rows behind the prefix are masked out of every attention, so both must agree bit for bit."""
+    import echo_tts_b200
+    from echo_tts_b200.sampler import _text_valid_len, sample_euler_cfg_independent_guidances as sample
+    cfg, sd, model, g = tiny
+    S = int(g["eu_S"])
+    noise = torch.randn((2, S, 80), generator=torch.Generator().manual_seed(int(g["eu_seed"])))
+    spk, smask, ids, tmask = g["kv_spk"], g["eu_smask"], g["kv_ids"], g["kv_tmask"]
+    # pad the text to twice its length so that there is a masked tail whatever the golden's mask looks like
+    Lt = tmask.shape[1]
+    ids2 = torch.cat([ids, torch.zeros_like(ids)], 1)
+    tm2 = torch.cat([tmask, torch.zeros_like(tmask)], 1)
+    n = _text_valid_len(tm2)
+    assert 0 < n <= Lt and not bool(tm2[:, n:].any()) and bool(tm2[:, n - 1].any())
+    assert _text_valid_len(tm2.cuda()) == 0  # a device mask: not known without a round trip
+    try:
+        echo_tts_b200.set_deterministic(True)
+        short = sample(model, spk, smask, ids2, tm2, 0, sequence_length=S, noise=noise, **EULER_KNOBS)
+        full = sample(model, spk, smask, ids2.cuda(), tm2.cuda(), 0, sequence_length=S, noise=noise, **EULER_KNOBS)
+    finally:
+        echo_tts_b200.set_deterministic(False)
+    assert torch.equal(short, full)
+    assert rel_l2(short.cpu(), g["eu_latent"]) < LATENT_TOL  # zero-padding the text changes nothing either
+
+
 def test_speaker_kv_max_layers_zero_scales_no_layer(tiny):
     """reference `_multiply_kv_cache(cache, s, max_layers)` scales min(max_layers, L) layers: None = all, 0 = none
     (inference.py:408-414). With 0 layers the scaling knobs must change nothing."""

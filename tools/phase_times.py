@@ -16,7 +16,7 @@ model, dac, pca = bench.load_models(dev, 0, 1)
 ids_h, mask_h = bench.tokens(bench.PROMPT)
 spk = torch.randn(1, 212, 80, generator=torch.Generator().manual_seed(1)).to(dev)
 smask = torch.ones(1, 212, dtype=torch.bool, device=dev)
-ids, mask = ids_h.to(dev), mask_h.to(dev)
+ids, mask = ids_h.to(dev), bench.mask_to(mask_h, dev)
 noise = torch.randn(1, 640, 80, generator=torch.Generator().manual_seed(5)).to(dev)
 
 
