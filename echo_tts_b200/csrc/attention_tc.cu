@@ -44,14 +44,17 @@ namespace {
 
 constexpr int TQ = 128;  // query rows per CTA
 constexpr int TK = 64;   // keys per tile
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 192;      // WG = 1: producer warp, MMA warp, one softmax warpgroup
+constexpr int AT_THREADS_WG2 = 320;  // WG = 2: two softmax warpgroups, 64 keys of every 128-key tile each (one CTA per SM)
 constexpr int AT_MAX_TILES = 120;
 // per head dim D: Q = D/64 atoms [128 rows][64 d]; a K / V tile = D/64 atoms (boxes) [64 keys][64 d]
 __host__ __device__ constexpr int at_q_bytes(int D) { return TQ * D * 2; }
-__host__ __device__ constexpr int at_slot(int D) { return TK * D * 2; }
-__host__ __device__ constexpr int at_tile_bytes(int D) { return at_q_bytes(D) + 4 * at_slot(D); }  // 96 KB (D = 128) / 48 KB
-__host__ __device__ constexpr int at_smem(int D) {
-  return at_tile_bytes(D) + 1024 /*align slack*/ + 1024 /*barriers + tile list*/ + 1024 /*split-KV: (max, sum) per row*/;
+__host__ __device__ constexpr int at_tile_keys(int WG) { return TK * WG; }  // keys per tile of the list: 64, or 128 with two warpgroups
+__host__ __device__ constexpr int at_slot(int D, int WG = 1) { return at_tile_keys(WG) * D * 2; }
+__host__ __device__ constexpr int at_tile_bytes(int D, int WG = 1) { return at_q_bytes(D) + 4 * at_slot(D, WG); }  // 96 KB (D = 128) / 48 KB; WG = 2: 160 KB
+__host__ __device__ constexpr int at_smem(int D, int WG = 1) {
+  // WG = 2 (160 KB of tiles): a second (max, sum) table; two CTAs never share an SM (each takes all of TMEM)
+  return at_tile_bytes(D, WG) + 1024 /*align slack*/ + 1024 /*barriers + tile list*/ + 1024 * WG /*(max, sum) per row: split-KV / warpgroups*/;
 }
 constexpr float RESCALE_LOG2 = 8.f;  // O is rescaled only when a row max grows by more than 2^8
 
@@ -71,13 +74,23 @@ struct SmemCtl {
 };
 static_assert(sizeof(SmemCtl) <= 1024, "control block");
 
-template <int D>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// WG = 2 (few CTAs, one per SM: the b = 1 steps of a request): key tiles of 128 and TWO softmax warpgroups. S = Q K^T is
+// one M128 N128 MMA chain per tile (a K = 16 MMA costs the tensor pipe ~76 cycles whether N is 64 or 128 -- with 64-key
+// tiles the pipe, not the softmax, was the period: profiles/r02_attn_two_warpgroups.txt); warpgroup g takes keys
+// [64 g, 64 g + 64) of every tile, keeps its own running (max, sum) and its own O accumulator in TMEM (columns [256, 384)
+// and [384, 512)) fed by its own P_g V_g MMAs, and the two partial results are merged in the epilogue like two split-KV
+// shares, but inside the CTA (no cluster barrier, no DSMEM).
+template <int D, int WG>
+__global__ void __launch_bounds__(WG == 2 ? AT_THREADS_WG2 : AT_THREADS, WG == 2 ? 1 : 2)
 attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   static_assert(D == 128 || D == 64, "head dim");
+  static_assert(WG == 1 || (WG == 2 && D == 128), "two warpgroups: head dim 128 only");
+  constexpr int TMEM_COLS = WG == 2 ? 512 : 256;
   constexpr int NA = D / 64;  // 64-column atoms per row
-  constexpr int Q_BYTES = at_q_bytes(D), KSLOT = at_slot(D), VSLOT = at_slot(D), STAGE = KSLOT + VSLOT;
-  constexpr int TILE_BYTES = at_tile_bytes(D);
+  constexpr int TKT = at_tile_keys(WG);  // keys per tile of the list
+  constexpr int Q_BYTES = at_q_bytes(D), KSLOT = at_slot(D, WG), VSLOT = at_slot(D, WG), STAGE = KSLOT + VSLOT;
+  constexpr int TILE_BYTES = at_tile_bytes(D, WG);
+  constexpr uint32_t O_BASE = 2 * TKT;  // TMEM: two score stages of TKT columns, then one O accumulator of D columns per warpgroup
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -105,13 +118,13 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         mbar_init(&ctl->k_full[s], 1);
         mbar_init(&ctl->v_full[s], 1);
         mbar_init(&ctl->s_full[s], 1);
-        mbar_init(&ctl->p_ready[s], 4);
+        mbar_init(&ctl->p_ready[s], 4 * WG);
         mbar_init(&ctl->pv_done[s], 1);
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<256>(&ctl->tmem_slot);
+    tmem_alloc<TMEM_COLS>(&ctl->tmem_slot);
   }
   // ---- tile list, built BEFORE the dependency wait: it reads only the descriptor and eff_len[], which the kernel
   // chain computes once per request (mask_eff_len in sampler_prepare), never in the kernel right before this one.
@@ -139,7 +152,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       if (lo > hi) lo = hi;
       ctl->seg_hi[lane] = hi;
     }
-    const int nt = (hi - lo + TK - 1) / TK;
+    const int nt = (hi - lo + TKT - 1) / TKT;
     int off = nt;  // inclusive prefix sum over the (<= 4) segment lanes
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
@@ -148,7 +161,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     }
     const int total = __shfl_sync(0xffffffffu, off, 3);
     off -= nt;
-    for (int i = 0; i < nt && off + i < AT_MAX_TILES; ++i) ctl->tiles[off + i] = (lane << 24) | (lo + i * TK);
+    for (int i = 0; i < nt && off + i < AT_MAX_TILES; ++i) ctl->tiles[off + i] = (lane << 24) | (lo + i * TKT);
     if (lane == 0) {
       const int all = total < AT_MAX_TILES ? total : AT_MAX_TILES;
       const int t_lo = all * sp / nsplit, t_hi = all * (sp + 1) / nsplit;  // this CTA's share of the key tiles
@@ -182,16 +195,23 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         const int si = e >> 24, n0 = e & 0xFFFFFF;
         const int bm = d.seg[si].batch_mod;
         const int cb = d.seg[si].batch_stride == 0 ? 0 : (bm > 0 ? b % bm : b);  // stride 0: one cache for all rows
+        // a tile is WG boxes of 64 keys per atom: keys [64 g, 64 g + 64) sit 8 KB further down in each atom
         if (!is_v) {
           if (u > 0) mbar_wait(&ctl->s_full[st], (u - 1) & 1);  // S_{j-2} has consumed the slot
           mbar_expect_tx(&ctl->k_full[st], KSLOT);
 #pragma unroll
-          for (int a = 0; a < NA; ++a) tma_load_3d(sK(st) + a * (KSLOT / NA), &maps.k[si], &ctl->k_full[st], h * D + a * 64, n0, cb);
+          for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int g = 0; g < WG; ++g)
+              tma_load_3d(sK(st) + a * (KSLOT / NA) + g * (TK * 128), &maps.k[si], &ctl->k_full[st], h * D + a * 64, n0 + g * TK, cb);
         } else {
           if (u > 0) mbar_wait(&ctl->pv_done[st], (u - 1) & 1);  // PV_{j-2} has consumed the slot
           mbar_expect_tx(&ctl->v_full[st], VSLOT);
 #pragma unroll
-          for (int a = 0; a < NA; ++a) tma_load_3d(sV(st) + a * (VSLOT / NA), &maps.v[si], &ctl->v_full[st], h * D + a * 64, n0, cb);
+          for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int g = 0; g < WG; ++g)
+              tma_load_3d(sV(st) + a * (VSLOT / NA) + g * (TK * 128), &maps.v[si], &ctl->v_full[st], h * D + a * 64, n0 + g * TK, cb);
         }
       };
       // issue order K0 K1 V0 K2 V1 K3 ...: K_{j+2} only waits for S_j, which completes two tiles before S_{j+2} is issued
@@ -209,10 +229,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
     // so the issue path -- not the pipe -- bounds a tile (0.9 us per tile before this was trimmed:
     // profiles/r01_attn_tc_timeline.txt); per tile it is now 12 MMAs, 2 commits and 3 barrier waits.
     if (ntiles > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK);
+      constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TKT);
       constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D) | kIdescBMajorMN;
       const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t t_o = tmem_base + 128;
+      const uint32_t t_o = tmem_base + O_BASE;
       const uint64_t qd0 = make_smem_desc<128>(q_addr), qd1 = make_smem_desc<128>(q_addr + Q_BYTES / NA * (NA - 1));
       mbar_wait(&ctl->q_full, 0);
       if (trace && lane == 0) trace[3] = clock64();
@@ -225,10 +245,10 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         const uint64_t kd0 = make_smem_desc<128>(k_addr), kd1 = make_smem_desc<128>(k_addr + KSLOT / NA * (NA - 1));
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd0 + 2 * k, kd0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TKT, qd0 + 2 * k, kd0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
           if constexpr (NA == 2) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TK, qd1 + 2 * k, kd1 + 2 * k, idesc_s, 1u);
+            for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + st * TKT, qd1 + 2 * k, kd1 + 2 * k, idesc_s, 1u);
           }
           tc_commit(&ctl->s_full[st]);  // scores ready; also releases K_j's smem slot to the producer
         }
@@ -238,19 +258,24 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);  // scores of the next tile run under this tile's softmax
         const int st = j & 1, u = j >> 1;
-        mbar_wait(&ctl->p_ready[st], u & 1);
+        mbar_wait(&ctl->p_ready[st], u & 1);  // every softmax warp (of both warpgroups) has published its P
         mbar_wait(&ctl->v_full[st], u & 1);
         tc_fence_after();
         if (trace && lane == 0 && j < 13) trace[48 + j] = clock64();
-        const uint32_t p_tmem = tmem_base + st * TK;  // bf16 P_j, packed 2 keys per column over S_j's first 32 columns
-        const uint64_t vd = make_smem_desc_mn(smem_u32(sV(st)), VSLOT / NA, 1024);  // LBO = next 64-wide d group (D = 128 only)
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 keys per MMA: A advances 8 TMEM columns, B advances two 8-key atoms (2 KB = 128 x 16 B)
-            tc_mma_f16_ts(t_o, p_tmem + 8 * k, vd + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
+          for (int g = 0; g < WG; ++g) {
+            // warpgroup g: bf16 P of keys [64 g, 64 g + 64), packed 2 keys per column over the first 32 columns of its half of
+            // S_j, times the V rows of those keys (8 KB further down in each atom), into its own accumulator
+            const uint32_t p_tmem = tmem_base + st * TKT + g * TK;
+            const uint64_t vd = make_smem_desc_mn(smem_u32(sV(st)) + g * (TK * 128), VSLOT / NA, 1024);  // LBO = next 64-wide d group (D = 128 only)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // 16 keys per MMA: A advances 8 TMEM columns, B advances two 8-key atoms (2 KB = 128 x 16 B)
+              tc_mma_f16_ts(t_o + g * 128, p_tmem + 8 * k, vd + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
+            }
           }
-          tc_commit(&ctl->pv_done[st]);  // O holds tiles 0..j; also releases V_j's smem slot
+          tc_commit(&ctl->pv_done[st]);  // the accumulators hold tiles 0..j; also releases V_j's smem slot
         }
         __syncwarp();
       }
@@ -258,16 +283,19 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
     const int quarter = warp & 3;
+    const int wg = WG == 2 ? (warp - 2) >> 2 : 0;  // softmax warpgroup: warps 2-5 / 6-9
     const int row = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t o_col = O_BASE + (uint32_t)wg * 128u;  // this warpgroup's O accumulator
+    const uint32_t s_col = (uint32_t)wg * TK;             // its 64 keys inside a score stage
     const float sl2 = d.scale * 1.4426950408889634f;
     float m_used = -INFINITY;  // running max in the log2 domain the exponentials are taken against
     float l_run = 0.f;
     for (int j = 0; j < ntiles; ++j) {
       const int st = j & 1, u = j >> 1;
-      // ---- key validity of this tile as a 64-bit mask (before the scores are ready)
+      // ---- key validity of this warpgroup's 64 keys of the tile as a 64-bit mask (before the scores are ready)
       const int e = lds_i32(&ctl->tiles[t_lo + j]);
-      const int si = e >> 24, n0 = e & 0xFFFFFF;
+      const int si = e >> 24, n0 = (e & 0xFFFFFF) + wg * TK;
       const echo_attn_segment& sg = d.seg[si];
       const int hi = lds_i32(&ctl->seg_hi[si]);
       uint32_t vm_lo, vm_hi;
@@ -286,8 +314,8 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       tc_fence_after();
       if (trace && threadIdx.x == 64 && j < 13) trace[4 + 2 * j] = clock64();
       float v[64];
-      tc_ld_32x32(tmem_base + lane_base + st * TK, v);
-      tc_ld_32x32(tmem_base + lane_base + st * TK + 32, v + 32);
+      tc_ld_32x32(tmem_base + lane_base + st * TKT + s_col, v);
+      tc_ld_32x32(tmem_base + lane_base + st * TKT + s_col + 32, v + 32);
       tc_wait_ld();
       if (trace && threadIdx.x == 64 && j == 5) trace[27] = clock64();
       // causal / window segments: rows of this warp's slab see keys j with q - window < j <= q. Tiles entirely below the
@@ -344,11 +372,11 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
 #pragma unroll 1
           for (int c = 0; c < D / 32; ++c) {
             float o[32];
-            tc_ld_32x32(tmem_base + lane_base + 128 + c * 32, o);
+            tc_ld_32x32(tmem_base + lane_base + o_col + c * 32, o);
             tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] *= corr;
-            tc_st_32x32(tmem_base + lane_base + 128 + c * 32, o);
+            tc_st_32x32(tmem_base + lane_base + o_col + c * 32, o);
           }
           tc_wait_st();
         }
@@ -385,7 +413,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
         l_run += ls2.x + ls2.y;
       }
       if (trace && threadIdx.x == 64 && j == 5) trace[61] = clock64();
-      tc_st_32x32(tmem_base + lane_base + st * TK, pk);
+      tc_st_32x32(tmem_base + lane_base + st * TKT + s_col, pk);
       tc_wait_st();
       if (trace && threadIdx.x == 64 && j == 5) trace[62] = clock64();
       tc_fence_before();
@@ -394,6 +422,82 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       if (trace && threadIdx.x == 64 && j < 13) trace[5 + 2 * j] = clock64();
     }
 
+    if constexpr (WG == 2) {
+      // ---- epilogue of the two-warpgroup form (never split over a cluster): merge the two partial results inside the CTA.
+      // Warpgroup g fed accumulator g from its 64 keys of every tile; thread `row` of BOTH warpgroups owns that query row.
+      constexpr int CPR = D / 8, RPI = 32 / CPR, NIT = 32 / RPI, NH = NIT / 2, ROWB = D * 2;
+      const size_t HD = (size_t)d.H * D;
+      const int rsel = lane / CPR, ch = lane % CPR;
+      const int rbase = wg * (32 / 2);  // rows of the quarter's 32 this warp stores: [16 wg, 16 wg + 16)
+      const size_t off0 = ((size_t)b * d.S + q0 + quarter * 32 + rbase + rsel) * HD + (size_t)h * D + ch * 8;
+      const int rows_ok = d.S - (q0 + quarter * 32);
+      uint4 gv[NH];
+      if (d.gate) {
+#pragma unroll
+        for (int i = 0; i < NH; ++i)
+          if (rbase + RPI * i + rsel < rows_ok)
+            gv[i] = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(d.gate) + off0 + (size_t)(RPI * i) * HD);
+      }
+      const bool have_g = ntiles > 0;  // warp-uniform
+      if (have_g) {
+        mbar_wait(&ctl->pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+        tc_fence_after();
+      }
+      if (trace && threadIdx.x == 64) trace[30] = clock64();
+      const uint32_t ml_mine = smem_u32(smem + TILE_BYTES + 1024 + wg * 1024), ml_other = smem_u32(smem + TILE_BYTES + 1024 + (1 - wg) * 1024);
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ml_mine + row * 8), "f"(have_g ? m_used : -INFINITY), "f"(have_g ? l_run : 0.f) : "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // both warpgroups are through their last PV: K / V stages are dead too
+      float m_ot, l_ot;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_ot), "=f"(l_ot) : "r"(ml_other + row * 8) : "memory");
+      const float l_me = have_g ? l_run : 0.f;
+      float mx = -INFINITY;
+      if (l_me > 0.f) mx = m_used;
+      if (l_ot > 0.f) mx = fmaxf(mx, m_ot);
+      const float w_me = l_me > 0.f ? fast_exp2(m_used - mx) : 0.f, w_ot = l_ot > 0.f ? fast_exp2(m_ot - mx) : 0.f;
+      const float l_tot = fmaf(l_me, w_me, l_ot * w_ot);
+      const float iv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      const float w0 = (wg == 0 ? w_me : w_ot) * iv, w1 = (wg == 0 ? w_ot : w_me) * iv;  // weights of accumulators 0 / 1
+      const bool has0 = ntiles > 0, has1 = ntiles > 0;  // accumulators no tile ever wrote hold stale TMEM: never read
+      const uint32_t stg = smem_u32(smem + Q_BYTES + quarter * (32 * ROWB));  // the quarter's 32 staged rows, shared by its two warps
+      const uint32_t srow = stg + lane * ROWB;
+#pragma unroll 1
+      for (int cc = 0; cc < D / 64; ++cc) {
+        const int c = wg * (D / 64) + cc;  // this warpgroup's half of the head dim, 32 columns at a time
+        float oa[32], ob[32];
+        if (has0) tc_ld_32x32(tmem_base + lane_base + O_BASE + c * 32, oa);
+        if (has1) tc_ld_32x32(tmem_base + lane_base + O_BASE + 128 + c * 32, ob);
+        if (has0 || has1) tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) oa[i] = (has0 ? oa[i] * w0 : 0.f) + (has1 ? ob[i] * w1 : 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int chk = c * 4 + k;  // 16-byte chunk of the row
+          sts_u4(srow + ((chk ^ (lane & 7)) << 4),
+                 make_uint4(pack_bf16(oa[8 * k], oa[8 * k + 1]), pack_bf16(oa[8 * k + 2], oa[8 * k + 3]),
+                            pack_bf16(oa[8 * k + 4], oa[8 * k + 5]), pack_bf16(oa[8 * k + 6], oa[8 * k + 7])));
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // both halves of every row are staged
+#pragma unroll
+      for (int i = 0; i < NH; ++i) {
+        const int r = rbase + RPI * i + rsel;
+        if (r < rows_ok) {
+          uint4 val = lds_u4(stg + r * ROWB + ((ch ^ (r & 7)) << 4));
+          if (d.gate) {
+            const uint32_t* vi = reinterpret_cast<const uint32_t*>(&val);
+            const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gv[i]);
+            uint32_t rr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 a = unpack_bf16(vi[k]), g = unpack_bf16(gi[k]);
+              rr[k] = pack_bf16(a.x * g.x, a.y * g.y);
+            }
+            val = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+          }
+          *reinterpret_cast<uint4*>(static_cast<bf16*>(d.out) + off0 + (size_t)(RPI * i) * HD) = val;
+        }
+      }
+    } else {
     // ---- epilogue: O / l -> bf16 -> (* gate) -> global, staged through smem so rows are written as 256 B runs.
     // The 16 gate vectors this lane needs are requested BEFORE waiting for the last PV (4.3 us of exposed L2 round
     // trips otherwise: the loop below was load -> multiply -> store, one row pair at a time).
@@ -483,6 +587,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
       }
     }
     }  // nsplit == 1
+    }  // WG == 1
   }
 
   if (nsplit > 1) {
@@ -604,7 +709,7 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   if (trace && threadIdx.x == 64) trace[31] = clock64();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem_base);
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 }  // namespace
@@ -630,13 +735,13 @@ static int attention_tile_bound(const echo_attn_desc& d) {
   return tiles;
 }
 
-template <int D>
+template <int D, int WG = 1>
 static cudaError_t attention_tc_launch_d(const echo_attn_desc& d_in, int nsplit, cudaStream_t s) {
   echo_attn_desc d = d_in;
   d.nsplit = nsplit;
   static std::atomic<uint64_t> configured{0};  // per device, see ensure_dyn_smem
   {
-    cudaError_t e = ensure_dyn_smem(configured, attn_tc_kernel<D>, at_smem(D));
+    cudaError_t e = ensure_dyn_smem(configured, attn_tc_kernel<D, WG>, at_smem(D, WG));
     if (e != cudaSuccess) return e;
   }
   AttnMaps maps;
@@ -658,7 +763,7 @@ static cudaError_t attention_tc_launch_d(const echo_attn_desc& d_in, int nsplit,
   cudaError_t err;
   {
     char tag[64];
-    if (prof_enabled()) snprintf(tag, sizeof(tag), "attn_tc D=%d b=%d S=%d H=%d nseg=%d split=%d", D, d.b, d.S, d.H, d.nseg, nsplit);
+    if (prof_enabled()) snprintf(tag, sizeof(tag), "attn_tc D=%d b=%d S=%d H=%d nseg=%d split=%d wg=%d", D, d.b, d.S, d.H, d.nseg, nsplit, WG);
     else tag[0] = 0;
     double keys = 0;  // keys a query can see (upper bound for masked segments)
     for (int i = 0; i < d.nseg; ++i) {
@@ -666,7 +771,7 @@ static cudaError_t attention_tc_launch_d(const echo_attn_desc& d_in, int nsplit,
       keys += g.causal ? (g.window > 0 && g.window < d.S ? (double)g.window : 0.5 * d.S) : (double)g.len;
     }
     ProfScope ps(PROF_ATTN, 4.0 * d.b * d.H * (double)d.S * keys * D, 0.0, s, tag);
-    err = launch_k(attn_tc_kernel<D>, grid, dim3(AT_THREADS), (size_t)at_smem(D), s, nsplit, maps, d);
+    err = launch_k(attn_tc_kernel<D, WG>, grid, dim3(WG == 2 ? AT_THREADS_WG2 : AT_THREADS), (size_t)at_smem(D, WG), s, nsplit, maps, d);
   }
   count_launch();
   return err;
@@ -701,6 +806,17 @@ cudaError_t attention_launch(const echo_attn_desc& d, cudaStream_t s) {
   if (nsplit > 8) nsplit = 8;
   if (nsplit > tiles) nsplit = tiles;
   if (nsplit < 1) nsplit = 1;
+  // 128-key tiles and two softmax warpgroups per CTA (one CTA per SM) instead of a split over a cluster when at most one
+  // CTA per SM is there to begin with and the key list is short enough that the in-CTA form wins (the b = 1 steps of a
+  // 640-latent request: 80 CTAs x ~12 tiles): no cluster barrier, no DSMEM merge. Joint attention only -- the encoders
+  // keep one form whatever their length, so that their rows do not depend on how many padded rows are computed next to
+  // them. nsplit = -2 in the descriptor forces it (tests), ECHO_ATTN_WG2=0 switches it off.
+  static const int env_wg2 = [] { const char* e = std::getenv("ECHO_ATTN_WG2"); return e ? atoi(e) : 1; }();
+  bool wg2_ok = d.D == 128;
+  for (int i = 0; i < d.nseg; ++i) wg2_ok = wg2_ok && !d.seg[i].causal;
+  const bool wg2 = wg2_ok && (d.nsplit == -2 || (d.nsplit == 0 && env_wg2 != 0 && d.nseg >= 2 &&
+                                                 groups <= (size_t)gemm_num_sms() && tiles <= 28));
+  if (wg2) return attention_tc_launch_d<128, 2>(d, 1, s);
   return d.D == 128 ? attention_tc_launch_d<128>(d, nsplit, s) : attention_tc_launch_d<64>(d, nsplit, s);
 }
 

@@ -258,7 +258,10 @@ def test_attention_d64_joint_with_gate_and_mask(ops):
 
 
 @pytest.mark.parametrize("b,S,H,D,L2,nsplit", [(1, 160, 4, 128, 2700, 8), (3, 160, 2, 128, 1100, 3), (1, 640, 4, 128, 100, 0),
-                                               (2, 100, 2, 64, 900, 5), (1, 130, 1, 128, 64, 2), (1, 64, 2, 128, 40, 8)])
+                                               (2, 100, 2, 64, 900, 5), (1, 130, 1, 128, 64, 2), (1, 64, 2, 128, 40, 8),
+                                               # nsplit = -2: two softmax warpgroups per CTA on alternate key tiles, merged in the CTA
+                                               (1, 640, 4, 128, 100, -2), (3, 160, 2, 128, 1100, -2), (1, 130, 1, 128, 64, -2),
+                                               (1, 64, 2, 128, 40, -2), (2, 300, 3, 128, 7, -2)])
 def test_attention_split_kv(ops, b, S, H, D, L2, nsplit):
     """Split-KV: the key tiles of one (query tile, head, batch row) divided over a thread-block cluster of CTAs whose
     partial (O, max, sum) are merged through distributed shared memory. Must match the fp32 reference like the unsplit
@@ -391,7 +394,7 @@ def test_gemm_gate_groups_must_be_multiples_of_32(ops):
         ops.gemm(a, w, gate=gate, rows_per_gate=77, resid=res, out_f32=res)
 
 
-@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("nsplit", [1, 3, -2])
 def test_attention_segment_kv_scale(ops, nsplit):
     """speaker_kv_scale applied inside the kernel (reference: the speaker K and V are multiplied in place,
     inference.py:408-414): a segment with kv_scale = s must behave as if its keys AND values were scaled by s."""

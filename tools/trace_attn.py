@@ -11,6 +11,8 @@ dev = "cuda"
 NS = int(sys.argv[1]) if len(sys.argv) > 1 else 1  # split-KV shares (1 = off)
 for b in (1, 3):
     S, H, Dh = 640, 16, 128
+    if NS == -2 and b == 3:
+        continue  # two softmax warpgroups: one CTA per SM, the b = 1 shape
     q = torch.randn(b, S, H, Dh, device=dev).bfloat16()
     k = torch.randn(b, S, H, Dh, device=dev).bfloat16()
     v = torch.randn(b, S, H, Dh, device=dev).bfloat16()
@@ -21,7 +23,7 @@ for b in (1, 3):
     eff = torch.tensor([36, 0, 36][:b], dtype=torch.int32, device=dev)
     effs = torch.tensor([53, 53, 0][:b], dtype=torch.int32, device=dev)
     segs = [dict(k=k, v=v), dict(k=kt, v=kt, eff_len=eff, batch_mod=1), dict(k=ks, v=ks, eff_len=effs, batch_mod=1)]
-    ncta = 5 * H * b * NS
+    ncta = 5 * H * b * max(NS, 1)
     trace = torch.zeros(ncta * 64, dtype=torch.int64, device=dev)
     for _ in range(3):
         ops.attention(q, segs, out, gate=g, trace=trace, nsplit=NS)
