@@ -24,7 +24,8 @@
 // Head dim 64: Q / K / V tiles are one 64-column atom instead of two, S = QK^T takes 4 MMAs (K = 64) and O is 64 TMEM columns.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax,
-// O correction and epilogue (TMEM lane quarter = warp & 3).
+// O correction and epilogue (TMEM lane quarter = warp & 3). The WG = 2 form (b = 1 joint attention, one CTA per SM, see
+// the kernel) has 128-key tiles and a second softmax warpgroup in warps 6-9.
 #include <cuda.h>
 
 #include <cstdio>
@@ -225,9 +226,11 @@ attn_tc_kernel(const __grid_constant__ AttnMaps maps, const echo_attn_desc d) {
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp runs the (warp-uniform) control flow and one elected lane issues each tcgen05 instruction: the
-    // descriptors then live in uniform registers. With N = 64 an MMA occupies the tensor pipe for only 32 cycles,
-    // so the issue path -- not the pipe -- bounds a tile (0.9 us per tile before this was trimmed:
-    // profiles/r01_attn_tc_timeline.txt); per tile it is now 12 MMAs, 2 commits and 3 barrier waits.
+    // descriptors then live in uniform registers. Per 64-key tile: 12 MMAs, 2 commits and 3 barrier waits (0.9 us per
+    // tile before the issue path was trimmed, profiles/r01_attn_tc_timeline.txt). Round 2 measured what is left: two
+    // back-to-back issues of 8 MMAs are 0.33 us apart whatever they wait for -- a K = 16 MMA occupies the pipe ~76 cycles
+    // at N = 64 (nominal 32) -- so with two CTAs per SM the pipe's ~0.9 us per tile pair IS the period at b = 3
+    // (profiles/r02_attn_two_warpgroups.txt); the WG = 2 form halves the S MMAs per key with N = 128.
     if (ntiles > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TKT);
       constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D) | kIdescBMajorMN;

@@ -298,11 +298,9 @@ cudaError_t gemm_launch(const GemmCall& c, cudaStream_t s) {
   bool ru_window = false;
   if (p.epi == EPI_RU && bn == 96 && p.taps == RUW_TAPS) {
     static const int env_w = [] { const char* e = std::getenv("ECHO_DAC_RU_WINDOW"); return e ? atoi(e) : 1; }();
-    static const int env_mode = [] { const char* e = std::getenv("ECHO_RUW_DESC_MODE"); return e ? atoi(e) : 0; }();
     const int d = p.tap_shift[1] - p.tap_shift[0];
     ru_window = env_w != 0 && d >= 0 && GEMM_BM + (RUW_TAPS - 1) * d <= RUW_WIN_ROWS;
     for (int j = 1; j < RUW_TAPS; ++j) ru_window = ru_window && (p.tap_shift[j] - p.tap_shift[0] == j * d);
-    p.ruw_desc_mode = env_mode;
   }
   CUtensorMap ma, mb;
   if (!get_tensor_map(&ma, c.A, 3, (uint64_t)p.Kc, (uint64_t)(c.a_rows > 0 ? c.a_rows : p.M), (uint64_t)a_batches, (uint64_t)c.lda * 2,

@@ -78,7 +78,6 @@ struct GemmParams {
   const float* ru_bias1;
   const float* ru_alpha_out;
   const float* ru_alpha_out_inv;
-  int ruw_desc_mode;  // EPI_RUW, debug only: how the row-shifted window descriptors encode their start (see gemm_tc.cuh)
   // ---- EPI_QKV with 384-column tiles only, set by gemm_launch: which three 128-column groups (heads) column tile t
   // holds -- groups [3t], [3t+1] feed the N = 256 MMA (one per CTA of the pair, one per epilogue warp half), group [3t+2]
   // the N = 128 MMA (its rows split across the pair, its chunks across the halves). A value >= N / 128 is an empty slot.

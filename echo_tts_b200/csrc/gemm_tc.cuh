@@ -398,14 +398,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
           for (int j = 0; j < RUW_TAPS; ++j) {
             // tap j reads window rows [shift(j) - shift(0), + 128): the descriptor's start address moves down by whole
-            // rows. The swizzle is a function of the shared-memory address bits, which the row shift changes -- the
-            // descriptor's base-offset field (bits 49-51) carries the start's phase inside the swizzle pattern.
+            // 64-byte rows. The swizzle is a function of the absolute shared-memory address bits, so the shifted start needs
+            // nothing else -- setting the descriptor's base-offset field (bits 49-51) to the start's phase inside the 512-byte
+            // pattern gives WRONG results (both forms were run against the seven separate loads on the hardware).
             const uint32_t roff = (uint32_t)(p.tap_shift[j] - p.tap_shift[0]) * ROW_BYTES;
 #pragma unroll
             for (int a = 0; a < ATOMS; ++a) {
               const uint32_t sa = win + a * WIN_ATOM + roff;
-              uint64_t adesc = make_smem_desc<ROW_BYTES>(sa);
-              if (p.ruw_desc_mode == 1) adesc |= (uint64_t)((sa >> 7) & 7) << 49;
+              const uint64_t adesc = make_smem_desc<ROW_BYTES>(sa);
               const uint64_t bdesc = make_smem_desc<ROW_BYTES>(w7 + (j * ATOMS + a) * B_ATOM);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (j | a | k) != 0 ? 1u : 0u);
