@@ -923,10 +923,10 @@ ECHO_CHUNK_UNROLL
             const bool all_rows = rows_left >= 32;  // warp-uniform
             if (p.part_out != nullptr) {
               // split-K without atomics: slice sk parks its gated partial sum in its own plane of a workspace and the
-              // LowRankAdaLN / RMSNorm kernel that follows adds the planes to the residual stream (glue.cu). The L2
-              // executes fp32 reductions element by element: %globaltimer stamps showed the dependent kernel's wait
-              // returning 8 us after the last CTA of a 3-way split wo had issued its reductions, against 1.2 us
-              // behind a kernel with plain stores (tools/trace_boundary.py). Fixed summation order: bit-reproducible.
+              // LowRankAdaLN / RMSNorm kernel that follows adds the planes to the residual stream (glue.cu). Fixed
+              // summation order: bit-reproducible. Not faster than the reductions: with all SMs pushing 128 x 256 tiles,
+              // red.global.add.v4.f32 drains 8 % slower than plain stores, three CTAs per tile or one
+              // (tools/red_drain.cu, profiles/r02_tma_reduce_experiment.txt), and the planes cost the next kernel reads.
               float* dst = p.part_out + (size_t)sk * p.part_stride + (row0 + sub) * (size_t)p.ld_f32 + c0 + 4 * c4;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
