@@ -34,8 +34,9 @@ def run(label, M, fn_factory):
     print(f"{label} M={M}: {t.shape[0]} CTAs, event {e0.elapsed_time(e1)*1e3:.1f} us")
     print("   " + "  ".join(f"{n}={v:.2f}" for n, v in zip(names, med[:8].tolist())))
     print("   tiles (acc ready -> epilogue done): " + "  ".join(
-        f"[{med[8 + 2 * i]:.2f} -> {med[9 + 2 * i]:.2f}]" for i in range(4) if med[8 + 2 * i] == med[8 + 2 * i]))
-    if med[12] == med[12]:
+        f"[{med[8 + 2 * i]:.2f} -> {med[9 + 2 * i]:.2f}]" for i in range(4) if med[9 + 2 * i] == med[9 + 2 * i]))
+    # slot 12 is the producer's wait-return stamp, but a CTA's third tile overwrites it (tile stamps use slots 8 .. 15)
+    if med[12] == med[12] and med[13] != med[13]:
         print(f"   producer: dependency wait returned {med[12]:.2f}, A tiles of the first fill issued {med[2]:.2f}, first stage full {med[3]:.2f}")
     print(f"   slowest CTA exit: {rel[:, 7].max():.2f} us", flush=True)
 
